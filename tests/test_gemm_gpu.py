@@ -1,0 +1,149 @@
+"""GPU parity of the tcgen05 GEMM (vtp_gemm_bf16) against a plain fp32 PyTorch reference of the same op."""
+import math
+
+import pytest
+import torch
+
+from vtp_b200 import lib
+
+pytestmark = pytest.mark.gpu
+
+
+def _mk(shape, seed, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+def _ref(A, B, a_mn, b_mn):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    Af = A.float().t() if a_mn else A.float()
+    Bf = B.float().t() if b_mn else B.float()
+    return Af @ Bf.t()
+
+
+def _relerr(x, y):
+    return ((x.float() - y.float()).norm() / (y.float().norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("a_mn", [False, True])
+@pytest.mark.parametrize("b_mn", [False, True])
+@pytest.mark.parametrize("M,N,K", [(300, 384, 384), (1000, 512, 200), (128, 64, 64), (777, 1152, 384), (513, 5472, 1024)])
+def test_gemm_majors(a_mn, b_mn, M, N, K):
+    A = _mk((K, M) if a_mn else (M, K), 1)
+    B = _mk((K, N) if b_mn else (N, K), 2)
+    out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
+    lib.gemm(A, B, out, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, round_bf16=False)
+    torch.cuda.synchronize()
+    ref = _ref(A, B, a_mn, b_mn)
+    assert torch.isfinite(out).all()
+    assert _relerr(out, ref) < 2e-5, _relerr(out, ref)
+
+
+def test_gemm_bias_bf16_out_large():
+    M, N, K = 65792, 1152, 384
+    A, B = _mk((M, K), 3), _mk((N, K), 4, 0.05)
+    bias = torch.randn(N, device="cuda")
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    lib.gemm(A, B, out, M=M, N=N, K=K, bias=bias)
+    torch.cuda.synchronize()
+    ref = (_ref(A, B, False, False) + bias).to(torch.bfloat16)
+    assert (out.float() - ref.float()).abs().max().item() <= 2 * 2**-8 * ref.float().abs().max().item()
+    assert _relerr(out, ref) < 1e-3
+
+
+def test_gemm_residual_rowremap_inplace():
+    B_, G, D, K = 3, 256, 384, 768
+    M = B_ * G
+    A, W = _mk((M, K), 5), _mk((D, K), 6, 0.05)
+    bias = torch.randn(D, device="cuda")
+    x = torch.randn(B_ * (G + 1), D, device="cuda")
+    x0 = x.clone()
+    lib.gemm(A, W, x, M=M, N=D, K=K, bias=bias, resid=x, rr_group=G, rr_skip=1)
+    torch.cuda.synchronize()
+    lin = (_ref(A, W, False, False) + bias).to(torch.bfloat16).float().view(B_, G, D)
+    exp = x0.view(B_, G + 1, D).clone()
+    exp[:, 1:] += lin
+    assert torch.equal(x.view(B_, G + 1, D)[:, 0], x0.view(B_, G + 1, D)[:, 0])
+    assert _relerr(x.view(B_, G + 1, D), exp) < 1e-3
+
+
+def test_gemm_splitk_accumulate():
+    M, N, K = 384, 1152, 8200
+    A, B = _mk((K, M), 7), _mk((K, N), 8)
+    out = torch.ones((M, N), device="cuda")
+    lib.gemm(A, B, out, M=M, N=N, K=K, a_mn=True, b_mn=True, accumulate=True, split_k=16, round_bf16=False)
+    torch.cuda.synchronize()
+    ref = _ref(A, B, True, True) + 1.0
+    assert _relerr(out, ref) < 2e-5
+
+
+def test_gemm_gelu_and_out2():
+    M, N, K = 500, 1536, 384
+    A, B = _mk((M, K), 9), _mk((N, K), 10, 0.05)
+    bias = torch.randn(N, device="cuda") * 0.1
+    out = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    pre = torch.empty((M, N), device="cuda", dtype=torch.bfloat16)
+    lib.gemm(A, B, out, M=M, N=N, K=K, bias=bias, act=lib.ACT_GELU, out2=pre)
+    torch.cuda.synchronize()
+    ref_pre = (_ref(A, B, False, False) + bias).to(torch.bfloat16)
+    ref = torch.nn.functional.gelu(ref_pre.float()).to(torch.bfloat16)
+    assert _relerr(pre, ref_pre) < 1e-3
+    assert _relerr(out, ref) < 2e-3
+
+
+def test_gemm_swiglu8():
+    M, Hs, K = 300, 1024, 384
+    A = _mk((M, K), 11)
+    W1, W2 = _mk((Hs, K), 12, 0.05), _mk((Hs, K), 13, 0.05)
+    b1, b2 = torch.randn(Hs, device="cuda") * 0.1, torch.randn(Hs, device="cuda") * 0.1
+    # 8-interleave: packed rows [16g,16g+8) = w1[8g:8g+8], [16g+8,16g+16) = w2[8g:8g+8]
+    Wp = torch.stack([W1.view(Hs // 8, 8, K), W2.view(Hs // 8, 8, K)], dim=1).reshape(2 * Hs, K).contiguous()
+    bp = torch.stack([b1.view(-1, 8), b2.view(-1, 8)], dim=1).reshape(-1).contiguous()
+    out = torch.empty((M, Hs), device="cuda", dtype=torch.bfloat16)
+    lib.gemm(A, Wp, out, M=M, N=2 * Hs, K=K, bias=bp, act=lib.ACT_SWIGLU8, ldo=Hs)
+    torch.cuda.synchronize()
+    x1 = (A.float() @ W1.float().t() + b1).to(torch.bfloat16)
+    x2 = (A.float() @ W2.float().t() + b2).to(torch.bfloat16)
+    ref = (torch.nn.functional.silu(x1.float()).to(torch.bfloat16).float() * x2.float()).to(torch.bfloat16)
+    assert _relerr(out, ref) < 3e-3
+
+
+def test_gemm_rope_epilogue():
+    Bn, Ntok, prefix, D, K = 2, 257, 1, 384, 384
+    H = D // 64
+    M = Bn * Ntok
+    A, W = _mk((M, K), 14), _mk((3 * D, K), 15, 0.05)
+    bias = torch.randn(3 * D, device="cuda") * 0.1
+    HW = Ntok - prefix
+    ang = torch.rand(HW, 64, device="cuda") * 6.28
+    sin, cos = torch.sin(ang).to(torch.bfloat16), torch.cos(ang).to(torch.bfloat16)
+    out = torch.empty((M, 3 * D), device="cuda", dtype=torch.bfloat16)
+    lib.gemm(A, W, out, M=M, N=3 * D, K=K, bias=bias, act=lib.ACT_ROPE, rope=(sin, cos, Ntok, prefix, 2 * D))
+    torch.cuda.synchronize()
+    qkv = (_ref(A, W, False, False) + bias).to(torch.bfloat16).view(Bn, Ntok, 3, H, 64)
+
+    def rot(x):  # layers/attention.py:12-23 in bf16
+        x1, x2 = x.chunk(2, dim=-1)
+        return torch.cat([-x2, x1], dim=-1)
+
+    ref = qkv.clone()
+    for i in (0, 1):
+        x = qkv[:, prefix:, i]  # [B, HW, H, 64]
+        ref[:, prefix:, i] = (x * cos[None, :, None, :]) + (rot(x) * sin[None, :, None, :])
+    got = out.view(Bn, Ntok, 3, H, 64)
+    assert torch.equal(got[:, :prefix], ref[:, :prefix]) or _relerr(got[:, :prefix], ref[:, :prefix]) < 1e-3
+    assert _relerr(got[:, :, 2], ref[:, :, 2]) < 1e-3
+    assert _relerr(got[:, :, :2], ref[:, :, :2]) < 3e-3
+
+
+def test_gemm_pixel_shuffle():
+    Bn, g, r, D = 2, 16, 16, 384
+    M, N = Bn * g * g, 3 * r * r
+    A, W = _mk((M, D), 16), _mk((N, D), 17, 0.05)
+    bias = torch.randn(N, device="cuda") * 0.1
+    out = torch.empty((Bn, 3, g * r, g * r), device="cuda")
+    lib.gemm(A, W, out, M=M, N=N, K=D, bias=bias, pixel_shuffle=(r, g, g, 3), ldo=g * r, round_bf16=False)
+    torch.cuda.synchronize()
+    y = (_ref(A, W, False, False) + bias).view(Bn, g, g, N).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.pixel_shuffle(y, r)
+    assert _relerr(out, ref) < 2e-5

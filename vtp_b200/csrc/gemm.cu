@@ -1,0 +1,451 @@
+// vtp_b200 — persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   out[M,N] = epilogue( A[M,K] · B[N,K]ᵀ )      bf16 operands, fp32 accumulators in TMEM
+//
+// Roles (192 threads): warp 0 = TMA producer, warp 1 = UMMA issuer (+ TMEM alloc), warps 2..5 = epilogue
+// (TMEM -> registers -> fused epilogue -> global).  BM = 128 (UMMA M=128, cta_group::1), BN in {128, 256},
+// BK = 64 bf16 = one 128B swizzle span.  The accumulator is double buffered in TMEM (2 x BN columns) so the
+// epilogue of tile i overlaps the MMAs of tile i+1.  Operands may be K-major or MN-major (UMMA major bits), so
+// forward (NT), dgrad (NN) and wgrad (TN) all run through this one kernel; wgrad uses split-K + fp32 atomics.
+//
+// Fused epilogues (all optional): +bias, bf16 rounding point, GELU, SwiGLU gate (8-interleaved w1|w2), axial
+// RoPE on q/k (bf16 arithmetic exactly as layers/attention.py:12-23,70-89), +residual, row remap (cls-token
+// slot), PixelShuffle NCHW store, secondary pre-activation output.
+#include "host.h"
+#include "ptx.cuh"
+
+namespace vtp {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int A_BYTES = BM * BK * 2;
+static constexpr int NUM_THREADS = 192;
+
+struct GemmDev {
+    int M, N, K;
+    int a_mn, b_mn;
+    int num_m_blocks, num_n_blocks, num_k_blocks, kb_per_split, num_splits;
+    void* out;
+    int ldo, out_dtype;
+    const float* bias;
+    int act, round_bf16;
+    const void* resid;
+    int ldr, resid_dtype;
+    int accumulate;
+    int rr_group, rr_skip;
+    const __nv_bfloat16* rope_sin;
+    const __nv_bfloat16* rope_cos;
+    int rope_tokens, rope_prefix, rope_cols;
+    int ps_r, ps_gh, ps_gw, ps_cout;
+    __nv_bfloat16* out2;
+    int ldo2;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// one 64-column unit of one output row
+__device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], int grow, int col0) {
+    const int N = p.N;
+    // ---- bias
+    if (p.bias) {
+        if (col0 + 64 <= N) {
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + i));
+                v[i] += b.x, v[i + 1] += b.y, v[i + 2] += b.z, v[i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+                if (col0 + i < N) v[i] += __ldg(p.bias + col0 + i);
+        }
+    }
+    if (p.round_bf16) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = bf16_round(v[i]);
+    }
+    // ---- output row (cls slot remap)
+    long orow = grow;
+    if (p.rr_group > 0) orow = (long)(grow / p.rr_group) * (p.rr_group + p.rr_skip) + p.rr_skip + grow % p.rr_group;
+
+    // ---- secondary output: pre-activation, bf16
+    if (p.out2) {
+        __nv_bfloat16* o2 = p.out2 + orow * p.ldo2 + col0;
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+            if (col0 + i + 8 <= N) {
+                uint4 w;
+                w.x = pack_bf16x2(v[i], v[i + 1]), w.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                w.z = pack_bf16x2(v[i + 4], v[i + 5]), w.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                *reinterpret_cast<uint4*>(o2 + i) = w;
+            }
+        }
+    }
+
+    int ncols = 64;        // number of output columns produced by this unit
+    int ocol0 = col0;      // first output column
+    int Nout = N;
+    // ---- activation
+    if (p.act == VTP_ACT_GELU) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) {
+            float g = gelu_erf(v[i]);
+            v[i] = p.round_bf16 ? bf16_round(g) : g;
+        }
+    } else if (p.act == VTP_ACT_SWIGLU8) {
+        // packed columns: [16g, 16g+8) = x1, [16g+8, 16g+16) = x2  ->  hidden[8g + i] = silu(x1) * x2
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float x1 = v[16 * g + i], x2 = v[16 * g + 8 + i];
+                float s = x1 / (1.0f + __expf(-x1));
+                if (p.round_bf16) s = bf16_round(s);
+                float h = s * x2;
+                v[8 * g + i] = p.round_bf16 ? bf16_round(h) : h;
+            }
+        }
+        ncols = 32;
+        ocol0 = col0 >> 1;
+        Nout = N >> 1;
+    } else if (p.act == VTP_ACT_ROPE) {
+        const int tok = grow % p.rope_tokens;
+        const int pos = tok - p.rope_prefix;
+        if (col0 < p.rope_cols && pos >= 0) {
+            const uint4* sp = reinterpret_cast<const uint4*>(p.rope_sin + (long)pos * 64);
+            const uint4* cp = reinterpret_cast<const uint4*>(p.rope_cos + (long)pos * 64);
+            float sn[64], cs[64];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint4 s4 = __ldg(sp + i), c4 = __ldg(cp + i);
+                sn[8 * i + 0] = bf16_lo(s4.x), sn[8 * i + 1] = bf16_hi(s4.x), sn[8 * i + 2] = bf16_lo(s4.y);
+                sn[8 * i + 3] = bf16_hi(s4.y), sn[8 * i + 4] = bf16_lo(s4.z), sn[8 * i + 5] = bf16_hi(s4.z);
+                sn[8 * i + 6] = bf16_lo(s4.w), sn[8 * i + 7] = bf16_hi(s4.w);
+                cs[8 * i + 0] = bf16_lo(c4.x), cs[8 * i + 1] = bf16_hi(c4.x), cs[8 * i + 2] = bf16_lo(c4.y);
+                cs[8 * i + 3] = bf16_hi(c4.y), cs[8 * i + 4] = bf16_lo(c4.z), cs[8 * i + 5] = bf16_hi(c4.z);
+                cs[8 * i + 6] = bf16_lo(c4.w), cs[8 * i + 7] = bf16_hi(c4.w);
+            }
+            // reference: x.to(bf16); (x*cos) + (rotate_half(x)*sin), every op rounded to bf16
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float a = bf16_round(v[i]), b = bf16_round(v[i + 32]);
+                float lo = bf16_round(bf16_round(a * cs[i]) + bf16_round((-b) * sn[i]));
+                float hi = bf16_round(bf16_round(b * cs[i + 32]) + bf16_round(a * sn[i + 32]));
+                v[i] = lo, v[i + 32] = hi;
+            }
+        }
+    }
+
+    // ---- PixelShuffle store (decoders/pixel_decoder.py:157-160): col = c*r*r + i*r + j
+    if (p.ps_r > 0) {
+        const int r = p.ps_r, gw = p.ps_gw, gh = p.ps_gh;
+        const int b = grow / (gh * gw), hi = (grow / gw) % gh, wi = grow % gw;
+        const int W = gw * r, H = gh * r;
+#pragma unroll
+        for (int i = 0; i < 64; i += 4) {
+            int col = col0 + i;
+            if (col + 4 <= N) {
+                int c = col / (r * r), ii = (col / r) % r, jj = col % r;
+                long idx = (((long)b * p.ps_cout + c) * H + hi * r + ii) * W + wi * r + jj;
+                if (p.out_dtype == VTP_F32) {
+                    float4 w = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + idx) = w;
+                } else {
+                    uint2 w;
+                    w.x = pack_bf16x2(v[i], v[i + 1]), w.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + idx) = w;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---- residual
+    if (p.resid) {
+        if (p.resid_dtype == VTP_F32) {
+            const float* rp = reinterpret_cast<const float*>(p.resid) + orow * p.ldr + ocol0;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+                if (i < ncols && ocol0 + i + 4 <= Nout) {
+                    float4 r4 = *reinterpret_cast<const float4*>(rp + i);
+                    v[i] += r4.x, v[i + 1] += r4.y, v[i + 2] += r4.z, v[i + 3] += r4.w;
+                }
+            }
+        } else {
+            const __nv_bfloat16* rp = reinterpret_cast<const __nv_bfloat16*>(p.resid) + orow * p.ldr + ocol0;
+#pragma unroll
+            for (int i = 0; i < 64; i += 8) {
+                if (i < ncols && ocol0 + i + 8 <= Nout) {
+                    uint4 r4 = *reinterpret_cast<const uint4*>(rp + i);
+                    v[i] += bf16_lo(r4.x), v[i + 1] += bf16_hi(r4.x), v[i + 2] += bf16_lo(r4.y);
+                    v[i + 3] += bf16_hi(r4.y), v[i + 4] += bf16_lo(r4.z), v[i + 5] += bf16_hi(r4.z);
+                    v[i + 6] += bf16_lo(r4.w), v[i + 7] += bf16_hi(r4.w);
+                }
+            }
+        }
+    }
+
+    // ---- store
+    if (p.out_dtype == VTP_F32) {
+        float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + ocol0;
+        if (p.accumulate) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i)
+                if (i < ncols && ocol0 + i < Nout) atomicAdd(op + i, v[i]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+                if (i < ncols && ocol0 + i + 4 <= Nout)
+                    *reinterpret_cast<float4*>(op + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+            }
+        }
+    } else {
+        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + ocol0;
+#pragma unroll
+        for (int i = 0; i < 64; i += 8) {
+            if (i < ncols && ocol0 + i + 8 <= Nout) {
+                uint4 w;
+                w.x = pack_bf16x2(v[i], v[i + 1]), w.y = pack_bf16x2(v[i + 2], v[i + 3]);
+                w.z = pack_bf16x2(v[i + 4], v[i + 5]), w.w = pack_bf16x2(v[i + 6], v[i + 7]);
+                *reinterpret_cast<uint4*>(op + i) = w;
+            }
+        }
+    }
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+    constexpr int B_BYTES = BN * BK * 2;
+    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+        for (int s = 0; s < 2; ++s) mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], 4);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
+    const int num_tiles = tiles_mn * p.num_splits;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int n_blk = t % p.num_n_blocks;
+                const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
+                const int ks = t / tiles_mn;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+                const int m0 = m_blk * BM, n0 = n_blk * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
+                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    const int k0 = kb * BK;
+                    if (!p.a_mn) {
+                        tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
+                    } else {
+                        tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
+                        tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
+                    }
+                    if (!p.b_mn) {
+                        tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BN / 64; ++i)
+                            tma_load_2d(sb + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, k0);
+                    }
+                    if (++s == STAGES) s = 0, ph ^= 1;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== UMMA issuer ==============================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+            int s = 0;
+            uint32_t ph = 0;
+            int as = 0;
+            uint32_t aph = 0;
+            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+                const int ks = t / tiles_mn;
+                const int kb0 = ks * p.kb_per_split;
+                const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
+                mbar_wait(&tempty_bar[as], aph ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * BN;
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
+                    const uint32_t b_base = a_base + A_BYTES;
+#pragma unroll
+                    for (int j = 0; j < BK / 16; ++j) {
+                        const uint64_t ad = p.a_mn ? umma_desc_sw128(a_base + j * 2048, 8192, 1024)
+                                                   : umma_desc_sw128(a_base + j * 32, 0, 1024);
+                        const uint64_t bd = p.b_mn ? umma_desc_sw128(b_base + j * 2048, 8192, 1024)
+                                                   : umma_desc_sw128(b_base + j * 32, 0, 1024);
+                        umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+                    if (++s == STAGES) s = 0, ph ^= 1;
+                }
+                umma_commit(&tfull_bar[as]);  // accumulator complete
+                if (++as == 2) as = 0, aph ^= 1;
+            }
+        }
+    } else {
+        // ============================== epilogue (warps 2..5) ==============================
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        int as = 0;
+        uint32_t aph = 0;
+        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            const int n_blk = t % p.num_n_blocks;
+            const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
+            const int m0 = m_blk * BM, n0 = n_blk * BN;
+            mbar_wait(&tfull_bar[as], aph);
+            tc_fence_after();
+            const int grow = m0 + q * 32 + lane;
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+#pragma unroll 1
+            for (int u = 0; u < BN / 64; ++u) {
+                const int col0 = n0 + u * 64;
+                if (col0 >= p.N) break;  // warp-uniform
+                uint32_t r0[32], r1[32];
+                tmem_ld_32x32(taddr + u * 64, r0);
+                tmem_ld_32x32(taddr + u * 64 + 32, r1);
+                tmem_ld_wait();
+                float v[64];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]), v[32 + i] = __uint_as_float(r1[i]);
+                if (grow < p.M) epilogue_unit(p, v, grow, col0);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (++as == 2) as = 0, aph ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+template <int BN, int STAGES>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream) {
+    constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + 1024 + 256;
+    static bool configured = false;
+    if (!configured) {
+        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        configured = true;
+    }
+    const int tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;
+    const int grid = tiles < num_sms() ? tiles : num_sms();
+    gemm_kernel<BN, STAGES><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+}  // namespace vtp
+
+using namespace vtp;
+
+extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    VTP_CHECK_ARG(a != nullptr, "gemm: null args");
+    VTP_CHECK_ARG(a->M > 0 && a->N > 0 && a->K > 0, "gemm: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+    VTP_CHECK_ARG(a->A && a->B && a->out, "gemm: null pointer");
+    VTP_CHECK_ARG(a->lda % 8 == 0 && a->ldb % 8 == 0, "gemm: lda/ldb must be multiples of 8 (16B TMA strides)");
+    VTP_CHECK_ARG((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
+                  "gemm: A/B must be 16B aligned");
+    VTP_CHECK_ARG((reinterpret_cast<uintptr_t>(a->out) & 15) == 0, "gemm: out must be 16B aligned");
+    VTP_CHECK_ARG(a->N % 8 == 0, "gemm: N must be a multiple of 8");
+    VTP_CHECK_ARG(a->out_dtype == VTP_F32 || a->out_dtype == VTP_BF16, "gemm: bad out dtype");
+    VTP_CHECK_ARG(a->ldo % (a->out_dtype == VTP_F32 ? 4 : 8) == 0 || a->ps_r > 0, "gemm: ldo alignment");
+    const int split_k = a->split_k < 1 ? 1 : a->split_k;
+    VTP_CHECK_ARG(split_k == 1 || (a->accumulate && a->out_dtype == VTP_F32 && a->act == VTP_ACT_NONE && !a->bias),
+                  "gemm: split_k needs accumulate=1, fp32 out, no bias/activation");
+    VTP_CHECK_ARG(!a->accumulate || a->out_dtype == VTP_F32, "gemm: accumulate needs fp32 out");
+    if (a->act == VTP_ACT_ROPE)
+        VTP_CHECK_ARG(a->rope_sin && a->rope_cos && a->rope_tokens > 0 && a->rope_cols % 64 == 0, "gemm: bad rope args");
+    if (a->act == VTP_ACT_SWIGLU8) VTP_CHECK_ARG(a->N % 16 == 0, "gemm: swiglu needs N %% 16 == 0");
+    if (a->ps_r > 0)
+        VTP_CHECK_ARG(a->ps_r % 4 == 0 && a->M % (a->ps_gh * a->ps_gw) == 0 && a->N == a->ps_cout * a->ps_r * a->ps_r,
+                      "gemm: bad pixel-shuffle args");
+    if (a->resid) VTP_CHECK_ARG(a->ldr % (a->resid_dtype == VTP_F32 ? 4 : 8) == 0, "gemm: ldr alignment");
+    if (a->out2) VTP_CHECK_ARG(a->ldo2 % 8 == 0, "gemm: ldo2 alignment");
+
+    // tile-N choice: minimise padded N, ties -> 256 (lower smem bandwidth per MMA)
+    const int pad128 = ceil_div(a->N, 128) * 128, pad256 = ceil_div(a->N, 256) * 256;
+    const int BN = (pad256 <= pad128) ? 256 : 128;
+
+    GemmDev p;
+    memset(&p, 0, sizeof(p));
+    p.M = a->M, p.N = a->N, p.K = a->K;
+    p.a_mn = a->a_mn_major ? 1 : 0, p.b_mn = a->b_mn_major ? 1 : 0;
+    p.num_m_blocks = ceil_div(a->M, BM);
+    p.num_n_blocks = ceil_div(a->N, BN);
+    p.num_k_blocks = ceil_div(a->K, BK);
+    p.kb_per_split = ceil_div(p.num_k_blocks, split_k);
+    p.num_splits = ceil_div(p.num_k_blocks, p.kb_per_split);
+    p.out = a->out, p.ldo = a->ldo, p.out_dtype = a->out_dtype;
+    p.bias = a->bias, p.act = a->act, p.round_bf16 = a->round_bf16;
+    p.resid = a->resid, p.ldr = a->ldr, p.resid_dtype = a->resid_dtype;
+    p.accumulate = a->accumulate;
+    p.rr_group = a->rr_group, p.rr_skip = a->rr_skip;
+    p.rope_sin = reinterpret_cast<const __nv_bfloat16*>(a->rope_sin);
+    p.rope_cos = reinterpret_cast<const __nv_bfloat16*>(a->rope_cos);
+    p.rope_tokens = a->rope_tokens, p.rope_prefix = a->rope_prefix, p.rope_cols = a->rope_cols;
+    p.ps_r = a->ps_r, p.ps_gh = a->ps_gh, p.ps_gw = a->ps_gw, p.ps_cout = a->ps_cout;
+    p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2), p.ldo2 = a->ldo2;
+
+    CUtensorMap tmA, tmB;
+    {
+        uint64_t dims[2], strides[1] = {(uint64_t)a->lda * 2};
+        uint32_t box[2];
+        if (!p.a_mn) dims[0] = a->K, dims[1] = a->M, box[0] = 64, box[1] = 128;
+        else dims[0] = a->M, dims[1] = a->K, box[0] = 64, box[1] = 64;
+        int rc = make_tmap_bf16(&tmA, a->A, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2], strides[1] = {(uint64_t)a->ldb * 2};
+        uint32_t box[2];
+        if (!p.b_mn) dims[0] = a->K, dims[1] = a->N, box[0] = 64, box[1] = (uint32_t)BN;
+        else dims[0] = a->N, dims[1] = a->K, box[0] = 64, box[1] = 64;
+        int rc = make_tmap_bf16(&tmB, a->B, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    if (BN == 256) return launch_gemm<256, 4>(tmA, tmB, p, stream);
+    return launch_gemm<128, 6>(tmA, tmB, p, stream);
+}
