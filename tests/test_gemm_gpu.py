@@ -29,8 +29,9 @@ def _relerr(x, y):
 @pytest.mark.parametrize("b_mn", [False, True])
 @pytest.mark.parametrize("M,N,K", [(300, 384, 384), (1000, 512, 200), (128, 64, 64), (777, 1152, 384), (513, 5472, 1024)])
 def test_gemm_majors(a_mn, b_mn, M, N, K):
-    A = _mk((K, M) if a_mn else (M, K), 1)
-    B = _mk((K, N) if b_mn else (N, K), 2)
+    r8 = lambda v: (v + 7) // 8 * 8
+    A = _mk((K, r8(M)), 1)[:, :M] if a_mn else _mk((M, r8(K)), 1)[:, :K]
+    B = _mk((K, r8(N)), 2)[:, :N] if b_mn else _mk((N, r8(K)), 2)[:, :K]
     out = torch.full((M, N), float("nan"), device="cuda", dtype=torch.float32)
     lib.gemm(A, B, out, M=M, N=N, K=K, a_mn=a_mn, b_mn=b_mn, round_bf16=False)
     torch.cuda.synchronize()

@@ -1,0 +1,439 @@
+// vtp_b200 — fused self-attention forward for short sequences (T = prefix + HW, HW <= 256) on tcgen05.
+//
+// Replaces layers/attention.py:110-126 (SelfAttention.compute_attention after RoPE: SDPA with scale 1/sqrt(64), no
+// mask, no dropout) and nn.MultiheadAttention's causal SDPA in the text tower (layers/block.py:387-412).
+//
+// One CTA per (query tile of 128 patch rows, head, image); 2 CTAs/SM (112 KB smem, 256 TMEM columns each).
+//   S = Q·Kᵀ     one UMMA chain  M=128, N=128|256, K=64      (Q,K tiles by TMA straight out of the packed qkv buffer)
+//   softmax      one thread per query row, the whole row lives in TMEM -> exact single-pass softmax (no online rescale)
+//   O = P·V      P written as bf16 into a swizzled K-major smem tile in two 128-key halves, V consumed as an MN-major
+//                B operand (no transpose); O accumulates in TMEM columns [0,64) that S no longer needs.
+// The `prefix` (cls / storage) tokens — 1 in the encoder, 0 in the decoder/text — would cost a third 128-row tile for
+// one row, so they are handled on CUDA cores: their key columns are folded into every row's softmax by the row
+// threads, and their query rows are computed by a spare warp from the K/V tiles already in smem.
+#include "host.h"
+#include "ptx.cuh"
+
+namespace vtp {
+
+static constexpr int ATT_THREADS = 192;
+static constexpr int MAX_PREFIX = 4;
+// smem: Q 16K | K 32K | V 32K | P 32K | barriers
+static constexpr int SQ = 0, SK = 16384, SV = SK + 32768, SP = SV + 32768, SBAR = SP + 32768;
+static constexpr int ATT_SMEM = SBAR + 128;  // 114816 B -> 2 CTAs/SM
+
+struct AttnDev {
+    const __nv_bfloat16* qkv;  // [B*T][3D]
+    __nv_bfloat16* out;        // [B*T][D]
+    float* lse;                // [B][H][T] or null
+    int B, T, H, D, prefix, HW, causal, nkt;  // nkt = number of 128-key tiles (1|2)
+    float scale_log2;                         // scale * log2(e)
+    float scale;
+};
+
+__device__ __forceinline__ uint32_t sw128_off(int row, int col /*bf16 element 0..63*/) {
+    return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const AttnDev p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (smem_u32(smem) & 1023) __trap();  // SWIZZLE_128B tiles need a 1024B-aligned base
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SBAR);
+    uint64_t* bar_qk = bars + 0;   // Q,K landed
+    uint64_t* bar_v = bars + 1;    // V landed
+    uint64_t* bar_s = bars + 2;    // S complete in TMEM
+    uint64_t* bar_p0 = bars + 3;   // P half 0 written (128 arrivals)
+    uint64_t* bar_pv0 = bars + 4;  // PV half 0 done (P buffer reusable)
+    uint64_t* bar_p1 = bars + 5;   // P half 1 written
+    uint64_t* bar_o = bars + 6;    // O complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int D = p.D, T = p.T, prefix = p.prefix, HW = p.HW;
+    const long seq_row0 = (long)b * T;
+    const int kvrows = 128 * p.nkt;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm);
+        mbar_init(bar_qk, 1), mbar_init(bar_v, 1), mbar_init(bar_s, 1), mbar_init(bar_p0, 128);
+        mbar_init(bar_pv0, 1), mbar_init(bar_p1, 128), mbar_init(bar_o, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---------------- TMA
+            const int row_q = (int)seq_row0 + prefix + 128 * qt;
+            const int row_k = (int)seq_row0 + prefix;
+            mbar_expect_tx(bar_qk, 16384 + 16384 * p.nkt);
+            tma_load_2d(smem + SQ, &tm, bar_qk, h * 64, row_q);
+            for (int i = 0; i < p.nkt; ++i) tma_load_2d(smem + SK + i * 16384, &tm, bar_qk, D + h * 64, row_k + 128 * i);
+            mbar_expect_tx(bar_v, 16384 * p.nkt);
+            for (int i = 0; i < p.nkt; ++i)
+                tma_load_2d(smem + SV + i * 16384, &tm, bar_v, 2 * D + h * 64, row_k + 128 * i);
+            // ---------------- S = Q Kᵀ
+            mbar_wait(bar_qk, 0);
+            tc_fence_after();
+            const uint32_t idesc_s = umma_idesc_bf16(128, kvrows, 0, 0);
+            const uint32_t qa = smem_u32(smem + SQ), ka = smem_u32(smem + SK);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                umma_bf16_ss(tmem, umma_desc_sw128(qa + j * 32, 0, 1024), umma_desc_sw128(ka + j * 32, 0, 1024), idesc_s,
+                             j > 0);
+            umma_commit(bar_s);
+            // ---------------- O = P V  (two 128-key halves through one P buffer)
+            const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (=V) is MN-major
+            const uint32_t pa = smem_u32(smem + SP), va = smem_u32(smem + SV);
+            mbar_wait(bar_v, 0);
+            for (int half = 0; half < p.nkt; ++half) {
+                mbar_wait(half == 0 ? bar_p0 : bar_p1, 0);
+                tc_fence_after();
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {  // 8 k-steps of 16 keys
+                    const uint64_t ad = umma_desc_sw128(pa + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024);
+                    const uint64_t bd = umma_desc_sw128(va + half * 16384 + j * 2048, 8192, 1024);
+                    umma_bf16_ss(tmem, ad, bd, idesc_o, (half > 0 || j > 0) ? 1u : 0u);
+                }
+                umma_commit(half == 0 && p.nkt == 2 ? bar_pv0 : bar_o);
+            }
+        }
+    } else if (warp <= 4) {
+        // ---------------- softmax + epilogue: one thread per query row
+        const int q4 = warp & 3;
+        const int r = q4 * 32 + lane;             // row within the tile == TMEM lane
+        const int qpos = 128 * qt + r;            // patch index of this query
+        const int qtok = prefix + qpos;           // token index within the sequence
+        const bool row_valid = qpos < HW;
+        const uint32_t trow = tmem + (uint32_t(q4 * 32) << 16);
+
+        // scores against the prefix keys (CUDA cores): q row from smem (swizzled), k rows from global
+        float s_pre[MAX_PREFIX];
+        mbar_wait(bar_qk, 0);
+        if (prefix > 0) {
+            float qf[64];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 w = *reinterpret_cast<const uint4*>(smem + SQ + sw128_off(r, c * 8));
+                qf[c * 8 + 0] = bf16_lo(w.x), qf[c * 8 + 1] = bf16_hi(w.x), qf[c * 8 + 2] = bf16_lo(w.y);
+                qf[c * 8 + 3] = bf16_hi(w.y), qf[c * 8 + 4] = bf16_lo(w.z), qf[c * 8 + 5] = bf16_hi(w.z);
+                qf[c * 8 + 6] = bf16_lo(w.w), qf[c * 8 + 7] = bf16_hi(w.w);
+            }
+#pragma unroll
+            for (int j = 0; j < MAX_PREFIX; ++j) {
+                s_pre[j] = -INFINITY;
+                if (j < prefix) {
+                    const uint4* kp = reinterpret_cast<const uint4*>(p.qkv + (seq_row0 + j) * 3 * D + D + h * 64);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 w = __ldg(kp + c);
+                        acc += qf[c * 8 + 0] * bf16_lo(w.x) + qf[c * 8 + 1] * bf16_hi(w.x) + qf[c * 8 + 2] * bf16_lo(w.y) +
+                               qf[c * 8 + 3] * bf16_hi(w.y) + qf[c * 8 + 4] * bf16_lo(w.z) + qf[c * 8 + 5] * bf16_hi(w.z) +
+                               qf[c * 8 + 6] * bf16_lo(w.w) + qf[c * 8 + 7] * bf16_hi(w.w);
+                    }
+                    if (!p.causal || j <= qtok) s_pre[j] = acc;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < MAX_PREFIX; ++j) s_pre[j] = -INFINITY;
+        }
+
+        mbar_wait(bar_s, 0);
+        tc_fence_after();
+        // pass 1: row max
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < MAX_PREFIX; ++j) m = fmaxf(m, s_pre[j]);
+        const int kmax = p.causal ? min(HW, qpos + 1) : HW;  // keys [0,kmax) are visible
+        for (int c = 0; c < kvrows; c += 32) {
+            uint32_t rr[32];
+            tmem_ld_32x32(trow + c, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (c + i < kmax) m = fmaxf(m, __uint_as_float(rr[i]));
+        }
+        const float msc = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+        // pass 2: p = exp2(s*scale*log2e - m*scale*log2e), written as bf16 to the swizzled P tile, half by half
+        float l = 0.f;
+        float p_pre[MAX_PREFIX];
+#pragma unroll
+        for (int j = 0; j < MAX_PREFIX; ++j) {
+            p_pre[j] = (s_pre[j] == -INFINITY) ? 0.f : exp2f(s_pre[j] * p.scale_log2 - msc);
+            l += p_pre[j];
+            p_pre[j] = bf16_round(p_pre[j]);
+        }
+        for (int half = 0; half < p.nkt; ++half) {
+            if (half == 1) mbar_wait(bar_pv0, 0);  // P buffer free again
+#pragma unroll 1
+            for (int c32 = 0; c32 < 4; ++c32) {
+                const int c = half * 128 + c32 * 32;
+                uint32_t rr[32];
+                tmem_ld_32x32(trow + c, rr);
+                tmem_ld_wait();
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float e0 = (c + i < kmax) ? exp2f(__uint_as_float(rr[i]) * p.scale_log2 - msc) : 0.f;
+                    float e1 = (c + i + 1 < kmax) ? exp2f(__uint_as_float(rr[i + 1]) * p.scale_log2 - msc) : 0.f;
+                    l += e0 + e1;
+                    pk[i >> 1] = pack_bf16x2(e0, e1);
+                }
+                // 32 keys = 4 x 16B chunks into chunk-region (c32>>1), columns (c32&1)*32 ..
+                uint8_t* pb = smem + SP + (c32 >> 1) * 16384;
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const int col = (c32 & 1) * 32 + v4 * 8;
+                    *reinterpret_cast<uint4*>(pb + sw128_off(r, col)) =
+                        make_uint4(pk[v4 * 4], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(half == 0 ? bar_p0 : bar_p1);
+        }
+        // epilogue
+        mbar_wait(bar_o, 0);
+        tc_fence_after();
+        uint32_t o0[32], o1[32];
+        tmem_ld_32x32(trow, o0);
+        tmem_ld_32x32(trow + 32, o1);
+        tmem_ld_wait();
+        float o[64];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(o0[i]), o[32 + i] = __uint_as_float(o1[i]);
+#pragma unroll
+        for (int j = 0; j < MAX_PREFIX; ++j) {
+            if (j < prefix && p_pre[j] != 0.f) {
+                const uint4* vp = reinterpret_cast<const uint4*>(p.qkv + (seq_row0 + j) * 3 * D + 2 * D + h * 64);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 w = __ldg(vp + c);
+                    o[c * 8 + 0] += p_pre[j] * bf16_lo(w.x), o[c * 8 + 1] += p_pre[j] * bf16_hi(w.x);
+                    o[c * 8 + 2] += p_pre[j] * bf16_lo(w.y), o[c * 8 + 3] += p_pre[j] * bf16_hi(w.y);
+                    o[c * 8 + 4] += p_pre[j] * bf16_lo(w.z), o[c * 8 + 5] += p_pre[j] * bf16_hi(w.z);
+                    o[c * 8 + 6] += p_pre[j] * bf16_lo(w.w), o[c * 8 + 7] += p_pre[j] * bf16_hi(w.w);
+                }
+            }
+        }
+        if (row_valid) {
+            const float inv = 1.f / l;
+            __nv_bfloat16* op = p.out + (seq_row0 + qtok) * D + h * 64;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint4 w;
+                w.x = pack_bf16x2(o[c * 8] * inv, o[c * 8 + 1] * inv), w.y = pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+                w.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv), w.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+                *reinterpret_cast<uint4*>(op + c * 8) = w;
+            }
+            if (p.lse) p.lse[((long)b * p.H + h) * T + qtok] = m * p.scale + logf(l);
+        }
+        tc_fence_before();
+    } else {
+        // ---------------- warp 5: prefix query rows (only the qt==0 CTA), CUDA cores over the smem K/V tiles
+        if (qt == 0 && prefix > 0) {
+            mbar_wait(bar_qk, 0);
+            mbar_wait(bar_v, 0);
+            for (int j = 0; j < prefix; ++j) {
+                float qf[64];
+                {
+                    const uint4* qp = reinterpret_cast<const uint4*>(p.qkv + (seq_row0 + j) * 3 * D + h * 64);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 w = __ldg(qp + c);
+                        qf[c * 8 + 0] = bf16_lo(w.x), qf[c * 8 + 1] = bf16_hi(w.x), qf[c * 8 + 2] = bf16_lo(w.y);
+                        qf[c * 8 + 3] = bf16_hi(w.y), qf[c * 8 + 4] = bf16_lo(w.z), qf[c * 8 + 5] = bf16_hi(w.z);
+                        qf[c * 8 + 6] = bf16_lo(w.w), qf[c * 8 + 7] = bf16_hi(w.w);
+                    }
+                }
+                auto dot_row = [&](const uint4* kp, bool from_smem, int row) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 w = from_smem ? *reinterpret_cast<const uint4*>(smem + SK + sw128_off(row, c * 8))
+                                                  : __ldg(kp + c);
+                        acc += qf[c * 8 + 0] * bf16_lo(w.x) + qf[c * 8 + 1] * bf16_hi(w.x) + qf[c * 8 + 2] * bf16_lo(w.y) +
+                               qf[c * 8 + 3] * bf16_hi(w.y) + qf[c * 8 + 4] * bf16_lo(w.z) + qf[c * 8 + 5] * bf16_hi(w.z) +
+                               qf[c * 8 + 6] * bf16_lo(w.w) + qf[c * 8 + 7] * bf16_hi(w.w);
+                    }
+                    return acc;
+                };
+                float sp[MAX_PREFIX], s[8];
+                float m = -INFINITY;
+#pragma unroll
+                for (int t = 0; t < MAX_PREFIX; ++t) {
+                    sp[t] = -INFINITY;
+                    if (t < prefix && (!p.causal || t <= j))
+                        sp[t] = dot_row(reinterpret_cast<const uint4*>(p.qkv + (seq_row0 + t) * 3 * D + D + h * 64), false, 0);
+                    m = fmaxf(m, sp[t]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kk = lane + 32 * i;
+                    s[i] = -INFINITY;
+                    if (kk < HW && kk < kvrows && (!p.causal || prefix + kk <= j)) s[i] = dot_row(nullptr, true, kk);
+                    m = fmaxf(m, s[i]);
+                }
+                m = warp_max(m);
+                const float msc = m * p.scale_log2;
+                float l = 0.f, e[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    e[i] = (s[i] == -INFINITY) ? 0.f : exp2f(s[i] * p.scale_log2 - msc);
+                    l += e[i];
+                    e[i] = bf16_round(e[i]);
+                }
+                l = warp_sum(l);
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int t = 0; t < MAX_PREFIX; ++t) {
+                    if (t < prefix && sp[t] != -INFINITY) {
+                        const float pe = exp2f(sp[t] * p.scale_log2 - msc);
+                        l += pe;
+                        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p.qkv + (seq_row0 + t) * 3 * D + 2 * D + h * 64) + lane);
+                        a0 += bf16_round(pe) * bf16_lo(w), a1 += bf16_round(pe) * bf16_hi(w);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (32 * i < HW && 32 * i < kvrows) {
+                        for (int t = 0; t < 32; ++t) {
+                            const float pk = __shfl_sync(0xffffffffu, e[i], t);
+                            const int kk = 32 * i + t;
+                            if (kk < HW) {
+                                const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + SV + sw128_off(kk, 2 * lane));
+                                a0 += pk * bf16_lo(w), a1 += pk * bf16_hi(w);
+                            }
+                        }
+                    }
+                }
+                const float inv = 1.f / l;
+                *reinterpret_cast<uint32_t*>(p.out + (seq_row0 + j) * D + h * 64 + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
+                if (p.lse && lane == 0) p.lse[((long)b * p.H + h) * T + j] = m * p.scale + logf(l);
+            }
+        }
+    }
+
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
+}  // namespace vtp
+
+namespace vtp {
+
+// ------------------------------------------------------------------------------------------------------------
+// fp32 attention (accuracy mode): CUDA cores, one CTA per (head, image), K/V tiles in padded smem, one warp per
+// query row.  Used by the fp32-exact inference mode only (layers/attention.py:124 with fp32 q,k,v).
+__global__ void attn_fwd_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int H, int causal,
+                                    float scale) {
+    extern __shared__ float sm[];
+    const int D = H * 64, h = blockIdx.x, b = blockIdx.y;
+    float* Ks = sm;                 // [T][65]
+    float* Vs = Ks + (long)T * 65;  // [T][64]
+    float* Ps = Vs + (long)T * 64;  // [nwarps][T]
+    const float* base = qkv + (long)b * T * 3 * D;
+    for (int i = threadIdx.x; i < T * 64; i += blockDim.x) {
+        const int t = i >> 6, d = i & 63;
+        Ks[t * 65 + d] = base[(long)t * 3 * D + D + h * 64 + d];
+        Vs[t * 64 + d] = base[(long)t * 3 * D + 2 * D + h * 64 + d];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    float* pw = Ps + (long)warp * T;
+    for (int q = warp; q < T; q += nw) {
+        const float* qp = base + (long)q * 3 * D + h * 64;
+        float qf[64];
+#pragma unroll
+        for (int d = 0; d < 64; ++d) qf[d] = qp[d];
+        const int kend = causal ? q + 1 : T;
+        float m = -INFINITY;
+        for (int k = lane; k < kend; k += 32) {
+            float acc = 0.f;
+#pragma unroll
+            for (int d = 0; d < 64; ++d) acc += qf[d] * Ks[k * 65 + d];
+            acc *= scale;
+            pw[k] = acc;
+            m = fmaxf(m, acc);
+        }
+        m = warp_max(m);
+        float l = 0.f;
+        for (int k = lane; k < kend; k += 32) {
+            const float e = expf(pw[k] - m);
+            pw[k] = e;
+            l += e;
+        }
+        l = warp_sum(l);
+        __syncwarp();
+        float a0 = 0.f, a1 = 0.f;
+        for (int k = 0; k < kend; ++k) {
+            const float pk = pw[k];
+            a0 += pk * Vs[k * 64 + lane], a1 += pk * Vs[k * 64 + 32 + lane];
+        }
+        float* op = out + ((long)b * T + q) * D + h * 64;
+        op[lane] = a0 / l, op[32 + lane] = a1 / l;
+        __syncwarp();
+    }
+}
+
+}  // namespace vtp
+
+using namespace vtp;
+
+extern "C" int vtp_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int H, int prefix, int causal,
+                                 vtp_stream_t st) {
+    VTP_CHECK_ARG(qkv && out && B > 0 && T > 0 && H > 0, "attention_fwd: bad args");
+    VTP_CHECK_ARG(prefix >= 0 && prefix <= MAX_PREFIX && prefix < T, "attention_fwd: prefix must be in [0,%d]", MAX_PREFIX);
+    const int HW = T - prefix;
+    VTP_CHECK_ARG(HW <= 256, "attention_fwd: %d non-prefix tokens > 256 is not supported by the single-pass kernel", HW);
+    VTP_CHECK_ARG(B <= 65535 && H <= 65535, "attention_fwd: grid too large");
+    const int D = H * 64;
+    AttnDev p;
+    p.qkv = (const __nv_bfloat16*)qkv, p.out = (__nv_bfloat16*)out, p.lse = lse;
+    p.B = B, p.T = T, p.H = H, p.D = D, p.prefix = prefix, p.HW = HW, p.causal = causal;
+    p.nkt = HW > 128 ? 2 : 1;
+    p.scale = 0.125f;
+    p.scale_log2 = 0.125f * 1.4426950408889634f;
+    CUtensorMap tm;
+    uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)B * T}, strides[1] = {(uint64_t)3 * D * 2};
+    uint32_t box[2] = {64, 128};
+    int rc = make_tmap_bf16(&tm, qkv, 2, dims, strides, box);
+    if (rc) return rc;
+    static bool configured = false;
+    if (!configured) {
+        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        configured = true;
+    }
+    dim3 grid(ceil_div(HW, 128), H, B);
+    attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tm, p);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_attention_fwd_f32(const float* qkv, float* out, int B, int T, int H, int causal, vtp_stream_t st) {
+    VTP_CHECK_ARG(qkv && out && B > 0 && T > 0 && H > 0 && B <= 65535, "attention_fwd_f32: bad args");
+    const int nw = 8;
+    const size_t smem = ((size_t)T * 65 + (size_t)T * 64 + (size_t)nw * T) * sizeof(float);
+    VTP_CHECK_ARG(smem <= 220 * 1024, "attention_fwd_f32: T=%d too long for the smem-resident kernel", T);
+    static size_t configured = 0;
+    if (smem > configured) {
+        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    attn_fwd_f32_kernel<<<dim3(H, B), nw * 32, smem, (cudaStream_t)st>>>(qkv, out, T, H, causal, 0.125f);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
