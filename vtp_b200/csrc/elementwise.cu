@@ -9,7 +9,8 @@ namespace vtp {
 // ------------------------------------------------------------------------------------------------ patchify
 // img fp32 [B,C,H,W] -> out bf16 [B*gh*gw][C*p*p], k = c*p*p + i*p + j  (== Conv2d weight.flatten(1) order,
 // layers/embeddings.py:58).  One thread handles 4 consecutive j (16B load, 8B store).
-__global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int B, int C, int H,
+template <typename TO>
+__global__ void patchify_kernel(const float* __restrict__ img, TO* __restrict__ out, int B, int C, int H,
                                 int W, int p, long total4) {
     const int gw = W / p, gh = H / p, K = C * p * p;
     for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total4; t += (long)gridDim.x * blockDim.x) {
@@ -20,9 +21,13 @@ __global__ void patchify_kernel(const float* __restrict__ img, __nv_bfloat16* __
         const int b = (int)(row / (gh * gw)), ph = (int)((row / gw) % gh), pw = (int)(row % gw);
         const float4 v =
             __ldg(reinterpret_cast<const float4*>(img + (((long)b * C + c) * H + ph * p + i) * W + pw * p + j));
-        uint2 w;
-        w.x = pack_bf16x2(v.x, v.y), w.y = pack_bf16x2(v.z, v.w);
-        *reinterpret_cast<uint2*>(out + e) = w;
+        if constexpr (sizeof(TO) == 4) {
+            *reinterpret_cast<float4*>(out + e) = v;
+        } else {
+            uint2 w;
+            w.x = pack_bf16x2(v.x, v.y), w.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(out + e) = w;
+        }
     }
 }
 
@@ -185,12 +190,13 @@ __global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __rest
 // in [B][R][C] -> out [B][C][R] with dtype conversion (latents (B,HW,64) <-> (B,64,H,W), modeling_vtp.py:395,
 // pixel_decoder.py:141)
 template <typename TI, typename TO>
-__global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int C) {
+__global__ void transpose_kernel(const TI* __restrict__ in, TO* __restrict__ out, int R, int C, long in_bstride,
+                                 long out_bstride) {
     __shared__ float tile[32][33];
     const int b = blockIdx.z;
     const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
-    const TI* ib = in + (long)b * R * C;
-    TO* ob = out + (long)b * R * C;
+    const TI* ib = in + (long)b * in_bstride;
+    TO* ob = out + (long)b * out_bstride;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
         const int r = r0 + i, c = c0 + threadIdx.x;
         if (r < R && c < C) tile[i][threadIdx.x] = (float)ib[(long)r * C + c];
@@ -225,13 +231,17 @@ static inline int grid_for(long total, int block) {
 
 using namespace vtp;
 
-extern "C" int vtp_patchify(const float* img, void* out_bf16, int B, int C, int H, int W, int p, vtp_stream_t st) {
-    VTP_CHECK_ARG(img && out_bf16 && B > 0 && C > 0, "patchify: bad args");
+extern "C" int vtp_patchify(const float* img, void* out, int out_dtype, int B, int C, int H, int W, int p,
+                            vtp_stream_t st) {
+    VTP_CHECK_ARG(img && out && B > 0 && C > 0, "patchify: bad args");
     VTP_CHECK_ARG(H % p == 0 && W % p == 0 && p % 4 == 0, "patchify: H,W must be multiples of p, p %% 4 == 0");
     VTP_CHECK_ARG((reinterpret_cast<uintptr_t>(img) & 15) == 0 && W % 4 == 0, "patchify: alignment");
     const long total4 = (long)B * C * H * W / 4;
-    patchify_kernel<<<grid_for(total4, 256), 256, 0, (cudaStream_t)st>>>(img, (__nv_bfloat16*)out_bf16, B, C, H, W, p,
-                                                                          total4);
+    if (out_dtype == VTP_F32)
+        patchify_kernel<float><<<grid_for(total4, 256), 256, 0, (cudaStream_t)st>>>(img, (float*)out, B, C, H, W, p, total4);
+    else
+        patchify_kernel<__nv_bfloat16>
+            <<<grid_for(total4, 256), 256, 0, (cudaStream_t)st>>>(img, (__nv_bfloat16*)out, B, C, H, W, p, total4);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }
@@ -297,20 +307,20 @@ extern "C" int vtp_split3(const float* x, long ldx, void* out_bf16, long M, int 
     return VTP_OK;
 }
 
-extern "C" int vtp_transpose_batched(const void* in, int in_dtype, void* out, int out_dtype, int B, int R, int C,
-                                     vtp_stream_t st) {
+extern "C" int vtp_transpose_batched(const void* in, int in_dtype, long in_bstride, void* out, int out_dtype,
+                                     long out_bstride, int B, int R, int C, vtp_stream_t st) {
     VTP_CHECK_ARG(in && out && B > 0 && R > 0 && C > 0 && B <= 65535, "transpose: bad args");
     dim3 grid(ceil_div(C, 32), ceil_div(R, 32), B), block(32, 8);
     cudaStream_t s = (cudaStream_t)st;
     if (in_dtype == VTP_F32 && out_dtype == VTP_F32)
-        transpose_kernel<float, float><<<grid, block, 0, s>>>((const float*)in, (float*)out, R, C);
+        transpose_kernel<float, float><<<grid, block, 0, s>>>((const float*)in, (float*)out, R, C, in_bstride, out_bstride);
     else if (in_dtype == VTP_F32)
-        transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, s>>>((const float*)in, (__nv_bfloat16*)out, R, C);
+        transpose_kernel<float, __nv_bfloat16><<<grid, block, 0, s>>>((const float*)in, (__nv_bfloat16*)out, R, C, in_bstride, out_bstride);
     else if (out_dtype == VTP_F32)
-        transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, s>>>((const __nv_bfloat16*)in, (float*)out, R, C);
+        transpose_kernel<__nv_bfloat16, float><<<grid, block, 0, s>>>((const __nv_bfloat16*)in, (float*)out, R, C, in_bstride, out_bstride);
     else
         transpose_kernel<__nv_bfloat16, __nv_bfloat16>
-            <<<grid, block, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C);
+            <<<grid, block, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, R, C, in_bstride, out_bstride);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

@@ -111,6 +111,11 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
     } else if (p.act == VTP_ACT_ROPE) {
         const int tok = grow % p.rope_tokens;
         const int pos = tok - p.rope_prefix;
+        if (col0 < p.rope_cols && pos < 0) {
+            // prefix (cls) tokens are not rotated but still pass through q.to(bf16) (layers/attention.py:76-79)
+#pragma unroll
+            for (int i = 0; i < 64; ++i) v[i] = bf16_round(v[i]);
+        }
         if (col0 < p.rope_cols && pos >= 0) {
             const uint4* sp = reinterpret_cast<const uint4*>(p.rope_sin + (long)pos * 64);
             const uint4* cp = reinterpret_cast<const uint4*>(p.rope_cos + (long)pos * 64);

@@ -47,6 +47,20 @@ SIGNATURES: dict[str, tuple] = {
     "vtp_version": (C.c_int, []),
     "vtp_check_device": (C.c_int, []),
     "vtp_gemm_bf16": (C.c_int, [C.POINTER(GemmArgs), C.c_void_p]),
+    "vtp_patchify": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_fill_prefix_tokens": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_apply_mask_tokens": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p]),
+    "vtp_norm_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_float,
+                               C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vtp_split3": (C.c_int, [C.c_void_p, C.c_long, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_transpose_batched": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_long, C.c_int, C.c_int,
+                                        C.c_int, C.c_void_p]),
+    "vtp_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int,
+                                  C.c_int, C.c_void_p]),
+    "vtp_attention_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p]),
+    "vtp_attention_fwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }
 
 
@@ -119,3 +133,61 @@ def gemm(A, B, out, *, M: int, N: int, K: int, lda: int | None = None, ldb: int 
     if out2 is not None:
         a.out2, a.ldo2 = _ptr(out2), (ldo2 if ldo2 is not None else out2.stride(-2))
     check(load().vtp_gemm_bf16(C.byref(a), stream if stream is not None else current_stream()), "vtp_gemm_bf16")
+
+
+def _st(stream):
+    return stream if stream is not None else current_stream()
+
+
+def patchify(img, out, p: int = 16, stream=None):
+    B, Cc, H, W = img.shape
+    check(load().vtp_patchify(_ptr(img), _ptr(out), _dt(out), B, Cc, H, W, p, _st(stream)), "vtp_patchify")
+
+
+def fill_prefix_tokens(x, vec, B: int, tokens: int, nprefix: int, D: int, stream=None):
+    check(load().vtp_fill_prefix_tokens(_ptr(x), _dt(x), _ptr(vec), B, tokens, nprefix, D, _st(stream)),
+          "vtp_fill_prefix_tokens")
+
+
+def apply_mask_tokens(x, mask_token, idx, HW: int, tokens: int, prefix: int, D: int, stream=None):
+    check(load().vtp_apply_mask_tokens(_ptr(x), _dt(x), _ptr(mask_token), _ptr(idx), idx.numel(), HW, tokens, prefix, D,
+                                       _st(stream)), "vtp_apply_mask_tokens")
+
+
+OUT_F32, OUT_BF16, OUT_SPLIT3 = 0, 1, 2
+
+
+def norm_fwd(x, y, w, b, eps: float, M: int, D: int, *, y_mode: int, ldx: int | None = None, rstd=None, mean=None,
+             stream=None):
+    check(load().vtp_norm_fwd(_ptr(x), _dt(x), ldx if ldx is not None else D, _ptr(y), y_mode, _ptr(w), _ptr(b), eps,
+                              M, D, _ptr(rstd), _ptr(mean), _st(stream)), "vtp_norm_fwd")
+
+
+def split3(x, out, M: int, K: int, *, b_side: bool, ldx: int | None = None, stream=None):
+    check(load().vtp_split3(_ptr(x), ldx if ldx is not None else K, _ptr(out), M, K, int(b_side), _st(stream)),
+          "vtp_split3")
+
+
+def transpose_batched(inp, out, B: int, R: int, Cc: int, *, in_bstride: int | None = None,
+                      out_bstride: int | None = None, in_offset: int = 0, stream=None):
+    """in [B][R][Cc] (batch stride in_bstride elements, starting in_offset elements in) -> out [B][Cc][R]."""
+    ip = inp.data_ptr() + in_offset * inp.element_size()
+    check(load().vtp_transpose_batched(ip, _dt(inp), in_bstride if in_bstride is not None else R * Cc, _ptr(out),
+                                       _dt(out), out_bstride if out_bstride is not None else R * Cc, B, R, Cc,
+                                       _st(stream)), "vtp_transpose_batched")
+
+
+def gather_rows(inp, out, idx, D: int, *, ld_in: int | None = None, ld_out: int | None = None, stream=None):
+    check(load().vtp_gather_rows(_ptr(inp), _dt(inp), ld_in if ld_in is not None else D, _ptr(out), _dt(out),
+                                 ld_out if ld_out is not None else D, _ptr(idx), idx.numel(), D, _st(stream)),
+          "vtp_gather_rows")
+
+
+def attention_fwd(qkv, out, B: int, T: int, H: int, *, prefix: int, causal: bool = False, lse=None, stream=None):
+    check(load().vtp_attention_fwd(_ptr(qkv), _ptr(out), _ptr(lse), B, T, H, prefix, int(causal), _st(stream)),
+          "vtp_attention_fwd")
+
+
+def attention_fwd_f32(qkv, out, B: int, T: int, H: int, *, causal: bool = False, stream=None):
+    check(load().vtp_attention_fwd_f32(_ptr(qkv), _ptr(out), B, T, H, int(causal), _st(stream)),
+          "vtp_attention_fwd_f32")
