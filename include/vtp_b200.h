@@ -95,6 +95,12 @@ int vtp_transpose_batched(const void* in, int in_dtype, long in_bstride, void* o
 /* out[i,:] = in[idx[i],:] (vtp.py:432-439,470-473 iBOT gather; encoders/text_transformer.py:224 argmax pool) */
 int vtp_gather_rows(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, const int64_t* idx,
                     int n, int D, vtp_stream_t stream);
+/* vtp_hf/modeling_vtp.py:297-298 — out[b*L+l] = token_embedding[ids[b,l]] + positional_embedding[l] (fp32) */
+int vtp_embed_tokens(const int64_t* ids, const float* emb, const float* pos, float* out, long BL, int L, int D,
+                     vtp_stream_t stream);
+/* F.normalize(x, dim=-1, eps) (vtp_hf/modeling_vtp.py:276,310; heads/dino_head.py:83-84); norm_out [M] optional */
+int vtp_l2norm_fwd(const void* x, int x_dtype, void* y, int y_dtype, float* norm_out, int M, int D, float eps,
+                   vtp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Attention (vtp_b200/csrc/attention.cu)

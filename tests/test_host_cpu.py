@@ -1,0 +1,88 @@
+"""CPU: host-side logic — state-dict/ABI compatibility with the reference, config defaults, packing layouts."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from tests.util import load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_abi_exports_every_declared_symbol():
+    from vtp_b200 import lib
+
+    hdr = open(os.path.join(ROOT, "include", "vtp_b200.h")).read()
+    declared = set(re.findall(r"\b(vtp_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"vtp_stream_t"}
+    assert declared, "no declarations parsed"
+    assert os.path.exists(lib.LIB_PATH), "libvtp_b200.so missing: run python -m vtp_b200.build"
+    so = ctypes.CDLL(lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(so, name), f"{name} declared in include/vtp_b200.h but not exported"
+    assert declared == set(lib.SIGNATURES), declared ^ set(lib.SIGNATURES)
+    assert lib.load().vtp_version() >= 100
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_state_dict_keys_match_reference(name):
+    from vtp_b200.config import VTPConfig
+    from vtp_b200.model import VTPModel
+
+    meta, _ = load_golden(name)
+    m = VTPModel(VTPConfig(**meta["config"]))
+    mine = {k: list(v.shape) for k, v in m.state_dict().items()}
+    assert mine == meta["spec"]  # spec was dumped from the real reference's state_dict()
+
+
+def test_config_defaults_match_reference():
+    from vtp_b200.config import VTPConfig
+
+    c = VTPConfig()
+    assert (c.vision_embed_dim, c.vision_depth, c.vision_num_heads) == (768, 12, 12)
+    assert (c.vision_norm_layer, c.vision_ffn_layer, c.decoder_norm_layer) == ("rmsnorm", "swiglu", "layernorm")
+    assert c.vision_feature_bottleneck == 64 and c.vision_bottleneck_ae_only and c.vision_clip_feat == "cls"
+    assert c.text_context_length == 77 and c.text_vocab_size == 49408 and c.model_type == "vtp"
+
+
+def test_cpu_call_fails_loudly():
+    from vtp_b200 import lib
+    from vtp_b200.config import preset
+    from vtp_b200.model import VTPModel
+
+    m = VTPModel(preset("tiny"))
+    with pytest.raises(lib.VtpError):
+        m.get_reconstruction_latents(torch.zeros(1, 3, 64, 64))
+
+
+def test_save_load_roundtrip(tmp_path):
+    from vtp_b200.config import preset
+    from vtp_b200.model import VTPModel
+
+    m = VTPModel(preset("tiny"))
+    m.save_pretrained(str(tmp_path))
+    m2 = VTPModel.from_pretrained(str(tmp_path))
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+
+
+def test_interleave8_layout():
+    from vtp_b200.engine import interleave8
+
+    w1 = torch.arange(32).float().view(16, 2)
+    w2 = -w1
+    p = interleave8(w1, w2)
+    assert torch.equal(p[:8], w1[:8]) and torch.equal(p[8:16], w2[:8]) and torch.equal(p[16:24], w1[8:])
+
+
+def test_rope_table_matches_oracle():
+    from oracle import vtp_oracle as vo
+    from vtp_b200.rope import rope_periods, rope_sincos
+
+    per = rope_periods(64)
+    assert torch.equal(per, vo.rope_periods(64))
+    s, c = rope_sincos(16, 16, per)
+    so, co = vo.rope_table(16, 16, per)
+    assert torch.equal(s, so) and torch.equal(c, co) and s.dtype == torch.bfloat16

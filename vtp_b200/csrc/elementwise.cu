@@ -221,6 +221,42 @@ __global__ void gather_rows_kernel(const TI* __restrict__ in, TO* __restrict__ o
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------ text embedding
+// out[b*L + l][:] = emb[ids[b][l]][:] + pos[l][:]   (vtp_hf/modeling_vtp.py:297-298)
+__global__ void embed_tokens_kernel(const long long* __restrict__ ids, const float* __restrict__ emb,
+                                    const float* __restrict__ pos, float* __restrict__ out, long BL, int L, int D) {
+    const long total = BL * (D / 4);
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long r = t / (D / 4);
+        const int c = (int)(t % (D / 4)) * 4;
+        const float4 e = __ldg(reinterpret_cast<const float4*>(emb + ids[r] * D + c));
+        const float4 q = __ldg(reinterpret_cast<const float4*>(pos + (r % L) * D + c));
+        *reinterpret_cast<float4*>(out + r * D + c) = make_float4(e.x + q.x, e.y + q.y, e.z + q.z, e.w + q.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ L2 normalise
+// y = x / max(||x||_2, eps) per row (F.normalize, vtp_hf/modeling_vtp.py:276,310; heads/dino_head.py:83-84).
+// One warp per row; x fp32|bf16 [M][D], y fp32|bf16; optional norm_out [M] (saved for backward).
+template <typename TI, typename TO>
+__global__ void l2norm_kernel(const TI* __restrict__ x, TO* __restrict__ y, float* __restrict__ norm_out, int M, int D,
+                              float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    const TI* xr = x + (long)warp * D;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) {
+        const float v = (float)xr[c];
+        s += v * v;
+    }
+    s = warp_sum(s);
+    const float nrm = sqrtf(s);
+    const float inv = 1.f / fmaxf(nrm, eps);
+    if (lane == 0 && norm_out) norm_out[warp] = nrm;
+    for (int c = lane; c < D; c += 32) y[(long)warp * D + c] = (TO)((float)xr[c] * inv);
+}
+
 static inline int grid_for(long total, int block) {
     long g = (total + block - 1) / block;
     long cap = (long)num_sms() * 16;
@@ -344,6 +380,33 @@ extern "C" int vtp_gather_rows(const void* in, int in_dtype, long ld_in, void* o
     else
         gather_rows_kernel<__nv_bfloat16, __nv_bfloat16>
             <<<g, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, ix, n, D, ld_in, ld_out);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_embed_tokens(const int64_t* ids, const float* emb, const float* pos, float* out, long BL, int L, int D,
+                                vtp_stream_t st) {
+    VTP_CHECK_ARG(ids && emb && pos && out && BL > 0 && D % 4 == 0, "embed_tokens: bad args");
+    embed_tokens_kernel<<<grid_for(BL * (D / 4), 256), 256, 0, (cudaStream_t)st>>>((const long long*)ids, emb, pos, out,
+                                                                                   BL, L, D);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_l2norm_fwd(const void* x, int x_dtype, void* y, int y_dtype, float* norm_out, int M, int D, float eps,
+                              vtp_stream_t st) {
+    VTP_CHECK_ARG(x && y && M > 0 && D > 0, "l2norm_fwd: bad args");
+    const int grid = ceil_div(M, 8);
+    cudaStream_t s = (cudaStream_t)st;
+    if (x_dtype == VTP_F32 && y_dtype == VTP_F32)
+        l2norm_kernel<float, float><<<grid, 256, 0, s>>>((const float*)x, (float*)y, norm_out, M, D, eps);
+    else if (x_dtype == VTP_F32)
+        l2norm_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)x, (__nv_bfloat16*)y, norm_out, M, D, eps);
+    else if (y_dtype == VTP_F32)
+        l2norm_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (float*)y, norm_out, M, D, eps);
+    else
+        l2norm_kernel<__nv_bfloat16, __nv_bfloat16>
+            <<<grid, 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, norm_out, M, D, eps);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

@@ -58,6 +58,9 @@ SIGNATURES: dict[str, tuple] = {
                                         C.c_int, C.c_void_p]),
     "vtp_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int,
                                   C.c_int, C.c_void_p]),
+    "vtp_embed_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_l2norm_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                                 C.c_void_p]),
     "vtp_attention_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p]),
     "vtp_attention_fwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -191,3 +194,14 @@ def attention_fwd(qkv, out, B: int, T: int, H: int, *, prefix: int, causal: bool
 def attention_fwd_f32(qkv, out, B: int, T: int, H: int, *, causal: bool = False, stream=None):
     check(load().vtp_attention_fwd_f32(_ptr(qkv), _ptr(out), B, T, H, int(causal), _st(stream)),
           "vtp_attention_fwd_f32")
+
+
+def embed_tokens(ids, emb, pos, out, stream=None):
+    B, L = ids.shape
+    check(load().vtp_embed_tokens(_ptr(ids), _ptr(emb), _ptr(pos), _ptr(out), B * L, L, emb.shape[1], _st(stream)),
+          "vtp_embed_tokens")
+
+
+def l2norm_fwd(x, y, M: int, D: int, eps: float = 1e-12, norm_out=None, stream=None):
+    check(load().vtp_l2norm_fwd(_ptr(x), _dt(x), _ptr(y), _dt(y), _ptr(norm_out), M, D, eps, _st(stream)),
+          "vtp_l2norm_fwd")
