@@ -57,7 +57,8 @@ typedef struct {
     int ldr, resid_dtype;
     int accumulate;         /* 1: atomic fp32 add into out (required when split_k > 1) */
     int split_k;            /* >=1: split the reduction across CTAs */
-    int rr_group, rr_skip;  /* out_row = (row/rr_group)*(rr_group+rr_skip) + rr_skip + row%rr_group; 0 = identity */
+    int rr_group, rr_skip;  /* rr_skip>0: out_row = (row/rr_group)*(rr_group+rr_skip) + rr_skip + row%rr_group (cls slot);
+                             * rr_skip<0: drop the first -rr_skip rows of every rr_group rows (compaction); 0 = identity */
     const void* rope_sin;   /* VTP_ACT_ROPE: bf16 [rope_tokens-rope_prefix][64] tables (layers/embeddings.py:131-180) */
     const void* rope_cos;
     int rope_tokens, rope_prefix, rope_cols; /* tokens/sequence, un-rotated prefix tokens, leading columns rotated (2*D) */
@@ -113,6 +114,56 @@ int vtp_attention_fwd(const void* qkv, void* out, float* lse, int B, int T, int 
                       vtp_stream_t stream);
 /* same op on fp32 tensors (CUDA cores) for the fp32-accurate inference mode */
 int vtp_attention_fwd_f32(const float* qkv, float* out, int B, int T, int H, int causal, vtp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Training step (the reference releases no training loop — SURVEY.md M3/a21; these are the autograd duals of the
+ * forward stages above plus restated losses and a fused optimiser)
+ * ------------------------------------------------------------------------------------------------------------ */
+/* dual of vtp_attention_fwd incl. the RoPE rotation (layers/attention.py:70-89,110-126): dqkv = d/d(pre-RoPE qkv) */
+int vtp_attention_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
+                      const void* rope_sin, const void* rope_cos, int B, int T, int H, int prefix, int causal,
+                      vtp_stream_t stream);
+/* dual of vtp_norm_fwd: g[M][D] (fp32 stream gradient) += dx ; dw[D] += ; db[D] += (LayerNorm) */
+int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const float* mean, const float* w, const void* dy_bf16,
+                 float* g, float* dw, float* db, int M, int D, int is_ln, vtp_stream_t stream);
+/* dual of the SwiGLU gate epilogue (layers/ffn.py:77-81): pre [M][2Hs] 8-interleaved, dhid [M][Hs] -> dpre, dbias */
+int vtp_swiglu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int Hs, vtp_stream_t stream);
+/* dual of the GELU epilogue (text MLP layers/block.py:399-403, DINO head heads/dino_head.py:92-126) */
+int vtp_gelu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int N, vtp_stream_t stream);
+/* y_bf16[M][N] = cast(x[M][ldx]) (optional) ; colsum[N] += column sums (bias gradients) (optional) */
+int vtp_cast_colsum(const void* x, int x_dtype, long ldx, void* y_bf16, float* colsum, int M, int N, vtp_stream_t stream);
+/* dual of vtp_l2norm_fwd */
+int vtp_l2norm_bwd(const void* y, int y_dtype, const float* nrm, const float* dy, void* dx, int dx_dtype, int M, int D,
+                   float eps, vtp_stream_t stream);
+/* dst[idx[i]][:] += src[i][:] (fp32 atomics): dual of vtp_gather_rows / vtp_embed_tokens */
+int vtp_scatter_add_rows(const void* src, int src_dtype, long ld_src, float* dst, long ld_dst, const int64_t* idx, int n,
+                         int D, vtp_stream_t stream);
+/* g fp32 [B*T][D] -> bf16 [B*(T-prefix)][D] without the prefix rows (+ dcls[prefix][D] += their sum): dual of the
+ * cls concat (encoders/vision_transformer.py:198-217), operand of the patch-embed wgrad */
+int vtp_strip_prefix(const float* g, void* out_bf16, float* dcls, int B, int T, int prefix, int D, vtp_stream_t stream);
+/* fused multi-tensor AdamW on a flat fp32 master buffer: also zeroes grad, refreshes the bf16 compute copy and the EMA
+ * teacher (vtp.py:388-401: teacher = m*teacher + (1-m)*student) in the same pass */
+int vtp_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, float* teacher, void* teacher_bf16, long n,
+                   float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                   float ema_momentum, vtp_stream_t stream);
+int vtp_cast_f32_to_bf16(const float* x, void* y, long n, vtp_stream_t stream);
+int vtp_axpby(float* y, const float* x, float a, float b, long n, vtp_stream_t stream);
+/* OpenCLIP ClipLoss row-wise softmax-CE on a similarity block: loss, d(log-scale) and G = dL/dlogits (bf16) */
+int vtp_softmax_ce(const float* logits, long ld, int R, int C, int label0, void* G_bf16, long ldg, float coef,
+                   float* loss_acc, float* dscale_acc, vtp_stream_t stream);
+/* DINOv2 centred+sharpened teacher softmax, in place on bf16 logits [R][K] */
+int vtp_dino_teacher_probs(void* t_bf16, const float* center, int R, int K, float temp, vtp_stream_t stream);
+/* DINOv2 DINOLoss/iBOTPatchLoss cross-entropy of student logits [R][K] vs up to two teacher rows: loss + in-place grad */
+int vtp_dino_student_ce(void* s_bf16, const void* tprobs_bf16, const int* t0, const int* t1, const float* w, int R, int K,
+                        float temp, float* loss_acc, vtp_stream_t stream);
+/* pixel L1 loss + gradient (+ optional extra NCHW gradient, e.g. LPIPS), written pixel-unshuffled as the bf16 dY of
+ * proj_out (decoders/pixel_decoder.py:157-160) */
+int vtp_recon_l1_grad(const void* rec, int rec_dtype, const float* tgt, const float* dlp, void* out_bf16, float* loss_acc,
+                      int B, int C, int gh, int gw, int r, float coef, vtp_stream_t stream);
+/* heads/dino_head.py:48-49 weight_norm(dim=0): W[k,:] = g[k] v[k,:]/||v[k,:]|| (bf16) and its dual */
+int vtp_weight_norm_fwd(const float* v, const float* g, void* w_bf16, float* vnorm, int K, int D, vtp_stream_t stream);
+int vtp_weight_norm_bwd(const float* v, const float* g, const float* vnorm, const float* dW, float* dv, float* dg, int K,
+                        int D, vtp_stream_t stream);
 
 #ifdef __cplusplus
 }

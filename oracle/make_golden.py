@@ -69,13 +69,27 @@ def main():
                         out[f"txt_feat_{tag}"] = ft.float().numpy()
                         lg, _ = m.get_clip_logits(x, ids)
                         out[f"logits_{tag}"] = lg.float().numpy()
+        # conditioning of the REFERENCE ITSELF: response of each fp32 output to a 1e-6 relative input perturbation.
+        # (bf16 roundings inside the fp32 path — RoPE, layers/attention.py:74-89 — make some outputs, notably the cls
+        # token, discontinuous; an independent implementation cannot agree better than this floor.)
+        with torch.no_grad():
+            xp = x * (1 + 1e-6)
+            relf = lambda a, b: float(((a.float() - torch.from_numpy(b)).norm() / torch.from_numpy(b).norm()))
+            latp = m.get_reconstruction_latents(xp)
+            sens = {"latents": relf(latp, out["latents_fp32"]),
+                    "recon": relf(m.get_latents_decoded_images(latp), out["recon_fp32"]),
+                    "img_feat": relf(m.get_clip_image_feature(xp), out["img_feat_fp32"]),
+                    "cls": relf(m.get_last_layer_feature(xp)["cls_token"], out["cls_fp32"])}
+            if with_text:
+                sens["logits"] = relf(m.get_clip_logits(xp, ids)[0], out["logits_fp32"])
         out["ids"] = ids.numpy()
         out["x_checksum"] = np.array([x.double().sum().item(), x.double().abs().sum().item()])
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
         with open(os.path.join(OUT, f"{name}.json"), "w") as f:
             json.dump({"config": kw, "batch": B, "image_size": size, "spec": spec,
-                       "reference_commit": "5ce1eb6", "torch": torch.__version__}, f)
-        print(name, {k: v.shape for k, v in out.items()})
+                       "reference_commit": "5ce1eb6", "torch": torch.__version__,
+                       "ref_sensitivity_1e-6": sens}, f)
+        print(name, "reference sensitivity to 1e-6 input perturbation:", sens)
 
 
 if __name__ == "__main__":

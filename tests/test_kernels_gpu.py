@@ -51,7 +51,7 @@ def test_norm_fwd(D, ln, in_bf16):
     assert _rel(y16, ref.to(BF)) < 2e-3
     hi, hi2, lo = y3[:, :D].float(), y3[:, D:2 * D].float(), y3[:, 2 * D:].float()
     assert torch.equal(hi, hi2)
-    assert _rel(hi + lo, ref) < 2e-5
+    assert _rel(hi + lo, ref) < (1e-4 if in_bf16 else 2e-5)
 
 
 def test_split3_gemm_is_fp32_accurate():

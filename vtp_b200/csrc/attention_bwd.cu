@@ -1,0 +1,474 @@
+// vtp_b200 — fused self-attention BACKWARD for short sequences (T = prefix + HW, prefix <= 1, HW <= 256) on tcgen05.
+//
+// Gradient of layers/attention.py:110-126 (RoPE + SDPA) w.r.t. the packed pre-RoPE qkv projection output:
+//   P = exp(s·QKᵀ − lse)      dV = Pᵀ dO      dP = dO Vᵀ      dS = s · P ∘ (dP − δ),  δ_i = Σ_d dO_id O_id
+//   dQ = dS K                 dK = dSᵀ Q      then RoPEᵀ on dQ, dK (rotation is linear: layers/attention.py:12-23)
+//
+// One CTA per (head, image).  All five GEMMs run on tcgen05 with the operands exactly as TMA lands them (128-row x
+// 64-col bf16 tiles of Q, K, V out of the packed qkv buffer and of dO): the transposes are expressed through the UMMA
+// major-ness bits —  Pᵀ / dSᵀ are MN-major A operands read from the same swizzled smem tile that serves dS as a K-major
+// A operand for dQ; dO, Q, K are MN-major B operands.  Work is split in (key half kh, query tile t) steps:
+//   MMA1: S = Q_t K_khᵀ, dP = dO_t V_khᵀ   (TMEM cols 256..511)      -> 128 row-threads build P, dS (bf16, smem)
+//   MMA2: dV_kh += Pᵀ dO_t, dK_kh += dSᵀ Q_t (TMEM 0..127), dQ_t += dS K_kh (TMEM 128..255)
+// TMEM: dK|dV (128) + dQ_0|dQ_1 (128) + S|dP (256) = 512 columns.
+// The cls token (prefix) is handled on CUDA cores as in the forward kernel: as an extra key column by the row threads
+// (rank-1 updates + a warp-reduced column for dK_0/dV_0) and as an extra query row by a spare warp.
+#include "host.h"
+#include "ptx.cuh"
+
+namespace vtp {
+
+static constexpr int AB_THREADS = 192;
+static constexpr int BQ = 0, BK_ = 32768, BV = 65536, BDO = 98304, BP = 131072, BDS = 163840, BX = 196608;
+// extras after BX: p0[264] | ds0[264] | dk0[64] | dv0[64] | barriers
+static constexpr int X_P0 = 0, X_DS0 = 1056, X_DK0 = 2112, X_DV0 = 2368, X_BAR = 2624;
+static constexpr int AB_SMEM = BX + X_BAR + 128;
+
+struct AttnBwdDev {
+    const __nv_bfloat16* qkv;   // [B*T][3D] post-RoPE q,k ; v
+    const __nv_bfloat16* o;     // [B*T][D]
+    const __nv_bfloat16* dout;  // [B*T][D]
+    const float* lse;           // [B][H][T]
+    __nv_bfloat16* dqkv;        // [B*T][3D] gradient w.r.t. the PRE-RoPE qkv
+    const __nv_bfloat16* rope_sin;  // [HW][64] or null (no RoPE: text tower)
+    const __nv_bfloat16* rope_cos;
+    int B, T, H, D, prefix, HW, causal, nkt;
+    float scale, scale_log2;
+};
+
+__device__ __forceinline__ uint32_t sw_off(int row, int col) {
+    return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
+}
+__device__ __forceinline__ void load_row64(const uint8_t* tile, int row, float (&f)[64]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 w = *reinterpret_cast<const uint4*>(tile + sw_off(row, c * 8));
+        f[c * 8 + 0] = bf16_lo(w.x), f[c * 8 + 1] = bf16_hi(w.x), f[c * 8 + 2] = bf16_lo(w.y), f[c * 8 + 3] = bf16_hi(w.y);
+        f[c * 8 + 4] = bf16_lo(w.z), f[c * 8 + 5] = bf16_hi(w.z), f[c * 8 + 6] = bf16_lo(w.w), f[c * 8 + 7] = bf16_hi(w.w);
+    }
+}
+__device__ __forceinline__ void load_grow64(const __nv_bfloat16* g, float (&f)[64]) {
+    const uint4* p = reinterpret_cast<const uint4*>(g);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 w = __ldg(p + c);
+        f[c * 8 + 0] = bf16_lo(w.x), f[c * 8 + 1] = bf16_hi(w.x), f[c * 8 + 2] = bf16_lo(w.y), f[c * 8 + 3] = bf16_hi(w.y);
+        f[c * 8 + 4] = bf16_lo(w.z), f[c * 8 + 5] = bf16_hi(w.z), f[c * 8 + 6] = bf16_lo(w.w), f[c * 8 + 7] = bf16_hi(w.w);
+    }
+}
+__device__ __forceinline__ void store_row64(__nv_bfloat16* g, const float (&f)[64]) {
+    uint4* p = reinterpret_cast<uint4*>(g);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint4 w;
+        w.x = pack_bf16x2(f[c * 8], f[c * 8 + 1]), w.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
+        w.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), w.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
+        p[c] = w;
+    }
+}
+// dx = RoPEᵀ dy :  dx[i] = dy[i] cos[i] + dy[i+32] sin[i+32] ;  dx[i+32] = dy[i+32] cos[i+32] − dy[i] sin[i]
+__device__ __forceinline__ void rope_bwd64(float (&g)[64], const __nv_bfloat16* sin_row, const __nv_bfloat16* cos_row) {
+    float sn[64], cs[64];
+    load_grow64(sin_row, sn);
+    load_grow64(cos_row, cs);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        const float a = g[i], b = g[i + 32];
+        g[i] = a * cs[i] + b * sn[i + 32];
+        g[i + 32] = b * cs[i + 32] - a * sn[i];
+    }
+}
+
+__global__ void __launch_bounds__(AB_THREADS, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const AttnBwdDev p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (smem_u32(smem) & 1023) __trap();
+    float* p0 = reinterpret_cast<float*>(smem + BX + X_P0);
+    float* ds0 = reinterpret_cast<float*>(smem + BX + X_DS0);
+    float* dk0 = reinterpret_cast<float*>(smem + BX + X_DK0);
+    float* dv0 = reinterpret_cast<float*>(smem + BX + X_DV0);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BX + X_BAR);
+    uint64_t* bar_ld = bars + 0;       // [2] tile loads
+    uint64_t* bar_sdp = bars + 2;      // S,dP in TMEM
+    uint64_t* bar_pds = bars + 3;      // P,dS in smem (128 arrivals), S/dP TMEM consumed
+    uint64_t* bar_mma2 = bars + 4;     // dV/dK/dQ MMAs of a step complete
+    uint64_t* bar_accfree = bars + 5;  // dK/dV accumulators drained by the epilogue (128 arrivals)
+    uint64_t* bar_cls = bars + 6;      // p0/ds0 rows written by the cls warp
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.x, b = blockIdx.y;
+    const int D = p.D, T = p.T, prefix = p.prefix, HW = p.HW, nkt = p.nkt;
+    const long row0 = (long)b * T;
+    const int nsteps = nkt * nkt;
+    const float lse_l2 = 1.4426950408889634f;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm_qkv);
+        tma_prefetch_desc(&tm_do);
+        mbar_init(&bar_ld[0], 1), mbar_init(&bar_ld[1], 1), mbar_init(bar_sdp, 1), mbar_init(bar_pds, 128);
+        mbar_init(bar_mma2, 1), mbar_init(bar_accfree, 128), mbar_init(bar_cls, 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 128) dk0[threadIdx.x & 63] = 0.f, dv0[threadIdx.x & 63] = 0.f;
+    if (warp == 4) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    // TMEM columns
+    const uint32_t C_DV = 0, C_DK = 64, C_DQ = 128 /* + 64*t */, C_S = 256, C_DP = 384;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // ------------------------------------------------ TMA: tile i = rows [128i, 128i+128) of Q,K,V,dO
+            for (int i = 0; i < nkt; ++i) {
+                const int r = (int)row0 + prefix + 128 * i;
+                mbar_expect_tx(&bar_ld[i], 4 * 16384);
+                tma_load_2d(smem + BQ + i * 16384, &tm_qkv, &bar_ld[i], h * 64, r);
+                tma_load_2d(smem + BK_ + i * 16384, &tm_qkv, &bar_ld[i], D + h * 64, r);
+                tma_load_2d(smem + BV + i * 16384, &tm_qkv, &bar_ld[i], 2 * D + h * 64, r);
+                tma_load_2d(smem + BDO + i * 16384, &tm_do, &bar_ld[i], h * 64, r);
+            }
+            const uint32_t id_nt = umma_idesc_bf16(128, 128, 0, 0);  // S, dP: A K-major, B K-major
+            const uint32_t id_tn = umma_idesc_bf16(128, 64, 1, 1);   // dV, dK: A MN-major (Pᵀ), B MN-major
+            const uint32_t id_nn = umma_idesc_bf16(128, 64, 0, 1);   // dQ: A K-major (dS), B MN-major (K)
+            const uint32_t aQ = smem_u32(smem + BQ), aK = smem_u32(smem + BK_), aV = smem_u32(smem + BV);
+            const uint32_t aDO = smem_u32(smem + BDO), aP = smem_u32(smem + BP), aDS = smem_u32(smem + BDS);
+            auto mma1 = [&](int kh, int t) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    umma_bf16_ss(tmem + C_S, umma_desc_sw128(aQ + t * 16384 + j * 32, 0, 1024),
+                                 umma_desc_sw128(aK + kh * 16384 + j * 32, 0, 1024), id_nt, j > 0);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    umma_bf16_ss(tmem + C_DP, umma_desc_sw128(aDO + t * 16384 + j * 32, 0, 1024),
+                                 umma_desc_sw128(aV + kh * 16384 + j * 32, 0, 1024), id_nt, j > 0);
+                umma_commit(bar_sdp);
+            };
+            mbar_wait(&bar_ld[0], 0);
+            tc_fence_after();
+            mma1(0, 0);
+            bool ld1_waited = false;
+            for (int n = 0; n < nsteps; ++n) {
+                const int kh = n / nkt, t = n % nkt;
+                mbar_wait(bar_pds, n & 1);
+                tc_fence_after();
+                if (n + 1 < nsteps) {
+                    if (!ld1_waited) mbar_wait(&bar_ld[1], 0), ld1_waited = true;
+                    mma1((n + 1) / nkt, (n + 1) % nkt);
+                }
+                if (kh > 0 && t == 0) {  // dK/dV accumulators of the previous key half must be drained
+                    mbar_wait(bar_accfree, (kh - 1) & 1);
+                    tc_fence_after();
+                }
+                // P / dS tile: [128 q][128 keys] as 2 chunks of 64 keys.  As MN-major A (M = keys): LBO = chunk
+                // stride 16384, SBO = 1024 (8 queries), K-step of 16 queries = 2048 B.  As K-major A (M = queries):
+                // k-step 32 B inside a chunk, next chunk +16384.
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {  // reduction over 128 queries
+                    const uint64_t bdo = umma_desc_sw128(aDO + t * 16384 + j * 2048, 8192, 1024);
+                    const uint64_t bq = umma_desc_sw128(aQ + t * 16384 + j * 2048, 8192, 1024);
+                    umma_bf16_ss(tmem + C_DV, umma_desc_sw128(aP + j * 2048, 16384, 1024), bdo, id_tn, (t > 0 || j > 0));
+                    umma_bf16_ss(tmem + C_DK, umma_desc_sw128(aDS + j * 2048, 16384, 1024), bq, id_tn, (t > 0 || j > 0));
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {  // reduction over 128 keys
+                    const uint64_t ads = umma_desc_sw128(aDS + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024);
+                    const uint64_t bk = umma_desc_sw128(aK + kh * 16384 + j * 2048, 8192, 1024);
+                    umma_bf16_ss(tmem + C_DQ + 64 * t, ads, bk, id_nn, (kh > 0 || j > 0));
+                }
+                umma_commit(bar_mma2);
+            }
+        }
+    } else if (warp < 4) {
+        // ---------------------------------------------------- row threads
+        const int r = warp * 32 + lane;
+        const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
+        float lse_i[2], delta_i[2], p_i0[2], ds_i0[2];
+        const __nv_bfloat16* kcls = p.qkv + row0 * 3 * D + D + h * 64;
+        const __nv_bfloat16* vcls = p.qkv + row0 * 3 * D + 2 * D + h * 64;
+
+        for (int n = 0; n < nsteps; ++n) {
+            const int kh = n / nkt, t = n % nkt;
+            const int qi = 128 * t + r;  // patch index of my query row in this step
+            const bool qvalid = qi < HW;
+            if (kh == 0) {
+                // per-query-tile scalars (first visit of tile t): lse, delta = dO·O, and the cls-key column
+                mbar_wait(&bar_ld[t], 0);
+                lse_i[t] = 0.f, delta_i[t] = 0.f, p_i0[t] = 0.f, ds_i0[t] = 0.f;
+                if (qvalid) {
+                    const long grow = row0 + prefix + qi;
+                    lse_i[t] = p.lse[((long)b * p.H + h) * T + prefix + qi];
+                    float dof[64], tmpf[64];
+                    load_row64(smem + BDO + t * 16384, r, dof);
+                    load_grow64(p.o + grow * D + h * 64, tmpf);
+                    float dl = 0.f;
+#pragma unroll
+                    for (int d = 0; d < 64; ++d) dl += dof[d] * tmpf[d];
+                    delta_i[t] = dl;
+                    if (prefix > 0) {
+                        float qf[64];
+                        load_row64(smem + BQ + t * 16384, r, qf);
+                        load_grow64(kcls, tmpf);
+                        float s0 = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 64; ++d) s0 += qf[d] * tmpf[d];
+                        load_grow64(vcls, tmpf);
+                        float dp0 = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 64; ++d) dp0 += dof[d] * tmpf[d];
+                        const float pp = exp2f(s0 * p.scale_log2 - lse_i[t] * lse_l2);
+                        p_i0[t] = pp;
+                        ds_i0[t] = p.scale * pp * (dp0 - dl);
+                    }
+                }
+                if (prefix > 0) {
+                    // column reductions for the cls key: dV_0 += Σ_i p_i0 dO_i ;  dK_0 += Σ_i ds_i0 q_i
+                    float dof[64], qf[64];
+                    load_row64(smem + BDO + t * 16384, r, dof);
+                    load_row64(smem + BQ + t * 16384, r, qf);
+                    const float pb = bf16_round(p_i0[t]), db = bf16_round(ds_i0[t]);
+#pragma unroll
+                    for (int d = 0; d < 64; ++d) {
+                        const float a = warp_sum(pb * dof[d]);
+                        const float c = warp_sum(db * qf[d]);
+                        if (lane == (d & 31)) atomicAdd(&dv0[d], a), atomicAdd(&dk0[d], c);
+                    }
+                }
+            }
+            mbar_wait(bar_sdp, n & 1);
+            tc_fence_after();
+            if (n > 0) mbar_wait(bar_mma2, (n - 1) & 1);  // P/dS smem tiles free again
+            const int kmax = p.causal ? min(HW, qi + 1) : HW;
+            const float lsc = lse_i[t] * lse_l2, dl = delta_i[t];
+#pragma unroll 1
+            for (int c32 = 0; c32 < 4; ++c32) {
+                uint32_t rs[32], rd[32];
+                tmem_ld_32x32(trow + C_S + c32 * 32, rs);
+                tmem_ld_32x32(trow + C_DP + c32 * 32, rd);
+                tmem_ld_wait();
+                uint32_t pk[16], dk[16];
+                const int kbase = 128 * kh + c32 * 32;
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                    float pa = 0.f, pb = 0.f, da = 0.f, db = 0.f;
+                    if (qvalid && kbase + i < kmax) {
+                        pa = exp2f(__uint_as_float(rs[i]) * p.scale_log2 - lsc);
+                        da = p.scale * pa * (__uint_as_float(rd[i]) - dl);
+                    }
+                    if (qvalid && kbase + i + 1 < kmax) {
+                        pb = exp2f(__uint_as_float(rs[i + 1]) * p.scale_log2 - lsc);
+                        db = p.scale * pb * (__uint_as_float(rd[i + 1]) - dl);
+                    }
+                    pk[i >> 1] = pack_bf16x2(pa, pb);
+                    dk[i >> 1] = pack_bf16x2(da, db);
+                }
+                uint8_t* pb_ = smem + BP + (c32 >> 1) * 16384;
+                uint8_t* db_ = smem + BDS + (c32 >> 1) * 16384;
+#pragma unroll
+                for (int v4 = 0; v4 < 4; ++v4) {
+                    const uint32_t off = sw_off(r, (c32 & 1) * 32 + v4 * 8);
+                    *reinterpret_cast<uint4*>(pb_ + off) = make_uint4(pk[v4 * 4], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
+                    *reinterpret_cast<uint4*>(db_ + off) = make_uint4(dk[v4 * 4], dk[v4 * 4 + 1], dk[v4 * 4 + 2], dk[v4 * 4 + 3]);
+                }
+            }
+            tc_fence_before();
+            fence_proxy_async_smem();
+            mbar_arrive(bar_pds);
+
+            if (t == nkt - 1) {
+                // ------------ epilogue of key half kh: I own key row kj = 128*kh + r
+                mbar_wait(bar_mma2, n & 1);
+                tc_fence_after();
+                const int kj = 128 * kh + r;
+                uint32_t a0[32], a1[32];
+                float g[64];
+                if (prefix > 0) mbar_wait(bar_cls, 0);
+                // dV
+                tmem_ld_32x32(trow + C_DV, a0);
+                tmem_ld_32x32(trow + C_DV + 32, a1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(a0[i]), g[32 + i] = __uint_as_float(a1[i]);
+                if (kj < HW) {
+                    if (prefix > 0) {
+                        float f[64];
+                        load_grow64(p.dout + row0 * D + h * 64, f);  // dO of the cls query
+                        const float pc = bf16_round(p0[kj]);
+#pragma unroll
+                        for (int d = 0; d < 64; ++d) g[d] += pc * f[d];
+                    }
+                    store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + 2 * D + h * 64, g);
+                }
+                // dK
+                tmem_ld_32x32(trow + C_DK, a0);
+                tmem_ld_32x32(trow + C_DK + 32, a1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(a0[i]), g[32 + i] = __uint_as_float(a1[i]);
+                tc_fence_before();
+                mbar_arrive(bar_accfree);
+                if (kj < HW) {
+                    if (prefix > 0) {
+                        float f[64];
+                        load_grow64(p.qkv + row0 * 3 * D + h * 64, f);  // q of the cls query
+                        const float dc = bf16_round(ds0[kj]);
+#pragma unroll
+                        for (int d = 0; d < 64; ++d) g[d] += dc * f[d];
+                    }
+                    if (p.rope_sin) rope_bwd64(g, p.rope_sin + (long)kj * 64, p.rope_cos + (long)kj * 64);
+                    store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + D + h * 64, g);
+                }
+            }
+        }
+        // ------------ dQ epilogue (all steps done; last bar_mma2 phase already observed above)
+        for (int t = 0; t < nkt; ++t) {
+            const int qi = 128 * t + r;
+            uint32_t a0[32], a1[32];
+            tmem_ld_32x32(trow + C_DQ + 64 * t, a0);
+            tmem_ld_32x32(trow + C_DQ + 64 * t + 32, a1);
+            tmem_ld_wait();
+            if (qi < HW) {
+                float g[64];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(a0[i]), g[32 + i] = __uint_as_float(a1[i]);
+                if (prefix > 0) {
+                    float f[64];
+                    load_grow64(kcls, f);
+                    const float dc = bf16_round(ds_i0[t]);
+#pragma unroll
+                    for (int d = 0; d < 64; ++d) g[d] += dc * f[d];
+                }
+                if (p.rope_sin) rope_bwd64(g, p.rope_sin + (long)qi * 64, p.rope_cos + (long)qi * 64);
+                store_row64(p.dqkv + (row0 + prefix + qi) * 3 * D + h * 64, g);
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ---------------------------------------------------- warp 5: the cls query row (prefix == 1)
+        if (prefix > 0) {
+            for (int i = 0; i < nkt; ++i) mbar_wait(&bar_ld[i], 0);
+            float q0[64], do0[64];
+            load_grow64(p.qkv + row0 * 3 * D + h * 64, q0);
+            load_grow64(p.dout + row0 * D + h * 64, do0);
+            float delta0 = 0.f;
+            {
+                float o0[64];
+                load_grow64(p.o + row0 * D + h * 64, o0);
+#pragma unroll
+                for (int d = 0; d < 64; ++d) delta0 += do0[d] * o0[d];
+            }
+            const float lse0 = p.lse[((long)b * p.H + h) * T] * lse_l2;
+            for (int i = 0; i < 8; ++i) {
+                const int kj = lane + 32 * i;
+                if (kj < 128 * nkt) {
+                    float pv = 0.f, dsv = 0.f;
+                    if (kj < HW) {
+                        float f[64];
+                        load_row64(smem + BK_, kj, f);  // K tiles are contiguous: row kj of [256][128B]
+                        float s = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 64; ++d) s += q0[d] * f[d];
+                        load_row64(smem + BV, kj, f);
+                        float dp = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 64; ++d) dp += do0[d] * f[d];
+                        pv = exp2f(s * p.scale_log2 - lse0);
+                        dsv = p.scale * pv * (dp - delta0);
+                    }
+                    p0[kj] = pv, ds0[kj] = dsv;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_cls);
+            // cls-cls term
+            float kc[64], vc[64];
+            load_grow64(p.qkv + row0 * 3 * D + D + h * 64, kc);
+            load_grow64(p.qkv + row0 * 3 * D + 2 * D + h * 64, vc);
+            float s00 = 0.f, dp00 = 0.f;
+#pragma unroll
+            for (int d = 0; d < 64; ++d) s00 += q0[d] * kc[d], dp00 += do0[d] * vc[d];
+            const float p00 = exp2f(s00 * p.scale_log2 - lse0);
+            const float ds00 = p.scale * p00 * (dp00 - delta0);
+            // dQ_0[d] = Σ_j ds_0j k_j[d] + ds_00 k_0[d]; lane owns dims 2*lane, 2*lane+1
+            float a0 = 0.f, a1 = 0.f;
+            for (int kj = 0; kj < HW; ++kj) {
+                const float dsv = ds0[kj];
+                const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + BK_ + sw_off(kj, 2 * lane));
+                a0 += dsv * bf16_lo(w), a1 += dsv * bf16_hi(w);
+            }
+            {
+                const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p.qkv + row0 * 3 * D + D + h * 64) + lane);
+                a0 += ds00 * bf16_lo(w), a1 += ds00 * bf16_hi(w);
+            }
+            *reinterpret_cast<uint32_t*>(p.dqkv + row0 * 3 * D + h * 64 + 2 * lane) = pack_bf16x2(a0, a1);
+            // stash p00/ds00 for the final dK_0/dV_0 write
+            if (lane == 0) p0[260] = p00, ds0[260] = ds00;
+        }
+    }
+
+    __syncthreads();
+    if (warp == 5 && prefix > 0) {
+        // dV_0 = Σ_i p_i0 dO_i (+ p_00 dO_0) ;  dK_0 = Σ_i ds_i0 q_i (+ ds_00 q_0)   — cls key row, no RoPE
+        const float p00 = p0[260], ds00 = ds0[260];
+        const uint32_t wdo = __ldg(reinterpret_cast<const uint32_t*>(p.dout + row0 * D + h * 64) + lane);
+        const uint32_t wq = __ldg(reinterpret_cast<const uint32_t*>(p.qkv + row0 * 3 * D + h * 64) + lane);
+        const float v0 = dv0[2 * lane] + p00 * bf16_lo(wdo), v1 = dv0[2 * lane + 1] + p00 * bf16_hi(wdo);
+        const float k0 = dk0[2 * lane] + ds00 * bf16_lo(wq), k1 = dk0[2 * lane + 1] + ds00 * bf16_hi(wq);
+        *reinterpret_cast<uint32_t*>(p.dqkv + row0 * 3 * D + 2 * D + h * 64 + 2 * lane) = pack_bf16x2(v0, v1);
+        *reinterpret_cast<uint32_t*>(p.dqkv + row0 * 3 * D + D + h * 64 + 2 * lane) = pack_bf16x2(k0, k1);
+    }
+    if (warp == 4) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 512);
+    }
+}
+
+}  // namespace vtp
+
+using namespace vtp;
+
+extern "C" int vtp_attention_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
+                                 const void* rope_sin, const void* rope_cos, int B, int T, int H, int prefix, int causal,
+                                 vtp_stream_t st) {
+    VTP_CHECK_ARG(qkv && o && dout && lse && dqkv && B > 0 && T > 0 && H > 0, "attention_bwd: bad args");
+    VTP_CHECK_ARG(prefix == 0 || prefix == 1, "attention_bwd: prefix must be 0 or 1");
+    VTP_CHECK_ARG(!(prefix && causal), "attention_bwd: causal + prefix is not supported");
+    VTP_CHECK_ARG((rope_sin == nullptr) == (rope_cos == nullptr), "attention_bwd: rope tables");
+    const int HW = T - prefix;
+    VTP_CHECK_ARG(HW >= 1 && HW <= 256, "attention_bwd: %d non-prefix tokens not in [1,256]", HW);
+    VTP_CHECK_ARG(B <= 65535, "attention_bwd: grid too large");
+    const int D = H * 64;
+    AttnBwdDev p;
+    p.qkv = (const __nv_bfloat16*)qkv, p.o = (const __nv_bfloat16*)o, p.dout = (const __nv_bfloat16*)dout;
+    p.lse = lse, p.dqkv = (__nv_bfloat16*)dqkv;
+    p.rope_sin = (const __nv_bfloat16*)rope_sin, p.rope_cos = (const __nv_bfloat16*)rope_cos;
+    p.B = B, p.T = T, p.H = H, p.D = D, p.prefix = prefix, p.HW = HW, p.causal = causal;
+    p.nkt = HW > 128 ? 2 : 1;
+    p.scale = 0.125f, p.scale_log2 = 0.125f * 1.4426950408889634f;
+    CUtensorMap tq, td;
+    {
+        uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)B * T}, strides[1] = {(uint64_t)3 * D * 2};
+        uint32_t box[2] = {64, 128};
+        int rc = make_tmap_bf16(&tq, qkv, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)D, (uint64_t)B * T}, strides[1] = {(uint64_t)D * 2};
+        uint32_t box[2] = {64, 128};
+        int rc = make_tmap_bf16(&td, dout, 2, dims, strides, box);
+        if (rc) return rc;
+    }
+    static bool configured = false;
+    if (!configured) {
+        VTP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+        configured = true;
+    }
+    attn_bwd_kernel<<<dim3(H, B), AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, p);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}

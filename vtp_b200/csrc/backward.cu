@@ -1,0 +1,474 @@
+// vtp_b200 — HBM-bound kernels of the training step: norm / SwiGLU / GELU / L2-normalise backward, bias-gradient
+// column sums, gradient casts, embedding scatter, fused AdamW (+ bf16 weight refresh + EMA teacher).
+// The reference publishes no training loop; these are the autograd duals of the forward stages in
+// layers/normalization.py:17-22, layers/ffn.py:77-81, heads/dino_head.py:83-84, vtp.py:388-401 (EMA).
+#include "host.h"
+#include "ptx.cuh"
+
+namespace vtp {
+
+static inline int grid_cap(long n, int block) {
+    long g = (n + block - 1) / block;
+    long cap = (long)num_sms() * 16;
+    return (int)(g < 1 ? 1 : (g < cap ? g : cap));
+}
+
+template <typename T>
+__device__ __forceinline__ void ld4(const T* p, float (&v)[4]);
+template <>
+__device__ __forceinline__ void ld4<float>(const float* p, float (&v)[4]) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x, v[1] = t.y, v[2] = t.z, v[3] = t.w;
+}
+template <>
+__device__ __forceinline__ void ld4<__nv_bfloat16>(const __nv_bfloat16* p, float (&v)[4]) {
+    uint2 t = *reinterpret_cast<const uint2*>(p);
+    v[0] = bf16_lo(t.x), v[1] = bf16_hi(t.x), v[2] = bf16_lo(t.y), v[3] = bf16_hi(t.y);
+}
+
+// ------------------------------------------------------------------------------------------------ norm backward
+// g[m,:] += dx[m,:] where dx is the input-gradient of RMSNorm / LayerNorm given dy (bf16) ; dw += Σ dy∘xhat ; db += Σ dy
+// One warp per row, 8 rows per warp-iteration strip; per-block column partials -> fp32 atomics.
+template <typename TX, int MAXV>
+__global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restrict__ rstd_, const float* __restrict__ mean_,
+                                const float* __restrict__ w, const __nv_bfloat16* __restrict__ dy, float* __restrict__ g,
+                                float* __restrict__ dw, float* __restrict__ db, int M, int D, int rows_per_block,
+                                int is_ln, int x_rounded_bf16) {
+    extern __shared__ float sred[];  // [2][D]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sred[i] = 0.f;
+    __syncthreads();
+    float aw[MAXV][4], ab[MAXV][4];
+#pragma unroll
+    for (int gidx = 0; gidx < MAXV; ++gidx)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) aw[gidx][i] = 0.f, ab[gidx][i] = 0.f;
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(M, r0 + rows_per_block);
+    for (int row = r0 + warp; row < r1; row += nw) {
+        const float rstd = rstd_[row];
+        const float mean = is_ln ? mean_[row] : 0.f;
+        float xh[MAXV][4], dxh[MAXV][4];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int gidx = 0; gidx < MAXV; ++gidx) {
+            const int c = (gidx * 32 + lane) * 4;
+            if (c < D) {
+                float xv[4], dv[4];
+                ld4<TX>(x + (long)row * D + c, xv);
+                ld4<__nv_bfloat16>(dy + (long)row * D + c, dv);
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
+                const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float h = (xv[i] - mean) * rstd;
+                    if (x_rounded_bf16) h = bf16_round(h);
+                    xh[gidx][i] = h;
+                    dxh[gidx][i] = dv[i] * wv[i];
+                    s1 += dxh[gidx][i];
+                    s2 += dxh[gidx][i] * h;
+                    aw[gidx][i] += dv[i] * h;
+                    ab[gidx][i] += dv[i];
+                }
+            }
+        }
+        s1 = warp_sum(s1), s2 = warp_sum(s2);
+        const float m1 = is_ln ? s1 / D : 0.f, m2 = s2 / D;
+#pragma unroll
+        for (int gidx = 0; gidx < MAXV; ++gidx) {
+            const int c = (gidx * 32 + lane) * 4;
+            if (c < D) {
+                float4* gp = reinterpret_cast<float4*>(g + (long)row * D + c);
+                float4 gv = *gp;
+                gv.x += rstd * (dxh[gidx][0] - m1 - xh[gidx][0] * m2);
+                gv.y += rstd * (dxh[gidx][1] - m1 - xh[gidx][1] * m2);
+                gv.z += rstd * (dxh[gidx][2] - m1 - xh[gidx][2] * m2);
+                gv.w += rstd * (dxh[gidx][3] - m1 - xh[gidx][3] * m2);
+                *gp = gv;
+            }
+        }
+    }
+#pragma unroll
+    for (int gidx = 0; gidx < MAXV; ++gidx) {
+        const int c = (gidx * 32 + lane) * 4;
+        if (c < D) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                atomicAdd(&sred[c + i], aw[gidx][i]);
+                if (is_ln) atomicAdd(&sred[D + c + i], ab[gidx][i]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        atomicAdd(dw + i, sred[i]);
+        if (is_ln && db) atomicAdd(db + i, sred[D + i]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ SwiGLU / GELU backward
+// pre packed [M][2Hs] (8-interleaved x1|x2, bf16), dhid [M][Hs] bf16 -> dpre [M][2Hs] bf16 ; dbias[2Hs] += colsum(dpre)
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dhid,
+                                  __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int Hs,
+                                  int rows_per_block) {
+    // thread -> group of 8 hidden columns; loops over the block's rows
+    const int G = Hs / 8;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < G; gidx += gridDim.x * blockDim.x) {
+        float b1[8], b2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b1[i] = 0.f, b2[i] = 0.f;
+        for (int row = r0; row < r1; ++row) {
+            const uint4 x1p = *reinterpret_cast<const uint4*>(pre + (long)row * 2 * Hs + 16 * gidx);
+            const uint4 x2p = *reinterpret_cast<const uint4*>(pre + (long)row * 2 * Hs + 16 * gidx + 8);
+            const uint4 dhp = *reinterpret_cast<const uint4*>(dhid + (long)row * Hs + 8 * gidx);
+            const uint32_t x1w[4] = {x1p.x, x1p.y, x1p.z, x1p.w}, x2w[4] = {x2p.x, x2p.y, x2p.z, x2p.w};
+            const uint32_t dhw[4] = {dhp.x, dhp.y, dhp.z, dhp.w};
+            uint32_t o1[4], o2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float d1[2], d2[2];
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const float x1 = hlf ? bf16_hi(x1w[k]) : bf16_lo(x1w[k]);
+                    const float x2 = hlf ? bf16_hi(x2w[k]) : bf16_lo(x2w[k]);
+                    const float dh = hlf ? bf16_hi(dhw[k]) : bf16_lo(dhw[k]);
+                    const float sg = 1.f / (1.f + __expf(-x1));
+                    const float silu = x1 * sg;
+                    d1[hlf] = dh * x2 * (sg * (1.f + x1 * (1.f - sg)));
+                    d2[hlf] = dh * silu;
+                    b1[2 * k + hlf] += d1[hlf], b2[2 * k + hlf] += d2[hlf];
+                }
+                o1[k] = pack_bf16x2(d1[0], d1[1]), o2[k] = pack_bf16x2(d2[0], d2[1]);
+            }
+            *reinterpret_cast<uint4*>(dpre + (long)row * 2 * Hs + 16 * gidx) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
+            *reinterpret_cast<uint4*>(dpre + (long)row * 2 * Hs + 16 * gidx + 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
+        }
+        if (dbias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(dbias + 16 * gidx + i, b1[i]), atomicAdd(dbias + 16 * gidx + 8 + i, b2[i]);
+        }
+    }
+}
+
+// pre [M][N] bf16, dhid [M][N] bf16 -> dpre = dhid * gelu'(pre) ; dbias[N] += colsum(dpre)
+__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dhid,
+                                __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int N,
+                                int rows_per_block) {
+    const int G = N / 8;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < G; gidx += gridDim.x * blockDim.x) {
+        float bs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) bs[i] = 0.f;
+        for (int row = r0; row < r1; ++row) {
+            const uint4 xp = *reinterpret_cast<const uint4*>(pre + (long)row * N + 8 * gidx);
+            const uint4 dp = *reinterpret_cast<const uint4*>(dhid + (long)row * N + 8 * gidx);
+            const uint32_t xw[4] = {xp.x, xp.y, xp.z, xp.w}, dw[4] = {dp.x, dp.y, dp.z, dp.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float r[2];
+#pragma unroll
+                for (int hlf = 0; hlf < 2; ++hlf) {
+                    const float xv = hlf ? bf16_hi(xw[k]) : bf16_lo(xw[k]);
+                    const float dv = hlf ? bf16_hi(dw[k]) : bf16_lo(dw[k]);
+                    const float cdf = 0.5f * (1.f + erff(xv * 0.70710678118654752f));
+                    const float pdf = 0.3989422804014327f * __expf(-0.5f * xv * xv);
+                    r[hlf] = dv * (cdf + xv * pdf);
+                    bs[2 * k + hlf] += r[hlf];
+                }
+                o[k] = pack_bf16x2(r[0], r[1]);
+            }
+            *reinterpret_cast<uint4*>(dpre + (long)row * N + 8 * gidx) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (dbias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) atomicAdd(dbias + 8 * gidx + i, bs[i]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ cast + column sum
+// y bf16 [M][N] = (bf16) x[M][N] (TX fp32|bf16, row stride ldx) ; colsum[N] += Σ_m x  (bias gradient)
+template <typename TX>
+__global__ void cast_colsum_kernel(const TX* __restrict__ x, long ldx, __nv_bfloat16* __restrict__ y,
+                                   float* __restrict__ colsum, int M, int N, int rows_per_block) {
+    const int G = N / 4;
+    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
+    for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < G; gidx += gridDim.x * blockDim.x) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int row = r0; row < r1; ++row) {
+            float v[4];
+            ld4<TX>(x + (long)row * ldx + 4 * gidx, v);
+            s[0] += v[0], s[1] += v[1], s[2] += v[2], s[3] += v[3];
+            if (y) {
+                uint2 t;
+                t.x = pack_bf16x2(v[0], v[1]), t.y = pack_bf16x2(v[2], v[3]);
+                *reinterpret_cast<uint2*>(y + (long)row * N + 4 * gidx) = t;
+            }
+        }
+        if (colsum) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) atomicAdd(colsum + 4 * gidx + i, s[i]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ L2-normalise backward
+// y = x / max(||x||, eps):  dx = (dy − y (y·dy)) / max(||x||, eps).   One warp per row.
+template <typename TY, typename TO>
+__global__ void l2norm_bwd_kernel(const TY* __restrict__ y, const float* __restrict__ nrm, const float* __restrict__ dy,
+                                  TO* __restrict__ dx, int M, int D, float eps) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    float dot = 0.f;
+    for (int c = lane; c < D; c += 32) dot += (float)y[(long)warp * D + c] * dy[(long)warp * D + c];
+    dot = warp_sum(dot);
+    const float inv = 1.f / fmaxf(nrm[warp], eps);
+    for (int c = lane; c < D; c += 32)
+        dx[(long)warp * D + c] = (TO)((dy[(long)warp * D + c] - (float)y[(long)warp * D + c] * dot) * inv);
+}
+
+// ------------------------------------------------------------------------------------------------ scatter-add rows
+// dst[idx[i]][:] += src[i][:] (fp32 atomics): token-embedding gradient, gather backward
+template <typename TS>
+__global__ void scatter_add_rows_kernel(const TS* __restrict__ src, long ld_src, float* __restrict__ dst, long ld_dst,
+                                        const long long* __restrict__ idx, int n, int D) {
+    const long total = (long)n * D;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int d = (int)(t % D);
+        const long i = t / D;
+        atomicAdd(dst + idx[i] * ld_dst + d, (float)src[i * ld_src + d]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ fused AdamW (+EMA)
+// p -= lr * (m̂ / (sqrt(v̂)+eps) + wd * p) on the fp32 master, refresh the bf16 compute copy in the same pass, and
+// (optionally) the EMA teacher  t = mom*t + (1-mom)*p  (vtp.py:388-401) with its bf16 copy.  grad is scaled by
+// gscale (1/world or loss scaling) and zeroed for the next step.
+__global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                             __nv_bfloat16* __restrict__ pb, float* __restrict__ tp, __nv_bfloat16* __restrict__ tpb,
+                             long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
+                             float ema_mom) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const float gi = g[i] * gscale;
+        g[i] = 0.f;
+        float mi = m[i] = b1 * m[i] + (1.f - b1) * gi;
+        float vi = v[i] = b2 * v[i] + (1.f - b2) * gi * gi;
+        float pi = p[i];
+        pi -= lr * ((mi / bc1) / (sqrtf(vi / bc2) + eps) + wd * pi);
+        p[i] = pi;
+        if (pb) pb[i] = __float2bfloat16_rn(pi);
+        if (tp) {
+            const float ti = ema_mom * tp[i] + (1.f - ema_mom) * pi;
+            tp[i] = ti;
+            if (tpb) tpb[i] = __float2bfloat16_rn(ti);
+        }
+    }
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ y, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        y[i] = __float2bfloat16_rn(x[i]);
+}
+
+// g fp32 [B*T][D] -> out bf16 [B*HW][D] skipping the prefix rows (patch-embed wgrad operand); also returns
+// dcls[D] += Σ_b g[b*T + 0][:]
+__global__ void strip_prefix_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ out, float* __restrict__ dcls,
+                                    int B, int T, int prefix, int D) {
+    const int HW = T - prefix;
+    const long total = (long)B * T * (D / 4);
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(t % (D / 4)) * 4;
+        const long row = t / (D / 4);
+        const int tok = (int)(row % T);
+        const long b = row / T;
+        const float4 v = *reinterpret_cast<const float4*>(g + row * D + c);
+        if (tok < prefix) {
+            if (dcls) {
+                atomicAdd(dcls + tok * D + c, v.x), atomicAdd(dcls + tok * D + c + 1, v.y);
+                atomicAdd(dcls + tok * D + c + 2, v.z), atomicAdd(dcls + tok * D + c + 3, v.w);
+            }
+        } else {
+            uint2 w;
+            w.x = pack_bf16x2(v.x, v.y), w.y = pack_bf16x2(v.z, v.w);
+            *reinterpret_cast<uint2*>(out + (b * HW + tok - prefix) * D + c) = w;
+        }
+    }
+}
+
+}  // namespace vtp
+
+using namespace vtp;
+
+extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const float* mean, const float* w, const void* dy,
+                            float* g, float* dw, float* db, int M, int D, int is_ln, vtp_stream_t st) {
+    VTP_CHECK_ARG(x && rstd && w && dy && g && dw && M > 0, "norm_bwd: bad args");
+    VTP_CHECK_ARG(D % 4 == 0 && D <= 2048, "norm_bwd: D %% 4 == 0 and D <= 2048");
+    VTP_CHECK_ARG(!is_ln || mean, "norm_bwd: LayerNorm needs mean");
+    const int threads = 256, rows_per_block = 64;
+    const int grid = ceil_div(M, rows_per_block);
+    const size_t smem = 2 * (size_t)D * sizeof(float);
+    cudaStream_t s = (cudaStream_t)st;
+    const int xr = (x_dtype == VTP_BF16 && !is_ln) ? 1 : 0;  // RMSNorm .type_as(x) rounding of xhat
+#define LB(T, MV) \
+    norm_bwd_kernel<T, MV><<<grid, threads, smem, s>>>((const T*)x, rstd, mean, w, (const __nv_bfloat16*)dy, g, dw, db, M, D, rows_per_block, is_ln, xr)
+    if (x_dtype == VTP_F32) {
+        if (D <= 512) LB(float, 4);
+        else if (D <= 1024) LB(float, 8);
+        else LB(float, 16);
+    } else {
+        if (D <= 512) LB(__nv_bfloat16, 4);
+        else if (D <= 1024) LB(__nv_bfloat16, 8);
+        else LB(__nv_bfloat16, 16);
+    }
+#undef LB
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_swiglu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int Hs, vtp_stream_t st) {
+    VTP_CHECK_ARG(pre && dhid && dpre && M > 0 && Hs % 8 == 0, "swiglu_bwd: bad args");
+    const int rpb = 32;
+    dim3 grid(ceil_div(Hs / 8, 128), ceil_div(M, rpb));
+    swiglu_bwd_kernel<<<grid, 128, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
+                                                          (__nv_bfloat16*)dpre, dbias, M, Hs, rpb);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_gelu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int N, vtp_stream_t st) {
+    VTP_CHECK_ARG(pre && dhid && dpre && M > 0 && N % 8 == 0, "gelu_bwd: bad args");
+    const int rpb = 32;
+    dim3 grid(ceil_div(N / 8, 128), ceil_div(M, rpb));
+    gelu_bwd_kernel<<<grid, 128, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
+                                                        (__nv_bfloat16*)dpre, dbias, M, N, rpb);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_cast_colsum(const void* x, int x_dtype, long ldx, void* y_bf16, float* colsum, int M, int N,
+                               vtp_stream_t st) {
+    VTP_CHECK_ARG(x && M > 0 && N % 4 == 0 && (y_bf16 || colsum), "cast_colsum: bad args");
+    const int rpb = 32;
+    dim3 grid(ceil_div(N / 4, 128), ceil_div(M, rpb));
+    if (x_dtype == VTP_F32)
+        cast_colsum_kernel<float><<<grid, 128, 0, (cudaStream_t)st>>>((const float*)x, ldx, (__nv_bfloat16*)y_bf16, colsum,
+                                                                     M, N, rpb);
+    else
+        cast_colsum_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, ldx,
+                                                                             (__nv_bfloat16*)y_bf16, colsum, M, N, rpb);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_l2norm_bwd(const void* y, int y_dtype, const float* nrm, const float* dy, void* dx, int dx_dtype, int M,
+                              int D, float eps, vtp_stream_t st) {
+    VTP_CHECK_ARG(y && nrm && dy && dx && M > 0, "l2norm_bwd: bad args");
+    const int grid = ceil_div(M, 8);
+    cudaStream_t s = (cudaStream_t)st;
+    if (y_dtype == VTP_F32 && dx_dtype == VTP_F32)
+        l2norm_bwd_kernel<float, float><<<grid, 256, 0, s>>>((const float*)y, nrm, dy, (float*)dx, M, D, eps);
+    else if (y_dtype == VTP_F32)
+        l2norm_bwd_kernel<float, __nv_bfloat16><<<grid, 256, 0, s>>>((const float*)y, nrm, dy, (__nv_bfloat16*)dx, M, D, eps);
+    else if (dx_dtype == VTP_F32)
+        l2norm_bwd_kernel<__nv_bfloat16, float><<<grid, 256, 0, s>>>((const __nv_bfloat16*)y, nrm, dy, (float*)dx, M, D, eps);
+    else
+        l2norm_bwd_kernel<__nv_bfloat16, __nv_bfloat16>
+            <<<grid, 256, 0, s>>>((const __nv_bfloat16*)y, nrm, dy, (__nv_bfloat16*)dx, M, D, eps);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_scatter_add_rows(const void* src, int src_dtype, long ld_src, float* dst, long ld_dst, const int64_t* idx,
+                                    int n, int D, vtp_stream_t st) {
+    VTP_CHECK_ARG(src && dst && (idx || n == 0), "scatter_add_rows: bad args");
+    if (n == 0) return VTP_OK;
+    const long total = (long)n * D;
+    if (src_dtype == VTP_F32)
+        scatter_add_rows_kernel<float><<<grid_cap(total, 256), 256, 0, (cudaStream_t)st>>>((const float*)src, ld_src, dst,
+                                                                                           ld_dst, (const long long*)idx, n, D);
+    else
+        scatter_add_rows_kernel<__nv_bfloat16><<<grid_cap(total, 256), 256, 0, (cudaStream_t)st>>>(
+            (const __nv_bfloat16*)src, ld_src, dst, ld_dst, (const long long*)idx, n, D);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, float* teacher, void* teacher_bf16,
+                              long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
+                              float grad_scale, float ema_momentum, vtp_stream_t st) {
+    VTP_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adamw_step: bad args");
+    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    adamw_kernel<<<grid_cap(n, 256), 256, 0, (cudaStream_t)st>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, teacher,
+                                                                 (__nv_bfloat16*)teacher_bf16, n, lr, beta1, beta2, eps,
+                                                                 weight_decay, bc1, bc2, grad_scale, ema_momentum);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_cast_f32_to_bf16(const float* x, void* y, long n, vtp_stream_t st) {
+    VTP_CHECK_ARG(x && y && n > 0, "cast: bad args");
+    cast_f32_bf16_kernel<<<grid_cap(n, 256), 256, 0, (cudaStream_t)st>>>(x, (__nv_bfloat16*)y, n);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_strip_prefix(const float* g, void* out_bf16, float* dcls, int B, int T, int prefix, int D,
+                                vtp_stream_t st) {
+    VTP_CHECK_ARG(g && out_bf16 && B > 0 && D % 4 == 0 && prefix >= 0 && prefix < T, "strip_prefix: bad args");
+    const long total = (long)B * T * (D / 4);
+    strip_prefix_kernel<<<grid_cap(total, 256), 256, 0, (cudaStream_t)st>>>(g, (__nv_bfloat16*)out_bf16, dcls, B, T, prefix, D);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ weight norm
+// heads/dino_head.py:48-49 (torch weight_norm, dim=0): W[k,:] = g[k] * v[k,:] / ||v[k,:]||
+namespace vtp {
+__global__ void weight_norm_fwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                       __nv_bfloat16* __restrict__ w, float* __restrict__ vnorm, int K, int D) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= K) return;
+    float s = 0.f;
+    for (int c = lane; c < D; c += 32) {
+        const float x = v[(long)warp * D + c];
+        s += x * x;
+    }
+    s = warp_sum(s);
+    const float nrm = sqrtf(s);
+    if (lane == 0 && vnorm) vnorm[warp] = nrm;
+    const float sc = g[warp] / nrm;
+    for (int c = lane; c < D; c += 32) w[(long)warp * D + c] = __float2bfloat16_rn(v[(long)warp * D + c] * sc);
+}
+// dv += (g/||v||) (dW − (dW·v̂) v̂) ; dg += dW·v̂
+__global__ void weight_norm_bwd_kernel(const float* __restrict__ v, const float* __restrict__ g,
+                                       const float* __restrict__ vnorm, const float* __restrict__ dW,
+                                       float* __restrict__ dv, float* __restrict__ dg, int K, int D) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= K) return;
+    const float inv = 1.f / vnorm[warp];
+    float dot = 0.f;
+    for (int c = lane; c < D; c += 32) dot += dW[(long)warp * D + c] * v[(long)warp * D + c] * inv;
+    dot = warp_sum(dot);
+    const float sc = g[warp] * inv;
+    for (int c = lane; c < D; c += 32)
+        dv[(long)warp * D + c] += sc * (dW[(long)warp * D + c] - dot * v[(long)warp * D + c] * inv);
+    if (lane == 0) dg[warp] += dot;
+}
+}  // namespace vtp
+
+extern "C" int vtp_weight_norm_fwd(const float* v, const float* g, void* w_bf16, float* vnorm, int K, int D, vtp_stream_t st) {
+    VTP_CHECK_ARG(v && g && w_bf16 && K > 0 && D > 0, "weight_norm_fwd: bad args");
+    vtp::weight_norm_fwd_kernel<<<vtp::ceil_div(K, 8), 256, 0, (cudaStream_t)st>>>(v, g, (__nv_bfloat16*)w_bf16, vnorm, K, D);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+extern "C" int vtp_weight_norm_bwd(const float* v, const float* g, const float* vnorm, const float* dW, float* dv, float* dg,
+                                   int K, int D, vtp_stream_t st) {
+    VTP_CHECK_ARG(v && g && vnorm && dW && dv && dg && K > 0, "weight_norm_bwd: bad args");
+    vtp::weight_norm_bwd_kernel<<<vtp::ceil_div(K, 8), 256, 0, (cudaStream_t)st>>>(v, g, vnorm, dW, dv, dg, K, D);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}

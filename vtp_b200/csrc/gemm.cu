@@ -66,7 +66,15 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float (&v)[64], 
     }
     // ---- output row (cls slot remap)
     long orow = grow;
-    if (p.rr_group > 0) orow = (long)(grow / p.rr_group) * (p.rr_group + p.rr_skip) + p.rr_skip + grow % p.rr_group;
+    if (p.rr_group > 0) {
+        if (p.rr_skip >= 0) {  // expansion: leave rr_skip rows free in front of every group (cls slot)
+            orow = (long)(grow / p.rr_group) * (p.rr_group + p.rr_skip) + p.rr_skip + grow % p.rr_group;
+        } else {  // compaction: drop the first -rr_skip rows of every group of rr_group input rows
+            const int tok = grow % p.rr_group;
+            if (tok < -p.rr_skip) return;
+            orow = (long)(grow / p.rr_group) * (p.rr_group + p.rr_skip) + tok + p.rr_skip;
+        }
+    }
 
     // ---- secondary output: pre-activation, bf16
     if (p.out2) {

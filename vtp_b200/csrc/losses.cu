@@ -1,0 +1,220 @@
+// vtp_b200 — loss heads of the 3-objective step, forward value + gradient in one pass over the logits.
+// The reference ships NO loss code: these restate OpenCLIP ClipLoss (softmax cross-entropy over the
+// gathered similarity matrix), DINOv2 DINOLoss / iBOTPatchLoss (centred+sharpened teacher softmax vs student
+// log-softmax over K prototypes) and an L1 pixel loss; oracle/vtp_oracle.py holds the matching CPU definitions.
+#include "host.h"
+#include "ptx.cuh"
+
+namespace vtp {
+
+__device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = is_max ? warp_max(v) : warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    float r = (threadIdx.x < nw) ? sh[threadIdx.x] : (is_max ? -INFINITY : 0.f);
+    if (warp == 0) {
+        r = is_max ? warp_max(r) : warp_sum(r);
+        if (lane == 0) sh[0] = r;
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+// ------------------------------------------------------------------------------------------------ contrastive CE
+// logits fp32 [R][ld] (C valid columns), label(r) = label0 + r.
+//   loss_acc   += coef * Σ_r (lse_r − logit[r,label])
+//   dscale_acc += Σ_r Σ_c G[r,c] * logit[r,c]          (d loss / d log-scale when logits = exp(log_scale) * sim)
+//   G bf16 [R][ldg] = coef * (softmax(logits[r,:]) − onehot(label))
+__global__ void softmax_ce_kernel(const float* __restrict__ logits, long ld, int C, int label0,
+                                  __nv_bfloat16* __restrict__ G, long ldg, float coef, float* __restrict__ loss_acc,
+                                  float* __restrict__ dscale_acc) {
+    __shared__ float sh[32];
+    const int r = blockIdx.x;
+    const float* lr = logits + (long)r * ld;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, lr[c]);
+    m = block_reduce(m, sh, true);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s += __expf(lr[c] - m);
+    s = block_reduce(s, sh, false);
+    const float lse = m + logf(s);
+    const int label = label0 + r;
+    float ds = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float x = lr[c];
+        const float g = coef * (__expf(x - lse) - (c == label ? 1.f : 0.f));
+        ds += g * x;
+        G[(long)r * ldg + c] = __float2bfloat16_rn(g);
+    }
+    ds = block_reduce(ds, sh, false);
+    if (threadIdx.x == 0) {
+        atomicAdd(loss_acc, coef * (lse - lr[label]));
+        if (dscale_acc) atomicAdd(dscale_acc, ds);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ DINO / iBOT
+// teacher: probs[r,:] = softmax((t[r,:] − center) / temp), in place (bf16).  One block per row, row cached in smem.
+__global__ void dino_teacher_kernel(__nv_bfloat16* __restrict__ t, const float* __restrict__ center, int K, float inv_temp) {
+    extern __shared__ __nv_bfloat16 rowb[];  // K raw bf16 logits (128 KB at K = 65536)
+    __shared__ float sh[32];
+    __nv_bfloat16* tr = t + (long)blockIdx.x * K;
+    float m = -INFINITY;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        const __nv_bfloat16 raw = tr[c];
+        rowb[c] = raw;
+        m = fmaxf(m, (__bfloat162float(raw) - center[c]) * inv_temp);
+    }
+    m = block_reduce(m, sh, true);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) s += __expf((__bfloat162float(rowb[c]) - center[c]) * inv_temp - m);
+    s = block_reduce(s, sh, false);
+    const float lse = m + logf(s);
+    for (int c = threadIdx.x; c < K; c += blockDim.x)
+        tr[c] = __float2bfloat16_rn(__expf((__bfloat162float(rowb[c]) - center[c]) * inv_temp - lse));
+}
+
+// student: for row r with teacher rows t0[r], t1[r] (−1 = none), weight w[r]:
+//   z = s/τ ;  loss += w Σ_v (lse(z) − Σ_k T_v[k] z[k]) ;  ds[k] = (w/τ) (n_v softmax(z)[k] − Σ_v T_v[k])   (in place, bf16)
+__global__ void dino_student_kernel(__nv_bfloat16* __restrict__ s, const __nv_bfloat16* __restrict__ tprobs,
+                                    const int* __restrict__ t0, const int* __restrict__ t1, const float* __restrict__ w,
+                                    int K, float inv_temp, float* __restrict__ loss_acc) {
+    extern __shared__ __nv_bfloat16 rowb[];  // K raw bf16 student logits
+    __shared__ float sh[32];
+    const int r = blockIdx.x;
+    __nv_bfloat16* sr = s + (long)r * K;
+    const int i0 = t0[r], i1 = t1 ? t1[r] : -1;
+    const float wr = w[r];
+    const __nv_bfloat16* ta = i0 >= 0 ? tprobs + (long)i0 * K : nullptr;
+    const __nv_bfloat16* tb = i1 >= 0 ? tprobs + (long)i1 * K : nullptr;
+    const float nv = (ta ? 1.f : 0.f) + (tb ? 1.f : 0.f);
+    float m = -INFINITY, dot = 0.f;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        const __nv_bfloat16 raw = sr[c];
+        rowb[c] = raw;
+        const float z = __bfloat162float(raw) * inv_temp;
+        m = fmaxf(m, z);
+        float tt = 0.f;
+        if (ta) tt += __bfloat162float(ta[c]);
+        if (tb) tt += __bfloat162float(tb[c]);
+        dot += tt * z;
+    }
+    m = block_reduce(m, sh, true);
+    dot = block_reduce(dot, sh, false);
+    float se = 0.f;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) se += __expf(__bfloat162float(rowb[c]) * inv_temp - m);
+    se = block_reduce(se, sh, false);
+    const float lse = m + logf(se);
+    const float gscale = wr * inv_temp;
+    for (int c = threadIdx.x; c < K; c += blockDim.x) {
+        float tt = 0.f;
+        if (ta) tt += __bfloat162float(ta[c]);
+        if (tb) tt += __bfloat162float(tb[c]);
+        sr[c] = __float2bfloat16_rn(gscale * (nv * __expf(__bfloat162float(rowb[c]) * inv_temp - lse) - tt));
+    }
+    if (threadIdx.x == 0) atomicAdd(loss_acc, wr * (nv * lse - dot));
+}
+
+// ------------------------------------------------------------------------------------------------ reconstruction L1
+// rec (bf16|fp32) NCHW [B,C,H,W], tgt fp32 NCHW ; dlp optional fp32 NCHW extra gradient (LPIPS) ;
+//   loss_acc += coef * Σ|rec − tgt|     out bf16 [B*gh*gw][C*r*r] = coef*sign(rec − tgt) + dlp   (pixel-unshuffled:
+//   the dY operand of proj_out's dgrad/wgrad, decoders/pixel_decoder.py:157-160)
+template <typename TR>
+__global__ void recon_grad_kernel(const TR* __restrict__ rec, const float* __restrict__ tgt, const float* __restrict__ dlp,
+                                  __nv_bfloat16* __restrict__ out, float* __restrict__ loss_acc, int B, int C, int gh,
+                                  int gw, int r, float coef) {
+    __shared__ float sh[32];
+    const int N = C * r * r;
+    const long total = (long)B * gh * gw * N;
+    const int H = gh * r, W = gw * r;
+    float acc = 0.f;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const int col = (int)(t % N);
+        const long row = t / N;
+        const int c = col / (r * r), ii = (col / r) % r, jj = col % r;
+        const int b = (int)(row / (gh * gw)), hi = (int)((row / gw) % gh), wi = (int)(row % gw);
+        const long idx = (((long)b * C + c) * H + hi * r + ii) * W + wi * r + jj;
+        const float d = (float)rec[idx] - tgt[idx];
+        acc += fabsf(d);
+        float g = coef * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
+        if (dlp) g += dlp[idx];
+        out[t] = __float2bfloat16_rn(g);
+    }
+    acc = block_reduce(acc, sh, false);
+    if (threadIdx.x == 0) atomicAdd(loss_acc, coef * acc);
+}
+
+// y = a*y + b*x  (teacher-centre EMA, misc)
+__global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x, float a, float b, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        y[i] = a * y[i] + b * x[i];
+}
+
+}  // namespace vtp
+
+using namespace vtp;
+
+extern "C" int vtp_softmax_ce(const float* logits, long ld, int R, int C, int label0, void* G_bf16, long ldg, float coef,
+                              float* loss_acc, float* dscale_acc, vtp_stream_t st) {
+    VTP_CHECK_ARG(logits && G_bf16 && loss_acc && R > 0 && C > 0 && label0 >= 0 && label0 + R <= C, "softmax_ce: bad args");
+    softmax_ce_kernel<<<R, 256, 0, (cudaStream_t)st>>>(logits, ld, C, label0, (__nv_bfloat16*)G_bf16, ldg, coef, loss_acc,
+                                                       dscale_acc);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_dino_teacher_probs(void* t_bf16, const float* center, int R, int K, float temp, vtp_stream_t st) {
+    VTP_CHECK_ARG(t_bf16 && center && R > 0 && K > 0 && temp > 0, "dino_teacher_probs: bad args");
+    const size_t smem = (size_t)K * sizeof(__nv_bfloat16);
+    VTP_CHECK_ARG(smem <= 220 * 1024, "dino_teacher_probs: K=%d too large for the smem-resident row", K);
+    static size_t conf = 0;
+    if (smem > conf) {
+        VTP_CUDA(cudaFuncSetAttribute(dino_teacher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conf = smem;
+    }
+    dino_teacher_kernel<<<R, 512, smem, (cudaStream_t)st>>>((__nv_bfloat16*)t_bf16, center, K, 1.f / temp);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_dino_student_ce(void* s_bf16, const void* tprobs_bf16, const int* t0, const int* t1, const float* w,
+                                   int R, int K, float temp, float* loss_acc, vtp_stream_t st) {
+    VTP_CHECK_ARG(s_bf16 && tprobs_bf16 && t0 && w && loss_acc && R > 0 && K > 0 && temp > 0, "dino_student_ce: bad args");
+    const size_t smem = (size_t)K * sizeof(__nv_bfloat16);
+    VTP_CHECK_ARG(smem <= 220 * 1024, "dino_student_ce: K=%d too large for the smem-resident row", K);
+    static size_t conf = 0;
+    if (smem > conf) {
+        VTP_CUDA(cudaFuncSetAttribute(dino_student_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        conf = smem;
+    }
+    dino_student_kernel<<<R, 512, smem, (cudaStream_t)st>>>((__nv_bfloat16*)s_bf16, (const __nv_bfloat16*)tprobs_bf16, t0, t1,
+                                                          w, K, 1.f / temp, loss_acc);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_recon_l1_grad(const void* rec, int rec_dtype, const float* tgt, const float* dlp, void* out_bf16,
+                                 float* loss_acc, int B, int C, int gh, int gw, int r, float coef, vtp_stream_t st) {
+    VTP_CHECK_ARG(rec && tgt && out_bf16 && loss_acc && B > 0, "recon_l1_grad: bad args");
+    const long total = (long)B * gh * gw * C * r * r;
+    long g = (total + 255) / 256;
+    const int grid = (int)(g < (long)num_sms() * 8 ? g : (long)num_sms() * 8);
+    if (rec_dtype == VTP_F32)
+        recon_grad_kernel<float><<<grid, 256, 0, (cudaStream_t)st>>>((const float*)rec, tgt, dlp, (__nv_bfloat16*)out_bf16,
+                                                                    loss_acc, B, C, gh, gw, r, coef);
+    else
+        recon_grad_kernel<__nv_bfloat16><<<grid, 256, 0, (cudaStream_t)st>>>(
+            (const __nv_bfloat16*)rec, tgt, dlp, (__nv_bfloat16*)out_bf16, loss_acc, B, C, gh, gw, r, coef);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_axpby(float* y, const float* x, float a, float b, long n, vtp_stream_t st) {
+    VTP_CHECK_ARG(y && x && n > 0, "axpby: bad args");
+    long g = (n + 255) / 256;
+    axpby_kernel<<<(int)(g < 4096 ? g : 4096), 256, 0, (cudaStream_t)st>>>(y, x, a, b, n);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}

@@ -64,6 +64,30 @@ SIGNATURES: dict[str, tuple] = {
     "vtp_attention_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                     C.c_void_p]),
     "vtp_attention_fwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_attention_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p]),
+    "vtp_norm_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_swiglu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_cast_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_l2norm_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                 C.c_float, C.c_void_p]),
+    "vtp_scatter_add_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_long, C.c_void_p, C.c_int, C.c_int,
+                                       C.c_void_p]),
+    "vtp_strip_prefix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_adamw_step": (C.c_int, [C.c_void_p] * 7 + [C.c_long] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_float,
+                                                                                  C.c_void_p]),
+    "vtp_cast_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]),
+    "vtp_axpby": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_long, C.c_void_p]),
+    "vtp_softmax_ce": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vtp_dino_teacher_probs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "vtp_dino_student_ce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_float, C.c_void_p, C.c_void_p]),
+    "vtp_weight_norm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_weight_norm_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
+    "vtp_recon_l1_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
 }
 
 
@@ -205,3 +229,86 @@ def embed_tokens(ids, emb, pos, out, stream=None):
 def l2norm_fwd(x, y, M: int, D: int, eps: float = 1e-12, norm_out=None, stream=None):
     check(load().vtp_l2norm_fwd(_ptr(x), _dt(x), _ptr(y), _dt(y), _ptr(norm_out), M, D, eps, _st(stream)),
           "vtp_l2norm_fwd")
+
+
+# ------------------------------------------------------------------------------------------------ training step
+def attention_bwd(qkv, o, dout, lse, dqkv, B: int, T: int, H: int, *, prefix: int, causal: bool = False, rope=None,
+                  stream=None):
+    sin, cos = (rope[0], rope[1]) if rope is not None else (None, None)
+    check(load().vtp_attention_bwd(_ptr(qkv), _ptr(o), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(sin), _ptr(cos), B, T, H,
+                                   prefix, int(causal), _st(stream)), "vtp_attention_bwd")
+
+
+def norm_bwd(x, rstd, mean, w, dy, g, dw, db, M: int, D: int, stream=None):
+    check(load().vtp_norm_bwd(_ptr(x), _dt(x), _ptr(rstd), _ptr(mean), _ptr(w), _ptr(dy), _ptr(g), _ptr(dw), _ptr(db), M, D,
+                              int(mean is not None), _st(stream)), "vtp_norm_bwd")
+
+
+def swiglu_bwd(pre, dhid, dpre, dbias, M: int, Hs: int, stream=None):
+    check(load().vtp_swiglu_bwd(_ptr(pre), _ptr(dhid), _ptr(dpre), _ptr(dbias), M, Hs, _st(stream)), "vtp_swiglu_bwd")
+
+
+def gelu_bwd(pre, dhid, dpre, dbias, M: int, N: int, stream=None):
+    check(load().vtp_gelu_bwd(_ptr(pre), _ptr(dhid), _ptr(dpre), _ptr(dbias), M, N, _st(stream)), "vtp_gelu_bwd")
+
+
+def cast_colsum(x, y, colsum, M: int, N: int, ldx: int | None = None, stream=None):
+    check(load().vtp_cast_colsum(_ptr(x), _dt(x), ldx if ldx is not None else N, _ptr(y), _ptr(colsum), M, N,
+                                 _st(stream)), "vtp_cast_colsum")
+
+
+def l2norm_bwd(y, nrm, dy, dx, M: int, D: int, eps: float = 1e-12, stream=None):
+    check(load().vtp_l2norm_bwd(_ptr(y), _dt(y), _ptr(nrm), _ptr(dy), _ptr(dx), _dt(dx), M, D, eps, _st(stream)),
+          "vtp_l2norm_bwd")
+
+
+def scatter_add_rows(src, dst, idx, D: int, *, ld_src: int | None = None, ld_dst: int | None = None, stream=None):
+    check(load().vtp_scatter_add_rows(_ptr(src), _dt(src), ld_src if ld_src is not None else D, _ptr(dst),
+                                      ld_dst if ld_dst is not None else D, _ptr(idx), idx.numel(), D, _st(stream)),
+          "vtp_scatter_add_rows")
+
+
+def strip_prefix(g, out, dcls, B: int, T: int, prefix: int, D: int, stream=None):
+    check(load().vtp_strip_prefix(_ptr(g), _ptr(out), _ptr(dcls), B, T, prefix, D, _st(stream)), "vtp_strip_prefix")
+
+
+def adamw_step(p, g, m, v, pb, teacher, teacher_b, n: int, *, lr, beta1, beta2, eps, wd, step, grad_scale=1.0,
+               ema_momentum=0.0, stream=None):
+    check(load().vtp_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(pb), _ptr(teacher), _ptr(teacher_b), n, lr, beta1,
+                                beta2, eps, wd, step, grad_scale, ema_momentum, _st(stream)), "vtp_adamw_step")
+
+
+def cast_f32_to_bf16(x, y, n: int, stream=None):
+    check(load().vtp_cast_f32_to_bf16(_ptr(x), _ptr(y), n, _st(stream)), "vtp_cast_f32_to_bf16")
+
+
+def axpby(y, x, a: float, b: float, n: int, stream=None):
+    check(load().vtp_axpby(_ptr(y), _ptr(x), a, b, n, _st(stream)), "vtp_axpby")
+
+
+def softmax_ce(logits, R: int, Cn: int, label0: int, G, coef: float, loss_acc, dscale_acc=None, stream=None):
+    check(load().vtp_softmax_ce(_ptr(logits), logits.stride(0), R, Cn, label0, _ptr(G), G.stride(0), coef, _ptr(loss_acc),
+                                _ptr(dscale_acc), _st(stream)), "vtp_softmax_ce")
+
+
+def dino_teacher_probs(t, center, R: int, K: int, temp: float, stream=None):
+    check(load().vtp_dino_teacher_probs(_ptr(t), _ptr(center), R, K, temp, _st(stream)), "vtp_dino_teacher_probs")
+
+
+def dino_student_ce(s, tprobs, t0, t1, w, R: int, K: int, temp: float, loss_acc, stream=None):
+    check(load().vtp_dino_student_ce(_ptr(s), _ptr(tprobs), _ptr(t0), _ptr(t1), _ptr(w), R, K, temp, _ptr(loss_acc),
+                                     _st(stream)), "vtp_dino_student_ce")
+
+
+def recon_l1_grad(rec, tgt, dlp, out, loss_acc, B: int, Cc: int, gh: int, gw: int, r: int, coef: float, stream=None):
+    check(load().vtp_recon_l1_grad(_ptr(rec), _dt(rec), _ptr(tgt), _ptr(dlp), _ptr(out), _ptr(loss_acc), B, Cc, gh, gw, r,
+                                   coef, _st(stream)), "vtp_recon_l1_grad")
+
+
+def weight_norm_fwd(v, g, w, vnorm, K: int, D: int, stream=None):
+    check(load().vtp_weight_norm_fwd(_ptr(v), _ptr(g), _ptr(w), _ptr(vnorm), K, D, _st(stream)), "vtp_weight_norm_fwd")
+
+
+def weight_norm_bwd(v, g, vnorm, dW, dv, dg, K: int, D: int, stream=None):
+    check(load().vtp_weight_norm_bwd(_ptr(v), _ptr(g), _ptr(vnorm), _ptr(dW), _ptr(dv), _ptr(dg), K, D, _st(stream)),
+          "vtp_weight_norm_bwd")
