@@ -148,9 +148,10 @@ int vtp_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, float* 
                    float ema_momentum, vtp_stream_t stream);
 int vtp_cast_f32_to_bf16(const float* x, void* y, long n, vtp_stream_t stream);
 int vtp_axpby(float* y, const float* x, float a, float b, long n, vtp_stream_t stream);
-/* OpenCLIP ClipLoss row-wise softmax-CE on a similarity block: loss, d(log-scale) and G = dL/dlogits (bf16) */
-int vtp_softmax_ce(const float* logits, long ld, int R, int C, int label0, void* G_bf16, long ldg, float coef,
-                   float* loss_acc, float* dscale_acc, vtp_stream_t stream);
+/* OpenCLIP ClipLoss row-wise softmax-CE on a similarity block sim = I·Tᵀ with logits = exp(*log_scale)·sim
+ * (vtp_hf/modeling_vtp.py:329): loss, d(log_scale) and G = dL/dsim (bf16) */
+int vtp_softmax_ce(const float* sim, long ld, int R, int C, int label0, const float* log_scale, void* G_bf16, long ldg,
+                   float coef, float* loss_acc, float* dscale_acc, vtp_stream_t stream);
 /* DINOv2 centred+sharpened teacher softmax, in place on bf16 logits [R][K] */
 int vtp_dino_teacher_probs(void* t_bf16, const float* center, int R, int K, float temp, vtp_stream_t stream);
 /* DINOv2 DINOLoss/iBOTPatchLoss cross-entropy of student logits [R][K] vs up to two teacher rows: loss + in-place grad */

@@ -23,34 +23,36 @@ __device__ __forceinline__ float block_reduce(float v, float* sh, bool is_max) {
 }
 
 // ------------------------------------------------------------------------------------------------ contrastive CE
-// logits fp32 [R][ld] (C valid columns), label(r) = label0 + r.
+// sim fp32 [R][ld] (C valid columns) = I·Tᵀ block; logits = exp(*log_scale) * sim (log_scale may be NULL -> 1);
+// label(r) = label0 + r.
 //   loss_acc   += coef * Σ_r (lse_r − logit[r,label])
-//   dscale_acc += Σ_r Σ_c G[r,c] * logit[r,c]          (d loss / d log-scale when logits = exp(log_scale) * sim)
-//   G bf16 [R][ldg] = coef * (softmax(logits[r,:]) − onehot(label))
+//   dscale_acc += Σ_r Σ_c g[r,c] * logit[r,c]           (= d loss / d log_scale),  g = coef (softmax − onehot)
+//   G bf16 [R][ldg] = exp(log_scale) * g                   (= d loss / d sim, the operand of the feature-grad GEMMs)
 __global__ void softmax_ce_kernel(const float* __restrict__ logits, long ld, int C, int label0,
-                                  __nv_bfloat16* __restrict__ G, long ldg, float coef, float* __restrict__ loss_acc,
-                                  float* __restrict__ dscale_acc) {
+                                  const float* __restrict__ log_scale, __nv_bfloat16* __restrict__ G, long ldg, float coef,
+                                  float* __restrict__ loss_acc, float* __restrict__ dscale_acc) {
     __shared__ float sh[32];
     const int r = blockIdx.x;
+    const float sc = log_scale ? __expf(*log_scale) : 1.f;
     const float* lr = logits + (long)r * ld;
     float m = -INFINITY;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, lr[c]);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) m = fmaxf(m, sc * lr[c]);
     m = block_reduce(m, sh, true);
     float s = 0.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) s += __expf(lr[c] - m);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) s += __expf(sc * lr[c] - m);
     s = block_reduce(s, sh, false);
     const float lse = m + logf(s);
     const int label = label0 + r;
     float ds = 0.f;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float x = lr[c];
+        const float x = sc * lr[c];
         const float g = coef * (__expf(x - lse) - (c == label ? 1.f : 0.f));
         ds += g * x;
-        G[(long)r * ldg + c] = __float2bfloat16_rn(g);
+        G[(long)r * ldg + c] = __float2bfloat16_rn(sc * g);
     }
     ds = block_reduce(ds, sh, false);
     if (threadIdx.x == 0) {
-        atomicAdd(loss_acc, coef * (lse - lr[label]));
+        atomicAdd(loss_acc, coef * (lse - sc * lr[label]));
         if (dscale_acc) atomicAdd(dscale_acc, ds);
     }
 }
@@ -156,11 +158,11 @@ __global__ void axpby_kernel(float* __restrict__ y, const float* __restrict__ x,
 
 using namespace vtp;
 
-extern "C" int vtp_softmax_ce(const float* logits, long ld, int R, int C, int label0, void* G_bf16, long ldg, float coef,
-                              float* loss_acc, float* dscale_acc, vtp_stream_t st) {
+extern "C" int vtp_softmax_ce(const float* logits, long ld, int R, int C, int label0, const float* log_scale, void* G_bf16,
+                              long ldg, float coef, float* loss_acc, float* dscale_acc, vtp_stream_t st) {
     VTP_CHECK_ARG(logits && G_bf16 && loss_acc && R > 0 && C > 0 && label0 >= 0 && label0 + R <= C, "softmax_ce: bad args");
-    softmax_ce_kernel<<<R, 256, 0, (cudaStream_t)st>>>(logits, ld, C, label0, (__nv_bfloat16*)G_bf16, ldg, coef, loss_acc,
-                                                       dscale_acc);
+    softmax_ce_kernel<<<R, 256, 0, (cudaStream_t)st>>>(logits, ld, C, label0, log_scale, (__nv_bfloat16*)G_bf16, ldg, coef,
+                                                       loss_acc, dscale_acc);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

@@ -297,13 +297,15 @@ def trunk_tokens(W: TowerW, img: torch.Tensor, mode: str, mask_idx: Optional[tor
     lib.fill_prefix_tokens(x, W.extra["cls"], B, T, 1, D)
     if mask_idx is not None and mask_idx.numel() > 0:
         lib.apply_mask_tokens(x, W.extra["mask_token"], mask_idx, HW, T, 1, D)
-    return x, (B, T, gh, gw)
+    return x, (B, T, gh, gw), a
 
 
 def trunk_forward(W: TowerW, img: torch.Tensor, mode: str, *, mask_idx=None, tape: Optional[dict] = None,
                   taps=None):
     """encoders/vision_transformer.py:221-258 for one resolution group.  Returns (x_prenorm [B*T,D] fp32, meta)."""
-    x, (B, T, gh, gw) = trunk_tokens(W, img, mode, mask_idx)
+    x, (B, T, gh, gw), a = trunk_tokens(W, img, mode, mask_idx)
+    if tape is not None:
+        tape["patch_a"] = a
     rope = W.rope(gh, gw, img.device)
     blk_tape = [] if tape is not None else None
     x = tower_blocks(W, x, B, T, rope, mode, tape=blk_tape, taps=taps)

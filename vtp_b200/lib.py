@@ -79,8 +79,8 @@ SIGNATURES: dict[str, tuple] = {
                                                                                   C.c_void_p]),
     "vtp_cast_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]),
     "vtp_axpby": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_long, C.c_void_p]),
-    "vtp_softmax_ce": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_long, C.c_float,
-                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vtp_softmax_ce": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_long,
+                                 C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vtp_dino_teacher_probs": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p]),
     "vtp_dino_student_ce": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                       C.c_float, C.c_void_p, C.c_void_p]),
@@ -286,9 +286,10 @@ def axpby(y, x, a: float, b: float, n: int, stream=None):
     check(load().vtp_axpby(_ptr(y), _ptr(x), a, b, n, _st(stream)), "vtp_axpby")
 
 
-def softmax_ce(logits, R: int, Cn: int, label0: int, G, coef: float, loss_acc, dscale_acc=None, stream=None):
-    check(load().vtp_softmax_ce(_ptr(logits), logits.stride(0), R, Cn, label0, _ptr(G), G.stride(0), coef, _ptr(loss_acc),
-                                _ptr(dscale_acc), _st(stream)), "vtp_softmax_ce")
+def softmax_ce(logits, R: int, Cn: int, label0: int, G, coef: float, loss_acc, dscale_acc=None, log_scale=None,
+               stream=None):
+    check(load().vtp_softmax_ce(_ptr(logits), logits.stride(0), R, Cn, label0, _ptr(log_scale), _ptr(G), G.stride(0), coef,
+                                _ptr(loss_acc), _ptr(dscale_acc), _st(stream)), "vtp_softmax_ce")
 
 
 def dino_teacher_probs(t, center, R: int, K: int, temp: float, stream=None):

@@ -1,0 +1,784 @@
+"""The 3-objective training step (CLIP contrastive + DINO/iBOT self-distillation + pixel reconstruction) on the sm_100a
+kernels, with hand-written backward (no torch.autograd): the B200-native counterpart of the reference's legacy
+meta-arch `VTP` (vtp/models/vtp.py:88-512: forward_clip / forward_ssl_learning / forward_reconstruction,
+update_teacher) plus the loss / optimiser layer that the reference does not release.
+
+  * parameters live in ONE flat fp32 master buffer with matching bf16 compute copy, fp32 gradient and Adam moments
+    (`ParamStore`); GEMM weights are stored in kernel layout (w1|w2 8-interleaved for the SwiGLU-gate epilogue);
+    `import_state_dict` / `export_state_dict` convert from/to the reference's state-dict keys;
+  * one fused kernel per region does AdamW + bf16 refresh + EMA teacher (vtp.py:388-401) + gradient zeroing;
+  * data parallel: gradients are all-reduced (NCCL) on the flat buffer, contrastive features are all-gathered and
+    their gradients reduced back — the only two collectives on the path.
+Precision is the reference-under-autocast ("bf16") mode throughout.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import engine as E
+from . import lib
+from .config import VTPConfig
+from .engine import BF, F32, BlockW, Lin, TowerW, _e
+
+_ALIGN = 64  # elements; keeps every tensor 128B-aligned in the bf16 copy (TMA needs 16B)
+
+
+# ------------------------------------------------------------------------------------------------------ parameters
+class ParamStore:
+    def __init__(self, device):
+        self.device = device
+        self.specs: List[Tuple[str, Tuple[int, ...], bool, bool]] = []
+        self.offset: Dict[str, int] = {}
+        self.shape: Dict[str, Tuple[int, ...]] = {}
+        self.regions: List[Tuple[int, int, bool, bool]] = []  # (start, end, decay, teacher)
+
+    def add(self, name, shape, decay=True, teacher=False):
+        self.specs.append((name, tuple(int(s) for s in shape), bool(decay), bool(teacher)))
+
+    def finalize(self):
+        off = 0
+        for teacher in (True, False):
+            for decay in (True, False):
+                start = off
+                for name, shape, d, t in self.specs:
+                    if d == decay and t == teacher:
+                        self.offset[name], self.shape[name] = off, shape
+                        n = 1
+                        for s in shape:
+                            n *= s
+                        off += (n + _ALIGN - 1) // _ALIGN * _ALIGN
+                if off > start:
+                    self.regions.append((start, off, decay, teacher))
+        self.n = off
+        self.n_teacher = max([e for s, e, d, t in self.regions if t], default=0)
+        dev = self.device
+        self.p = torch.zeros(self.n, dtype=F32, device=dev)
+        self.pb = torch.zeros(self.n, dtype=BF, device=dev)
+        self.g = torch.zeros(self.n, dtype=F32, device=dev)
+        self.m = torch.zeros(self.n, dtype=F32, device=dev)
+        self.v = torch.zeros(self.n, dtype=F32, device=dev)
+        self.tp = torch.zeros(self.n_teacher, dtype=F32, device=dev)
+        self.tpb = torch.zeros(self.n_teacher, dtype=BF, device=dev)
+
+    def _view(self, buf, name):
+        o, shape = self.offset[name], self.shape[name]
+        n = 1
+        for s in shape:
+            n *= s
+        return buf[o:o + n].view(shape)
+
+    def f32(self, name): return self._view(self.p, name)
+    def bf16(self, name): return self._view(self.pb, name)
+    def grad(self, name): return self._view(self.g, name)
+    def tf32(self, name): return self._view(self.tp, name)
+    def tbf16(self, name): return self._view(self.tpb, name)
+
+    def sync_compute_copies(self, init_teacher: bool = False):
+        lib.cast_f32_to_bf16(self.p, self.pb, self.n)
+        if init_teacher and self.n_teacher:
+            self.tp.copy_(self.p[:self.n_teacher])
+            self.tpb.copy_(self.pb[:self.n_teacher])
+
+
+def _vit_specs(store: ParamStore, pre: str, D: int, depth: int, hidden: int, ln: bool, teacher: bool, ffn_out: int):
+    for i in range(depth):
+        p = f"{pre}blocks.{i}."
+        store.add(p + "n1_w", (D,), False, teacher)
+        if ln: store.add(p + "n1_b", (D,), False, teacher)
+        store.add(p + "qkv.w", (3 * D, D), True, teacher); store.add(p + "qkv.b", (3 * D,), False, teacher)
+        store.add(p + "proj.w", (D, D), True, teacher); store.add(p + "proj.b", (D,), False, teacher)
+        store.add(p + "n2_w", (D,), False, teacher)
+        if ln: store.add(p + "n2_b", (D,), False, teacher)
+        store.add(p + "fc1.w", (ffn_out, D), True, teacher); store.add(p + "fc1.b", (ffn_out,), False, teacher)
+        store.add(p + "fc2.w", (D, hidden), True, teacher); store.add(p + "fc2.b", (D,), False, teacher)
+    store.add(pre + "norm_w", (D,), False, teacher)
+    if ln: store.add(pre + "norm_b", (D,), False, teacher)
+
+
+def _tower_views(store: ParamStore, pre: str, tw: TowerW, depth: int, hidden: int, ln: bool, *, kind: str):
+    """kind: 'param' (bf16 weights + fp32 vectors), 'teacher', or 'grad' (fp32 gradient views)."""
+    if kind == "param":
+        wv, fv = store.bf16, store.f32
+    elif kind == "teacher":
+        wv, fv = store.tbf16, store.tf32
+    else:
+        wv, fv = store.grad, store.grad
+
+    def lin(name):
+        w = wv(name + ".w")
+        b = fv(name + ".b") if (name + ".b") in store.offset else None
+        return Lin(w, b, w.shape[0], w.shape[1])
+
+    tw.blocks = []
+    for i in range(depth):
+        p = f"{pre}blocks.{i}."
+        tw.blocks.append(BlockW(n1_w=fv(p + "n1_w"), n1_b=fv(p + "n1_b") if ln else None, qkv=lin(p + "qkv"),
+                                proj=lin(p + "proj"), n2_w=fv(p + "n2_w"), n2_b=fv(p + "n2_b") if ln else None,
+                                fc1=lin(p + "fc1"), fc2=lin(p + "fc2"), hidden=hidden))
+    tw.norm_w = fv(pre + "norm_w")
+    tw.norm_b = fv(pre + "norm_b") if ln else None
+    return lin
+
+
+# ------------------------------------------------------------------------------------------------------ backward
+def wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, Mtok: int):
+    """dW[N_out, K_in] += dYᵀ X  (dY [Mtok, N_out] bf16, X [Mtok, K_in] bf16): TN GEMM, split-K + fp32 atomics."""
+    n_out, k_in = dw.shape
+    tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
+    nkb = (Mtok + 63) // 64
+    split = max(1, min(nkb // 4 if nkb >= 8 else 1, (2 * 148 + tiles - 1) // tiles))
+    lib.gemm(dy, x, dw, M=n_out, N=k_in, K=Mtok, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0), ldo=k_in,
+             accumulate=True, split_k=split, round_bf16=False)
+
+
+def dgrad(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor, Mtok: int, **kw):
+    """dX[Mtok, K_in] = dY[Mtok, N_out] · W[N_out, K_in]  (W consumed as an MN-major B operand, no transpose copy)."""
+    n_out, k_in = w.shape
+    lib.gemm(dy, w, out, M=Mtok, N=k_in, K=n_out, b_mn=True, lda=dy.stride(0), ldb=k_in, round_bf16=False, **kw)
+
+
+def tower_blocks_backward(W: TowerW, G: TowerW, tape: list, g: torch.Tensor, B: int, T: int, rope, causal=False):
+    """Reverse of engine.tower_blocks.  g fp32 [B*T, D]: in = dL/d(stream out), out = dL/d(stream in) (in place)."""
+    dev = g.device
+    M, D, H = B * T, W.D, W.heads
+    gb = _e((M, D), BF, dev)
+    for li in reversed(range(len(W.blocks))):
+        bw, gw, t = W.blocks[li], G.blocks[li], tape[li]
+        Hd = bw.hidden
+        # ---- FFN sub-layer
+        lib.cast_colsum(g, gb, gw.fc2.b, M, D)
+        dhid = _e((M, Hd), BF, dev)
+        dgrad(gb, bw.fc2.w, dhid, M)
+        wgrad(gb, t["hid"], gw.fc2.w, M)
+        dpre = torch.empty_like(t["pre"])
+        if W.ffn == "swiglu":
+            lib.swiglu_bwd(t["pre"], dhid, dpre, gw.fc1.b, M, Hd)
+        else:
+            lib.gelu_bwd(t["pre"], dhid, dpre, gw.fc1.b, M, Hd)
+        dh = _e((M, D), BF, dev)
+        dgrad(dpre, bw.fc1.w, dh, M)
+        wgrad(dpre, t["h2"], gw.fc1.w, M)
+        lib.norm_bwd(t["x_mid"], t["n2"]["rstd"], t["n2"]["mean"], bw.n2_w, dh, g, gw.n2_w, gw.n2_b, M, D)
+        # ---- attention sub-layer
+        lib.cast_colsum(g, gb, gw.proj.b, M, D)
+        do = _e((M, D), BF, dev)
+        dgrad(gb, bw.proj.w, do, M)
+        wgrad(gb, t["o"], gw.proj.w, M)
+        dqkv = _e((M, 3 * D), BF, dev)
+        lib.attention_bwd(t["qkv"], t["o"], do, t["lse"], dqkv, B, T, H, prefix=W.prefix, causal=causal, rope=rope)
+        lib.cast_colsum(dqkv, None, gw.qkv.b, M, 3 * D)
+        dgrad(dqkv, bw.qkv.w, dh, M)
+        wgrad(dqkv, t["h1"], gw.qkv.w, M)
+        lib.norm_bwd(t["x_in"], t["n1"]["rstd"], t["n1"]["mean"], bw.n1_w, dh, g, gw.n1_w, gw.n1_b, M, D)
+        tape[li] = None  # free the saved activations of this block
+    return g
+
+
+# ------------------------------------------------------------------------------------------------------ trainer
+@dataclass
+class TrainConfig:
+    lr: float = 1e-4
+    beta1: float = 0.9
+    beta2: float = 0.95
+    eps: float = 1e-8
+    weight_decay: float = 0.05
+    teacher_momentum: float = 0.994
+    teacher_temp: float = 0.07
+    student_temp: float = 0.1
+    center_momentum: float = 0.9
+    head_out_dim: int = 65536
+    head_hidden: int = 2048
+    head_bottleneck: int = 256
+    n_local_crops: int = 8
+    w_clip: float = 1.0
+    w_ssl: float = 1.0
+    w_rec: float = 1.0
+    lpips_weight: float = 1.0
+
+
+class VTPTrainer:
+    def __init__(self, cfg: VTPConfig, tc: Optional[TrainConfig] = None, device="cuda", process_group=None):
+        self.cfg, self.tc = cfg, tc or TrainConfig()
+        self.device = torch.device(device)
+        self.pg = process_group
+        import torch.distributed as dist
+        self.world = dist.get_world_size(process_group) if (dist.is_available() and dist.is_initialized()) else 1
+        self.rank = dist.get_rank(process_group) if self.world > 1 else 0
+        lib.check(lib.load().vtp_check_device(), "vtp_check_device")
+        c = cfg
+        if c.vision_norm_layer != "rmsnorm" or c.decoder_norm_layer not in ("layernorm", "layernormbf16"):
+            raise NotImplementedError("trainer supports the reference defaults: rmsnorm trunk, layernorm decoder")
+        from .model import _swiglu_hidden
+        self.D, self.Dd, self.Dt = c.vision_embed_dim, c.decoder_embed_dim, c.text_embed_dim
+        self.hs = _swiglu_hidden(self.D, c.vision_mlp_ratio, c.vision_ffn_layer)
+        self.hsd = _swiglu_hidden(self.Dd, 4.0, c.decoder_ffn_layer)
+        self.ht = int(self.Dt * c.text_mlp_ratio)
+        self.bn = c.vision_feature_bottleneck
+        st = ParamStore(self.device)
+        D, Dd, Dt, K = self.D, self.Dd, self.Dt, self.tc.head_out_dim
+        ps = c.vision_patch_size
+        # trunk (+ clip projection + DINO head): these have an EMA teacher (vtp.py:239-262)
+        st.add("trunk.patch.w", (D, 3 * ps * ps), True, True); st.add("trunk.patch.b", (D,), False, True)
+        st.add("trunk.cls", (D,), False, True); st.add("trunk.mask_token", (D,), False, True)
+        _vit_specs(st, "trunk.", D, c.vision_depth, self.hs, False, True, 2 * self.hs)
+        st.add("trunk.bneck.w", (self.bn, D), True, True)
+        st.add("visual_proj.w", (Dt, D), True, True)
+        hh, hb = self.tc.head_hidden, self.tc.head_bottleneck
+        st.add("head.mlp0.w", (hh, D), True, True); st.add("head.mlp0.b", (hh,), False, True)
+        st.add("head.mlp2.w", (hh, hh), True, True); st.add("head.mlp2.b", (hh,), False, True)
+        st.add("head.mlp4.w", (hb, hh), True, True); st.add("head.mlp4.b", (hb,), False, True)
+        st.add("head.last_v", (K, hb), True, True); st.add("head.last_g", (K,), False, True)
+        # decoder
+        st.add("decoder.proj_in.w", (Dd, self.bn), True); st.add("decoder.proj_in.b", (Dd,), False)
+        _vit_specs(st, "decoder.", Dd, c.decoder_depth, self.hsd, True, False, 2 * self.hsd)
+        st.add("decoder.proj_out.w", (3 * 256, Dd), True); st.add("decoder.proj_out.b", (3 * 256,), False)
+        # text
+        st.add("text.tok_emb", (c.text_vocab_size, Dt), True); st.add("text.pos", (c.text_context_length, Dt), False)
+        _vit_specs(st, "text.", Dt, c.text_depth, self.ht, True, False, self.ht)
+        st.add("text.proj.w", (Dt, Dt), True)
+        st.add("logit_scale", (1,), False)
+        st.finalize()
+        self.store = st
+        self._build_towers()
+        self.step_count = 0
+        self.loss_acc = torch.zeros(8, dtype=F32, device=self.device)  # clip, dino_local, dino_global, ibot, rec
+        self.center_dino = torch.zeros(K, dtype=F32, device=self.device)
+        self.center_ibot = torch.zeros(K, dtype=F32, device=self.device)
+        self.head_wn = _e((K, hb), BF, self.device)       # weight-normed last layer (student), rebuilt every step
+        self.head_wn_t = _e((K, hb), BF, self.device)     # teacher
+        self.head_vnorm = _e((K,), F32, self.device)
+        self.periods = E.rope_sincos  # table builder; periods are constants (layers/embeddings.py:182-195)
+        from .rope import rope_periods
+        self._periods_v = rope_periods(64)
+        self.reset_parameters()
+
+    # -------------------------------------------------------------- towers as views of the flat buffers
+    def _build_towers(self):
+        c, st = self.cfg, self.store
+
+        def mk(pre, D, heads, depth, hidden, ln, norm, eps, stream_bf16, prefix, ffn, kind):
+            tw = TowerW(D=D, heads=heads, norm=norm, eps=eps, stream_bf16=stream_bf16, prefix=prefix, ffn=ffn)
+            lin = _tower_views(st, pre, tw, depth, hidden, ln, kind=kind)
+            from .rope import rope_periods
+            tw.periods = rope_periods(64)
+            return tw, lin
+
+        self.towers = {}
+        for kind in ("param", "teacher", "grad"):
+            tw, lin = mk("trunk.", self.D, c.vision_num_heads, c.vision_depth, self.hs, False, "rms", 1e-5, False, 1,
+                         "swiglu", kind)
+            fv = {"param": st.f32, "teacher": st.tf32, "grad": st.grad}[kind]
+            tw.extra.update(patch=lin("trunk.patch"), patch_size=c.vision_patch_size, cls=fv("trunk.cls"),
+                            mask_token=fv("trunk.mask_token"), bneck=lin("trunk.bneck"),
+                            visual_proj=lin("visual_proj"), mlp0=lin("head.mlp0"), mlp2=lin("head.mlp2"),
+                            mlp4=lin("head.mlp4"), last_v=fv("head.last_v"), last_g=fv("head.last_g"))
+            self.towers[("trunk", kind)] = tw
+        for kind in ("param", "grad"):
+            eps_d = 1e-6 if c.decoder_norm_layer == "layernorm" else 1e-5
+            tw, lin = mk("decoder.", self.Dd, c.decoder_num_heads, c.decoder_depth, self.hsd, True, "ln", eps_d, True, 0,
+                         "swiglu", kind)
+            tw.extra.update(proj_in=lin("decoder.proj_in"), proj_out=lin("decoder.proj_out"))
+            self.towers[("decoder", kind)] = tw
+            tw, lin = mk("text.", self.Dt, c.text_num_heads, c.text_depth, self.ht, True, "ln", 1e-5, False, 0, "gelu",
+                         kind)
+            fv = st.f32 if kind == "param" else st.grad
+            tw.extra.update(tok_emb=fv("text.tok_emb"), pos=fv("text.pos"), proj=lin("text.proj"))
+            self.towers[("text", kind)] = tw
+
+    # -------------------------------------------------------------- init / state-dict exchange
+    @torch.no_grad()
+    def reset_parameters(self, seed: int = 0):
+        g = torch.Generator(device="cpu").manual_seed(seed)
+        st = self.store
+        for name, shape, decay, _ in st.specs:
+            v = st.f32(name)
+            leaf = name.rsplit(".", 1)[-1]
+            if name == "logit_scale":
+                v.fill_(math.log(1 / 0.07))
+            elif leaf in ("n1_w", "n2_w", "norm_w", "last_g"):
+                v.fill_(1.0)
+            elif leaf in ("b", "n1_b", "n2_b", "norm_b", "mask_token"):
+                v.zero_()
+            elif name == "text.pos":
+                v.copy_(torch.randn(shape, generator=g) * 0.01)
+            else:
+                std = 0.02
+                v.copy_((torch.randn(shape, generator=g) * std).clamp_(-2 * std, 2 * std))
+        st.sync_compute_copies(init_teacher=True)
+
+    @torch.no_grad()
+    def import_state_dict(self, sd: Dict[str, torch.Tensor], head_sd: Optional[Dict[str, torch.Tensor]] = None):
+        """Load a reference-format VTPModel state dict (+ optional DINOHead state dict with keys mlp.0.weight, ...,
+        last_layer.weight_g / weight_v or the parametrizations.* spelling)."""
+        st = self.store
+        dev = self.device
+
+        def put(name, t):
+            st.f32(name).copy_(t.to(dev, F32).reshape(st.shape[name]))
+
+        def vit(pre_ref, pre, depth, ln, swiglu=True):
+            for i in range(depth):
+                r, p = f"{pre_ref}blocks.{i}.", f"{pre}blocks.{i}."
+                put(p + "n1_w", sd[r + "norm1.weight"]); put(p + "n2_w", sd[r + "norm2.weight"])
+                if ln:
+                    put(p + "n1_b", sd[r + "norm1.bias"]); put(p + "n2_b", sd[r + "norm2.bias"])
+                put(p + "qkv.w", sd[r + "attn.qkv.weight"]); put(p + "qkv.b", sd[r + "attn.qkv.bias"])
+                put(p + "proj.w", sd[r + "attn.proj.weight"]); put(p + "proj.b", sd[r + "attn.proj.bias"])
+                put(p + "fc1.w", E.interleave8(sd[r + "mlp.w1.weight"], sd[r + "mlp.w2.weight"]))
+                put(p + "fc1.b", E.interleave8(sd[r + "mlp.w1.bias"], sd[r + "mlp.w2.bias"]))
+                put(p + "fc2.w", sd[r + "mlp.w3.weight"]); put(p + "fc2.b", sd[r + "mlp.w3.bias"])
+            put(pre + "norm_w", sd[pre_ref + "norm.weight"])
+            if ln: put(pre + "norm_b", sd[pre_ref + "norm.bias"])
+
+        c = self.cfg
+        put("trunk.patch.w", sd["trunk.patch_embed.proj.weight"].flatten(1)); put("trunk.patch.b", sd["trunk.patch_embed.proj.bias"])
+        put("trunk.cls", sd["trunk.cls_token"]); put("trunk.mask_token", sd["trunk.mask_token"])
+        vit("trunk.", "trunk.", c.vision_depth, False)
+        put("trunk.bneck.w", sd["trunk.feature_bottleneck.weight"])
+        put("visual_proj.w", sd["visual_proj.weight"])
+        put("decoder.proj_in.w", sd["pixel_decoder.proj_in.weight"].flatten(1)); put("decoder.proj_in.b", sd["pixel_decoder.proj_in.bias"])
+        vit("pixel_decoder.", "decoder.", c.decoder_depth, True)
+        put("decoder.proj_out.w", sd["pixel_decoder.proj_out.weight"].flatten(1)); put("decoder.proj_out.b", sd["pixel_decoder.proj_out.bias"])
+        put("text.tok_emb", sd["token_embedding.weight"]); put("text.pos", sd["positional_embedding"])
+        for i in range(c.text_depth):
+            r, p = f"text_transformer.resblocks.{i}.", f"text.blocks.{i}."
+            put(p + "n1_w", sd[r + "ln_1.weight"]); put(p + "n1_b", sd[r + "ln_1.bias"])
+            put(p + "n2_w", sd[r + "ln_2.weight"]); put(p + "n2_b", sd[r + "ln_2.bias"])
+            put(p + "qkv.w", sd[r + "attn.in_proj_weight"]); put(p + "qkv.b", sd[r + "attn.in_proj_bias"])
+            put(p + "proj.w", sd[r + "attn.out_proj.weight"]); put(p + "proj.b", sd[r + "attn.out_proj.bias"])
+            put(p + "fc1.w", sd[r + "mlp.c_fc.weight"]); put(p + "fc1.b", sd[r + "mlp.c_fc.bias"])
+            put(p + "fc2.w", sd[r + "mlp.c_proj.weight"]); put(p + "fc2.b", sd[r + "mlp.c_proj.bias"])
+        put("text.norm_w", sd["ln_final.weight"]); put("text.norm_b", sd["ln_final.bias"])
+        put("text.proj.w", sd["text_projection"].t())
+        put("logit_scale", sd["logit_scale"].reshape(1))
+        if head_sd is not None:
+            for j in (0, 2, 4):
+                put(f"head.mlp{j}.w", head_sd[f"mlp.{j}.weight"]); put(f"head.mlp{j}.b", head_sd[f"mlp.{j}.bias"])
+            gk = "last_layer.weight_g" if "last_layer.weight_g" in head_sd else "last_layer.parametrizations.weight.original0"
+            vk = "last_layer.weight_v" if "last_layer.weight_v" in head_sd else "last_layer.parametrizations.weight.original1"
+            put("head.last_g", head_sd[gk].reshape(-1)); put("head.last_v", head_sd[vk])
+        st.sync_compute_copies(init_teacher=True)
+
+    @torch.no_grad()
+    def export_state_dict(self) -> Dict[str, torch.Tensor]:
+        """Student weights in the reference's VTPModel state-dict format."""
+        st, c = self.store, self.cfg
+        out = {}
+
+        def de8(t):
+            n = t.shape[0] // 2
+            v = t.reshape(n // 8, 2, 8, *t.shape[1:])
+            return v[:, 0].reshape(n, *t.shape[1:]).clone(), v[:, 1].reshape(n, *t.shape[1:]).clone()
+
+        def vit(pre_ref, pre, depth, ln):
+            for i in range(depth):
+                r, p = f"{pre_ref}blocks.{i}.", f"{pre}blocks.{i}."
+                out[r + "norm1.weight"] = st.f32(p + "n1_w").clone(); out[r + "norm2.weight"] = st.f32(p + "n2_w").clone()
+                if ln:
+                    out[r + "norm1.bias"] = st.f32(p + "n1_b").clone(); out[r + "norm2.bias"] = st.f32(p + "n2_b").clone()
+                out[r + "attn.qkv.weight"] = st.f32(p + "qkv.w").clone(); out[r + "attn.qkv.bias"] = st.f32(p + "qkv.b").clone()
+                out[r + "attn.proj.weight"] = st.f32(p + "proj.w").clone(); out[r + "attn.proj.bias"] = st.f32(p + "proj.b").clone()
+                out[r + "mlp.w1.weight"], out[r + "mlp.w2.weight"] = de8(st.f32(p + "fc1.w"))
+                out[r + "mlp.w1.bias"], out[r + "mlp.w2.bias"] = de8(st.f32(p + "fc1.b"))
+                out[r + "mlp.w3.weight"] = st.f32(p + "fc2.w").clone(); out[r + "mlp.w3.bias"] = st.f32(p + "fc2.b").clone()
+            out[pre_ref + "norm.weight"] = st.f32(pre + "norm_w").clone()
+            if ln: out[pre_ref + "norm.bias"] = st.f32(pre + "norm_b").clone()
+
+        ps = c.vision_patch_size
+        out["trunk.patch_embed.proj.weight"] = st.f32("trunk.patch.w").reshape(self.D, 3, ps, ps).clone()
+        out["trunk.patch_embed.proj.bias"] = st.f32("trunk.patch.b").clone()
+        out["trunk.cls_token"] = st.f32("trunk.cls").reshape(1, 1, -1).clone()
+        out["trunk.mask_token"] = st.f32("trunk.mask_token").reshape(1, -1).clone()
+        vit("trunk.", "trunk.", c.vision_depth, False)
+        out["trunk.feature_bottleneck.weight"] = st.f32("trunk.bneck.w").clone()
+        out["visual_proj.weight"] = st.f32("visual_proj.w").clone()
+        out["pixel_decoder.proj_in.weight"] = st.f32("decoder.proj_in.w").reshape(self.Dd, self.bn, 1, 1).clone()
+        out["pixel_decoder.proj_in.bias"] = st.f32("decoder.proj_in.b").clone()
+        vit("pixel_decoder.", "decoder.", c.decoder_depth, True)
+        out["pixel_decoder.proj_out.weight"] = st.f32("decoder.proj_out.w").reshape(768, self.Dd, 1, 1).clone()
+        out["pixel_decoder.proj_out.bias"] = st.f32("decoder.proj_out.b").clone()
+        out["token_embedding.weight"] = st.f32("text.tok_emb").clone(); out["positional_embedding"] = st.f32("text.pos").clone()
+        for i in range(c.text_depth):
+            r, p = f"text_transformer.resblocks.{i}.", f"text.blocks.{i}."
+            for a, b_ in (("ln_1.weight", "n1_w"), ("ln_1.bias", "n1_b"), ("ln_2.weight", "n2_w"), ("ln_2.bias", "n2_b"),
+                          ("attn.in_proj_weight", "qkv.w"), ("attn.in_proj_bias", "qkv.b"), ("attn.out_proj.weight", "proj.w"),
+                          ("attn.out_proj.bias", "proj.b"), ("mlp.c_fc.weight", "fc1.w"), ("mlp.c_fc.bias", "fc1.b"),
+                          ("mlp.c_proj.weight", "fc2.w"), ("mlp.c_proj.bias", "fc2.b")):
+                out[r + a] = st.f32(p + b_).clone()
+        out["ln_final.weight"] = st.f32("text.norm_w").clone(); out["ln_final.bias"] = st.f32("text.norm_b").clone()
+        out["text_projection"] = st.f32("text.proj.w").t().contiguous()
+        out["logit_scale"] = st.f32("logit_scale").reshape(()).clone()
+        from .rope import rope_periods
+        out["trunk.rope_embed.periods"] = rope_periods(64).to(self.device)
+        out["pixel_decoder.rope_embed.periods"] = rope_periods(64).to(self.device)
+        return out
+
+    # -------------------------------------------------------------- pieces shared by the objectives
+    def _trunk_fwd(self, W: TowerW, img, tape: Optional[dict], mask_idx=None):
+        x, meta = E.trunk_forward(W, img, "bf16", mask_idx=mask_idx, tape=tape)
+        return x, meta
+
+    def _trunk_bwd(self, tape: dict, g: torch.Tensor, mask_idx=None):
+        """g fp32 [B*T, D] = dL/d(x_prenorm) -> accumulates all trunk parameter gradients."""
+        W, G = self.towers[("trunk", "param")], self.towers[("trunk", "grad")]
+        B, T, gh, gw = tape["meta"]
+        D, HW = W.D, gh * gw
+        rope = W.rope(gh, gw, g.device)
+        tower_blocks_backward(W, G, tape["blocks"], g, B, T, rope)
+        gp = _e((B * HW, D), BF, g.device)
+        lib.strip_prefix(g, gp, G.extra["cls"], B, T, 1, D)
+        if mask_idx is not None and mask_idx.numel() > 0:
+            rows = (mask_idx // HW) * T + 1 + mask_idx % HW
+            tmp = _e((mask_idx.numel(), D), F32, g.device)
+            lib.gather_rows(g, tmp, rows, D)
+            lib.cast_colsum(tmp, None, G.extra["mask_token"], mask_idx.numel(), D)
+            zeros = torch.zeros(D, dtype=F32, device=g.device)
+            lib.apply_mask_tokens(gp, zeros, mask_idx, HW, HW, 0, D)
+        wgrad(gp, tape["patch_a"], G.extra["patch"].w, B * HW)
+        lib.cast_colsum(gp, None, G.extra["patch"].b, B * HW, D)
+
+    # -------------------------------------------------------------- objective 1: CLIP (vtp.py:340-363 + ClipLoss)
+    def clip_fwd_bwd(self, image: torch.Tensor, text: torch.Tensor, weight: float = 1.0):
+        import torch.distributed as dist
+        dev = self.device
+        W, G = self.towers[("trunk", "param")], self.towers[("trunk", "grad")]
+        Wt, Gt = self.towers[("text", "param")], self.towers[("text", "grad")]
+        D, Dt = self.D, self.Dt
+        # ---- image tower -> cls -> visual_proj -> normalise
+        tp_i = {}
+        x, (B, T, gh, gw) = self._trunk_fwd(W, image, tp_i)
+        M = B * T
+        nt = {}
+        xn = E.norm(x, M, D, W.norm_w, None, W.eps, "bf16", want="f32", tape=nt)
+        cls_rows = torch.arange(B, device=dev, dtype=torch.long) * T
+        cls = _e((B, D), BF, dev)
+        lib.gather_rows(xn, cls, cls_rows, D)
+        vp: Lin = W.extra["visual_proj"]
+        fi_raw = _e((B, Dt), BF, dev)
+        lib.gemm(cls, vp.w, fi_raw, M=B, N=Dt, K=D)
+        nrm_i = _e((B,), F32, dev)
+        fi = torch.empty_like(fi_raw)
+        lib.l2norm_fwd(fi_raw, fi, B, Dt, 1e-12, norm_out=nrm_i)
+        # ---- text tower
+        tp_t = {}
+        ft_raw = E.text_forward(Wt, text, "bf16", tape=tp_t)
+        nrm_t = _e((B,), F32, dev)
+        ft = torch.empty_like(ft_raw)
+        lib.l2norm_fwd(ft_raw, ft, B, Dt, 1e-12, norm_out=nrm_t)
+        # ---- contrastive loss over the global batch (features all-gathered: collective C2)
+        if self.world > 1:
+            fi_all = _e((self.world * B, Dt), BF, dev)
+            ft_all = _e((self.world * B, Dt), BF, dev)
+            dist.all_gather_into_tensor(fi_all, fi, group=self.pg)
+            dist.all_gather_into_tensor(ft_all, ft, group=self.pg)
+        else:
+            fi_all, ft_all = fi, ft
+        Bg = fi_all.shape[0]
+        Bgp = (Bg + 7) // 8 * 8
+        sim_i = _e((B, Bgp), F32, dev)
+        sim_t = _e((B, Bgp), F32, dev)
+        pad = lambda t: t if Bg == Bgp else torch.cat([t, torch.zeros(Bgp - Bg, Dt, dtype=BF, device=dev)])
+        fi_allp, ft_allp = pad(fi_all), pad(ft_all)
+        lib.gemm(fi, ft_allp, sim_i, M=B, N=Bgp, K=Dt, round_bf16=False)
+        lib.gemm(ft, fi_allp, sim_t, M=B, N=Bgp, K=Dt, round_bf16=False)
+        Gi = torch.zeros((B, Bgp), dtype=BF, device=dev)
+        Gt_ = torch.zeros((B, Bgp), dtype=BF, device=dev)
+        ls = self.store.f32("logit_scale")
+        dls = self.store.grad("logit_scale")
+        coef = weight * 0.5 / B
+        lib.softmax_ce(sim_i, B, Bg, self.rank * B, Gi, coef, self.loss_acc[0:1], dls, log_scale=ls)
+        lib.softmax_ce(sim_t, B, Bg, self.rank * B, Gt_, coef, self.loss_acc[0:1], dls, log_scale=ls)
+        # d f_i(local) = Gi · T_all + [Gtᵀ · T_local]_(all ranks summed, local slice)   (and symmetrically for text)
+        dfi = _e((B, Dt), F32, dev)
+        dft = _e((B, Dt), F32, dev)
+        lib.gemm(Gi, ft_allp, dfi, M=B, N=Dt, K=Bgp, b_mn=True, ldb=Dt, round_bf16=False)
+        lib.gemm(Gt_, fi_allp, dft, M=B, N=Dt, K=Bgp, b_mn=True, ldb=Dt, round_bf16=False)
+        if self.world > 1:
+            cross_i = _e((Bgp, Dt), F32, dev)
+            cross_t = _e((Bgp, Dt), F32, dev)
+            lib.gemm(Gt_, ft, cross_i, M=Bgp, N=Dt, K=B, a_mn=True, b_mn=True, lda=Bgp, ldb=Dt, round_bf16=False)
+            lib.gemm(Gi, fi, cross_t, M=Bgp, N=Dt, K=B, a_mn=True, b_mn=True, lda=Bgp, ldb=Dt, round_bf16=False)
+            dist.all_reduce(cross_i, group=self.pg)
+            dist.all_reduce(cross_t, group=self.pg)
+            lib.axpby(dfi, cross_i[self.rank * B:(self.rank + 1) * B].contiguous(), 1.0, 1.0, B * Dt)
+            lib.axpby(dft, cross_t[self.rank * B:(self.rank + 1) * B].contiguous(), 1.0, 1.0, B * Dt)
+        else:
+            lib.gemm(Gt_, ft, dfi, M=B, N=Dt, K=B, a_mn=True, b_mn=True, lda=Bgp, ldb=Dt, accumulate=True, round_bf16=False)
+            lib.gemm(Gi, fi, dft, M=B, N=Dt, K=B, a_mn=True, b_mn=True, lda=Bgp, ldb=Dt, accumulate=True, round_bf16=False)
+        # ---- image side backward
+        dfi_raw = _e((B, Dt), BF, dev)
+        lib.l2norm_bwd(fi, nrm_i, dfi, dfi_raw, B, Dt)
+        dxn = torch.zeros((M, D), dtype=BF, device=dev)
+        dgrad(dfi_raw, vp.w, dxn, B, ldo=T * D)          # row b of d(cls) lands on token row b*T
+        wgrad(dfi_raw, cls, G.extra["visual_proj"].w, B)
+        g = torch.zeros((M, D), dtype=F32, device=dev)
+        lib.norm_bwd(x, nt["rstd"], None, W.norm_w, dxn, g, G.norm_w, None, M, D)
+        self._trunk_bwd(tp_i, g)
+        # ---- text side backward
+        self._text_bwd(tp_t, ft, nrm_t, dft, text)
+
+    def _text_bwd(self, tape, ft, nrm_t, dft, ids):
+        dev = self.device
+        Wt, Gt = self.towers[("text", "param")], self.towers[("text", "grad")]
+        B, L = tape["meta"]
+        Dt, M = self.Dt, B * L
+        dft_raw = _e((B, Dt), BF, dev)
+        lib.l2norm_bwd(ft, nrm_t, dft, dft_raw, B, Dt)
+        proj: Lin = Wt.extra["proj"]
+        dpool = _e((B, Dt), F32, dev)
+        dgrad(dft_raw, proj.w, dpool, B)
+        wgrad(dft_raw, tape["pooled"], Gt.extra["proj"].w, B)
+        dxn32 = torch.zeros((M, Dt), dtype=F32, device=dev)
+        lib.scatter_add_rows(dpool, dxn32, tape["eot"], Dt)
+        dxn = _e((M, Dt), BF, dev)
+        lib.cast_colsum(dxn32, dxn, None, M, Dt)
+        g = torch.zeros((M, Dt), dtype=F32, device=dev)
+        nf = tape["nf"]
+        lib.norm_bwd(tape["x_final"], nf["rstd"], nf["mean"], Wt.norm_w, dxn, g, Gt.norm_w, Gt.norm_b, M, Dt)
+        tower_blocks_backward(Wt, Gt, tape["blocks"], g, B, L, None, causal=True)
+        lib.scatter_add_rows(g, Gt.extra["tok_emb"], ids.reshape(-1), Dt)
+        lib.cast_colsum(g, None, Gt.extra["pos"].view(-1), B, L * Dt, ldx=L * Dt)
+
+    # -------------------------------------------------------------- objective 3: reconstruction (vtp.py:487-512)
+    def rec_fwd_bwd(self, image: torch.Tensor, weight: float = 1.0, return_image: bool = False):
+        dev = self.device
+        W, G = self.towers[("trunk", "param")], self.towers[("trunk", "grad")]
+        Wd, Gd = self.towers[("decoder", "param")], self.towers[("decoder", "grad")]
+        D, Dd, bn = self.D, self.Dd, self.bn
+        tp_e = {}
+        x, (B, T, gh, gw) = self._trunk_fwd(W, image, tp_e)
+        M, HW = B * T, gh * gw
+        Md = B * HW
+        nt = {}
+        xn = E.norm(x, M, D, W.norm_w, None, W.eps, "bf16", want="op", tape=nt)
+        bneck: Lin = W.extra["bneck"]
+        tok = _e((Md, bn), BF, dev)                      # latents as decoder tokens (cls rows dropped in the epilogue)
+        lib.gemm(xn, bneck.w, tok, M=M, N=bn, K=D, rr_group=T, rr_skip=-1)
+        # ---- decoder (decoders/pixel_decoder.py:134-162) on token-major latents
+        pin: Lin = Wd.extra["proj_in"]
+        xd = _e((Md, Dd), BF, dev)
+        lib.gemm(tok, pin.w, xd, M=Md, N=Dd, K=bn, bias=pin.b)
+        rope = Wd.rope(gh, gw, dev)
+        dtape = []
+        xd = E.tower_blocks(Wd, xd, B, HW, rope, "bf16", tape=dtape)
+        ntd = {}
+        xdn = E.norm(xd, Md, Dd, Wd.norm_w, Wd.norm_b, Wd.eps, "bf16", want="op", tape=ntd)
+        pout: Lin = Wd.extra["proj_out"]
+        r = 16
+        rec = _e((B, 3, gh * r, gw * r), BF, dev)
+        lib.gemm(xdn, pout.w, rec, M=Md, N=pout.N, K=Dd, bias=pout.b, pixel_shuffle=(r, gh, gw, 3), ldo=gw * r)
+        # ---- loss: L1 (+ LPIPS gradient if a perceptual module is attached)
+        dlp = None
+        if getattr(self, "lpips", None) is not None and self.tc.lpips_weight > 0:
+            dlp = self.lpips.loss_and_grad(rec, image, weight * self.tc.lpips_weight / B, self.loss_acc[5:6])
+        dY = _e((Md, pout.N), BF, dev)
+        lib.recon_l1_grad(rec, image.contiguous(), dlp, dY, self.loss_acc[4:5], B, 3, gh, gw, r, weight / rec.numel())
+        # ---- decoder backward
+        dxdn = _e((Md, Dd), BF, dev)
+        dgrad(dY, pout.w, dxdn, Md)
+        wgrad(dY, xdn, Gd.extra["proj_out"].w, Md)
+        lib.cast_colsum(dY, None, Gd.extra["proj_out"].b, Md, pout.N)
+        g = torch.zeros((Md, Dd), dtype=F32, device=dev)
+        lib.norm_bwd(xd, ntd["rstd"], ntd["mean"], Wd.norm_w, dxdn, g, Gd.norm_w, Gd.norm_b, Md, Dd)
+        tower_blocks_backward(Wd, Gd, dtape, g, B, HW, rope)
+        gb = _e((Md, Dd), BF, dev)
+        lib.cast_colsum(g, gb, Gd.extra["proj_in"].b, Md, Dd)
+        dz = torch.zeros((M, bn), dtype=BF, device=dev)  # d(latent tokens), re-expanded to [B*T] rows (cls rows = 0)
+        dgrad(gb, pin.w, dz, Md, rr_group=HW, rr_skip=1)
+        wgrad(gb, tok, Gd.extra["proj_in"].w, Md)
+        # ---- encoder side
+        dxn = _e((M, D), BF, dev)
+        dgrad(dz, bneck.w, dxn, M)
+        wgrad(dz, xn, G.extra["bneck"].w, M)
+        ge = torch.zeros((M, D), dtype=F32, device=dev)
+        lib.norm_bwd(x, nt["rstd"], None, W.norm_w, dxn, ge, G.norm_w, None, M, D)
+        self._trunk_bwd(tp_e, ge)
+        return rec if return_image else None
+
+    # -------------------------------------------------------------- DINO head (heads/dino_head.py:65-126)
+    def _head_prepare(self):
+        W, Wt = self.towers[("trunk", "param")], self.towers[("trunk", "teacher")]
+        K, hb = self.tc.head_out_dim, self.tc.head_bottleneck
+        lib.weight_norm_fwd(W.extra["last_v"], W.extra["last_g"], self.head_wn, self.head_vnorm, K, hb)
+        lib.weight_norm_fwd(Wt.extra["last_v"], Wt.extra["last_g"], self.head_wn_t, None, K, hb)
+
+    def _head_fwd(self, W: TowerW, wn: torch.Tensor, x: torch.Tensor, tape: Optional[dict]):
+        dev = self.device
+        Tn, D = x.shape
+        hh, hb, K = self.tc.head_hidden, self.tc.head_bottleneck, self.tc.head_out_dim
+        m0, m2, m4 = W.extra["mlp0"], W.extra["mlp2"], W.extra["mlp4"]
+        pre1 = _e((Tn, hh), BF, dev) if tape is not None else None
+        h1 = _e((Tn, hh), BF, dev)
+        lib.gemm(x, m0.w, h1, M=Tn, N=hh, K=D, bias=m0.b, act=lib.ACT_GELU, out2=pre1)
+        pre2 = _e((Tn, hh), BF, dev) if tape is not None else None
+        h2 = _e((Tn, hh), BF, dev)
+        lib.gemm(h1, m2.w, h2, M=Tn, N=hh, K=hh, bias=m2.b, act=lib.ACT_GELU, out2=pre2)
+        h3 = _e((Tn, hb), BF, dev)
+        lib.gemm(h2, m4.w, h3, M=Tn, N=hb, K=hh, bias=m4.b)
+        y = _e((Tn, hb), BF, dev)
+        nrm = _e((Tn,), F32, dev)
+        lib.l2norm_fwd(h3, y, Tn, hb, 1e-12, norm_out=nrm)
+        logits = _e((Tn, K), BF, dev)
+        lib.gemm(y, wn, logits, M=Tn, N=K, K=hb)
+        if tape is not None:
+            tape.update(x=x, pre1=pre1, h1=h1, pre2=pre2, h2=h2, y=y, nrm=nrm)
+        return logits
+
+    def _head_bwd(self, tape: dict, dlogits: torch.Tensor) -> torch.Tensor:
+        dev = self.device
+        W, G = self.towers[("trunk", "param")], self.towers[("trunk", "grad")]
+        Tn = dlogits.shape[0]
+        hh, hb, K, D = self.tc.head_hidden, self.tc.head_bottleneck, self.tc.head_out_dim, self.D
+        dy = _e((Tn, hb), F32, dev)
+        dgrad(dlogits, self.head_wn, dy, Tn)
+        dWn = torch.zeros((K, hb), dtype=F32, device=dev)
+        wgrad(dlogits, tape["y"], dWn, Tn)
+        lib.weight_norm_bwd(W.extra["last_v"], W.extra["last_g"], self.head_vnorm, dWn, G.extra["last_v"],
+                            G.extra["last_g"], K, hb)
+        dh3 = _e((Tn, hb), BF, dev)
+        lib.l2norm_bwd(tape["y"], tape["nrm"], dy, dh3, Tn, hb)
+        m0, m2, m4 = W.extra["mlp0"], W.extra["mlp2"], W.extra["mlp4"]
+        g0, g2, g4 = G.extra["mlp0"], G.extra["mlp2"], G.extra["mlp4"]
+        lib.cast_colsum(dh3, None, g4.b, Tn, hb)
+        dh2 = _e((Tn, hh), BF, dev)
+        dgrad(dh3, m4.w, dh2, Tn)
+        wgrad(dh3, tape["h2"], g4.w, Tn)
+        dpre2 = _e((Tn, hh), BF, dev)
+        lib.gelu_bwd(tape["pre2"], dh2, dpre2, g2.b, Tn, hh)
+        dh1 = _e((Tn, hh), BF, dev)
+        dgrad(dpre2, m2.w, dh1, Tn)
+        wgrad(dpre2, tape["h1"], g2.w, Tn)
+        dpre1 = _e((Tn, hh), BF, dev)
+        lib.gelu_bwd(tape["pre1"], dh1, dpre1, g0.b, Tn, hh)
+        dx = _e((Tn, D), BF, dev)
+        dgrad(dpre1, m0.w, dx, Tn)
+        wgrad(dpre1, tape["x"], g0.w, Tn)
+        return dx
+
+    # -------------------------------------------------------------- objective 2: SSL (vtp.py:365-386,410-484)
+    def ssl_fwd_bwd(self, global_crops, local_crops, mask_indices, masks_weight, weight: float = 1.0):
+        """global_crops [2B,3,H,W] (view-major), local_crops [n_local*B,3,h,w] (crop-major), mask_indices int64 flat
+        indices into [2B*HW] of masked global patches, masks_weight [n_masked] = 1/(#masked in that image)."""
+        import torch.distributed as dist
+        dev, tc = self.device, self.tc
+        W, G, Wt = self.towers[("trunk", "param")], self.towers[("trunk", "grad")], self.towers[("trunk", "teacher")]
+        D, K = self.D, tc.head_out_dim
+        self._head_prepare()
+        n_loc = tc.n_local_crops
+        B2 = global_crops.shape[0]
+        B = B2 // 2
+        n_m = mask_indices.numel()
+        # ---------------- teacher (no grad): get_teacher_forward_outputs vtp.py:410-450
+        xt, (_, T, gh, gw) = self._trunk_fwd(Wt, global_crops, None)
+        HW = gh * gw
+        xnt = E.norm(xt, B2 * T, D, Wt.norm_w, None, Wt.eps, "bf16", want="f32")
+        ar = torch.arange(B2, device=dev, dtype=torch.long)
+        cls_rows = ar * T
+        swapped = torch.cat([cls_rows[B:], cls_rows[:B]])                       # cat(chunk[1], chunk[0])
+        m_rows = (mask_indices // HW) * T + 1 + mask_indices % HW
+        Tt = B2 + n_m
+        tin = _e((Tt, D), BF, dev)
+        lib.gather_rows(xnt, tin, torch.cat([swapped, m_rows]), D)
+        tlog = self._head_fwd(Wt, self.head_wn_t, tin, None)
+        # centre statistics (batch mean of raw teacher logits), then centred + sharpened softmax in place
+        csum = torch.zeros((2, K), dtype=F32, device=dev)
+        lib.cast_colsum(tlog, None, csum[0], B2, K)
+        if n_m:
+            lib.cast_colsum(tlog[B2:], None, csum[1], n_m, K)
+        lib.dino_teacher_probs(tlog, self.center_dino, B2, K, tc.teacher_temp)
+        if n_m:
+            lib.dino_teacher_probs(tlog[B2:], self.center_ibot, n_m, K, tc.teacher_temp)
+        cnt = torch.tensor([float(B2), float(max(n_m, 1))], device=dev)
+        if self.world > 1:
+            dist.all_reduce(csum, group=self.pg)
+            dist.all_reduce(cnt, group=self.pg)
+        del xt, xnt
+        # ---------------- student: get_student_ssl_outputs vtp.py:452-484
+        tp_g, tp_l = {}, {}
+        xg, _ = self._trunk_fwd(W, global_crops, tp_g, mask_idx=mask_indices)
+        xl, (Bl, Tl, ghl, gwl) = self._trunk_fwd(W, local_crops, tp_l)
+        ntg, ntl = {}, {}
+        xng = E.norm(xg, B2 * T, D, W.norm_w, None, W.eps, "bf16", want="f32", tape=ntg)
+        xnl = E.norm(xl, Bl * Tl, D, W.norm_w, None, W.eps, "bf16", want="f32", tape=ntl)
+        l_rows = torch.arange(Bl, device=dev, dtype=torch.long) * Tl
+        Ts = Bl + B2 + n_m
+        sin_ = _e((Ts, D), BF, dev)
+        lib.gather_rows(xnl, sin_[:Bl], l_rows, D)
+        lib.gather_rows(xng, sin_[Bl:], torch.cat([cls_rows, m_rows]), D)
+        htape = {}
+        slog = self._head_fwd(W, self.head_wn, sin_, htape)
+        # ---------------- losses (DINOv2 DINOLoss / iBOTPatchLoss, see oracle.dino_ibot_loss)
+        n_terms = 2 + 2 * n_loc
+        bidx = torch.arange(B, device=dev, dtype=torch.int32)
+        t0 = torch.cat([bidx.repeat(n_loc), torch.arange(B2, device=dev, dtype=torch.int32),
+                        B2 + torch.arange(n_m, device=dev, dtype=torch.int32)])
+        t1 = torch.cat([(B + bidx).repeat(n_loc), torch.full((B2 + n_m,), -1, device=dev, dtype=torch.int32)])
+        wl = weight / (B * n_terms)
+        wrow = torch.cat([torch.full((Bl,), wl, device=dev), torch.full((B2,), wl, device=dev),
+                          masks_weight.to(F32) * (weight / B)])
+        lib.dino_student_ce(slog[:Bl], tlog, t0[:Bl], t1[:Bl], wrow[:Bl], Bl, K, tc.student_temp, self.loss_acc[1:2])
+        lib.dino_student_ce(slog[Bl:Bl + B2], tlog, t0[Bl:Bl + B2], t1[Bl:Bl + B2], wrow[Bl:Bl + B2], B2, K,
+                            tc.student_temp, self.loss_acc[2:3])
+        if n_m:
+            lib.dino_student_ce(slog[Bl + B2:], tlog, t0[Bl + B2:], t1[Bl + B2:], wrow[Bl + B2:], n_m, K,
+                                tc.student_temp, self.loss_acc[3:4])
+        # teacher centre EMA (DINOv2 softmax_center_teacher / update_center)
+        cm = tc.center_momentum
+        mean = csum / cnt[:, None]
+        lib.axpby(self.center_dino, mean[0].contiguous(), cm, 1 - cm, K)
+        lib.axpby(self.center_ibot, mean[1].contiguous(), cm, 1 - cm, K)
+        del tlog
+        # ---------------- backward: head -> scatter to the two trunk passes
+        dsin = self._head_bwd(htape, slog)
+        del slog, htape
+        dl32 = torch.zeros((Bl * Tl, D), dtype=F32, device=dev)
+        lib.scatter_add_rows(dsin[:Bl], dl32, l_rows, D)
+        dxl = _e((Bl * Tl, D), BF, dev)
+        lib.cast_colsum(dl32, dxl, None, Bl * Tl, D)
+        gl = dl32.zero_()
+        lib.norm_bwd(xl, ntl["rstd"], None, W.norm_w, dxl, gl, G.norm_w, None, Bl * Tl, D)
+        self._trunk_bwd(tp_l, gl)
+        del gl, dl32, dxl, xl, xnl, tp_l
+        dg32 = torch.zeros((B2 * T, D), dtype=F32, device=dev)
+        lib.scatter_add_rows(dsin[Bl:], dg32, torch.cat([cls_rows, m_rows]), D)
+        dxg = _e((B2 * T, D), BF, dev)
+        lib.cast_colsum(dg32, dxg, None, B2 * T, D)
+        gg = dg32.zero_()
+        lib.norm_bwd(xg, ntg["rstd"], None, W.norm_w, dxg, gg, G.norm_w, None, B2 * T, D)
+        self._trunk_bwd(tp_g, gg, mask_idx=mask_indices)
+
+    # -------------------------------------------------------------- optimiser (+ EMA teacher, vtp.py:388-401)
+    def allreduce_grads(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.store.g, group=self.pg)   # collective C3; averaged by grad_scale in the optimiser
+
+    def optimizer_step(self):
+        st, tc = self.store, self.tc
+        self.step_count += 1
+        for start, end, decay, teacher in st.regions:
+            n = end - start
+            lib.adamw_step(st.p[start:end], st.g[start:end], st.m[start:end], st.v[start:end], st.pb[start:end],
+                           st.tp[start:end] if teacher else None, st.tpb[start:end] if teacher else None, n,
+                           lr=tc.lr, beta1=tc.beta1, beta2=tc.beta2, eps=tc.eps, wd=tc.weight_decay if decay else 0.0,
+                           step=self.step_count, grad_scale=1.0 / self.world, ema_momentum=tc.teacher_momentum)
+
+    def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
+        """One full 3-objective step. Returns the device tensor of accumulated loss terms
+        [clip, dino_local, dino_global, ibot, rec_l1, lpips, -, -] (read it with .cpu() to synchronise)."""
+        tc = self.tc
+        self.loss_acc.zero_()
+        if tc.w_clip:
+            self.clip_fwd_bwd(batch["image"], batch["text"], tc.w_clip)
+        if tc.w_ssl:
+            self.ssl_fwd_bwd(batch["global_crops"], batch["local_crops"], batch["mask_indices"], batch["masks_weight"],
+                             tc.w_ssl)
+        if tc.w_rec:
+            self.rec_fwd_bwd(batch["rec_image"], tc.w_rec)
+        self.allreduce_grads()
+        self.optimizer_step()
+        return self.loss_acc
