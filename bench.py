@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""Benchmark of the VTP hot path on B200 (contract: see the task brief / DESIGN.md §Measurement).
+
+  python bench.py --gpus N --steps K --warmup W            our arm  (one rank per GPU under torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  reference arm: the CPU restatement of the reference's step
+                                                           (oracle/train_step.py) on the box's host cores, rank 0 only
+
+Workload (BASELINE.json configs[1]): VTP-Small f16d64, full 3-loss training step (contrastive + DINO/iBOT + recon),
+batch 256 per GPU, 256x256 synthetic RGB, 2 global + 8 local(96) crops, K=65536 prototypes, AdamW + EMA teacher.
+Prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "images/sec (256x256 encode+decode+3-loss step)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="small")
+    ap.add_argument("--batch", type=int, default=256, help="source images per GPU per step")
+    ap.add_argument("--prototypes", type=int, default=65536)
+    ap.add_argument("--cpu-batch", type=int, default=2, help="source images per step of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])), mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_baseline(args, steps: int, warmup: int):
+    """The reference's step restated on the CPU oracle (towers + restated losses + AdamW + EMA), bounded sample."""
+    import torch
+
+    from oracle.seeded import seeded_state_dict
+    from oracle.train_step import OracleTrainer
+    from vtp_b200.config import preset
+    from vtp_b200.model import VTPModel
+    from vtp_b200.synthetic import make_batch
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = preset(args.model)
+    m = VTPModel(cfg)
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    K = args.prototypes
+    g = torch.Generator().manual_seed(0)
+    D = cfg.vision_embed_dim
+    hsd = {"mlp.0.weight": torch.randn(2048, D, generator=g) * 0.02, "mlp.0.bias": torch.zeros(2048),
+           "mlp.2.weight": torch.randn(2048, 2048, generator=g) * 0.02, "mlp.2.bias": torch.zeros(2048),
+           "mlp.4.weight": torch.randn(256, 2048, generator=g) * 0.02, "mlp.4.bias": torch.zeros(256),
+           "last_layer.weight_g": torch.ones(K, 1), "last_layer.weight_v": torch.randn(K, 256, generator=g) * 0.02}
+    dims = dict(vision_depth=cfg.vision_depth, vision_num_heads=cfg.vision_num_heads, text_depth=cfg.text_depth,
+                text_num_heads=cfg.text_num_heads, decoder_depth=cfg.decoder_depth, decoder_num_heads=cfg.decoder_num_heads)
+    tr = OracleTrainer(sd, hsd, dims, n_local=8, mode="bf16")
+    Bc = args.cpu_batch
+    batch = make_batch(Bc, vocab=cfg.text_vocab_size)
+    for _ in range(warmup):
+        tr.step(batch)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        tr.step(batch)
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": Bc / dt, "unit": "images/sec", "cores": cores, "kind": "port",
+            "sample": f"{steps} step(s) of the same 3-loss step at batch {Bc} (bf16-autocast emulation, torch CPU, "
+                      f"{cores} threads), {dt:.2f} s/step"}, dt
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cb, dt = cpu_baseline(args, steps=max(1, min(args.steps, 2)), warmup=min(args.warmup, 1))
+        out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+               "config": {"workload": f"VTP-{args.model} full 3-loss training step, CPU restatement of the reference "
+                                      f"(oracle port), bounded sample of {args.cpu_batch} images/step"},
+               "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from vtp_b200 import lib
+    from vtp_b200.config import preset
+    from vtp_b200.flops import train_step_flops_per_image
+    from vtp_b200.synthetic import batch_bytes, make_batch, to_device
+    from vtp_b200.train import TrainConfig, VTPTrainer
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    cfg = preset(args.model)
+    tc = TrainConfig(head_out_dim=args.prototypes)
+    tr = VTPTrainer(cfg, tc, device=dev)
+    B = args.batch
+    host = make_batch(B, vocab=cfg.text_vocab_size, seed=1234 + rank, pin=True)
+    resident = to_device(host, dev, non_blocking=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for _ in range(args.warmup):
+        tr.train_step(resident)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident timing ("value")
+    l0 = lib.LAUNCHES
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        loss = tr.train_step(resident)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    launches = lib.LAUNCHES - l0
+    # ---- end-to-end timing: pinned host inputs -> H2D -> step -> D2H of the loss vector, every step
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d = batch_bytes(host)
+    e2.record()
+    for _ in range(args.steps):
+        dev_batch = to_device(host, dev, non_blocking=True)
+        loss = tr.train_step(dev_batch)
+        loss_host = loss.cpu()
+    e3.record()
+    barrier()
+    ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- dominant kernel: the tcgen05 GEMM, timed live on its largest recurring shape (SSL student FFN fc1)
+    Mg, Ng, Kg = 2 * B * 257, 2 * tr.hs, tr.D
+    A = torch.randn(Mg, Kg, device=dev).to(torch.bfloat16)
+    Wt = torch.randn(Ng, Kg, device=dev).to(torch.bfloat16)
+    bias = torch.zeros(Ng, device=dev)
+    outg = torch.empty(Mg, Ng // 2, device=dev, dtype=torch.bfloat16)
+    for _ in range(3):
+        lib.gemm(A, Wt, outg, M=Mg, N=Ng, K=Kg, bias=bias, act=lib.ACT_SWIGLU8, ldo=Ng // 2)
+    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    torch.cuda.synchronize()
+    g0.record()
+    for _ in range(reps):
+        lib.gemm(A, Wt, outg, M=Mg, N=Ng, K=Kg, bias=bias, act=lib.ACT_SWIGLU8, ldo=Ng // 2)
+    g1.record()
+    torch.cuda.synchronize()
+    gemm_ms = g0.elapsed_time(g1) / reps
+    gemm_tflops = 2.0 * Mg * Ng * Kg / (gemm_ms * 1e-3) / 1e12
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_burst = peaks.get("bf16_tflops", 1590.0)
+    peak_sust = peaks.get("bf16_tflops_sustained", 1400.0)
+    src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    fl = train_step_flops_per_image(cfg, K=args.prototypes)
+    imgs = B * world * args.steps
+    value = imgs / (ms * 1e-3)
+    step_tflops = fl["total"] * B / (ms / args.steps * 1e-3) / 1e12  # per GPU
+    out = {
+        "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"VTP-{args.model} f16d64 full 3-loss training step (contrastive+SSL+recon), batch={B}/GPU",
+                   "model": "VTP-Small 384/12/6 x3 towers (ASSUMED, SURVEY.md §8d)" if args.model == "small" else args.model,
+                   "global_batch": B * world, "image": 256, "crops": "2 global 256 + 8 local 96 per image",
+                   "prototypes": args.prototypes, "losses": ["clip", "dino_local", "dino_global", "ibot", "rec_l1"],
+                   "lpips": False, "optimizer": "fused AdamW + EMA teacher, in the timed region",
+                   "l2": "inputs (>1 GB/step) and activations far exceed the 126 MB L2; no reuse across steps",
+                   "parallelism": f"dp{world}", "flops_per_image": fl["total"]},
+        "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "kernel": f"vtp::gemm_kernel<256,4> SwiGLU-gate GEMM M={Mg} N={Ng} K={Kg}",
+                     "achieved": gemm_tflops, "peak": peak_burst, "unit": "TFLOP/s", "frac": gemm_tflops / peak_burst,
+                     "peak_source": src + " burst (kernel timed alone)", "traffic": None,
+                     "step": {"achieved": step_tflops, "peak": peak_sust, "frac": step_tflops / peak_sust,
+                              "note": "whole-step algorithmic FLOPs (vtp_b200/flops.py) / step time vs sustained bf16 peak"}},
+        "loss": [round(float(x), 5) for x in loss_host[:5]],
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cb, _ = cpu_baseline(args, steps=1, warmup=0)
+        out["cpu_baseline"] = cb
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

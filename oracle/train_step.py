@@ -76,4 +76,4 @@ class OracleTrainer:
                     self.teacher[k].mul_(self.mom).add_(v.detach(), alpha=1 - self.mom)
             for k, v in self.h.items():
                 self.teacher_h[k].mul_(self.mom).add_(v.detach(), alpha=1 - self.mom)
-        return {k: float(v) for k, v in losses.items()}
+        return {k: float(v.detach()) for k, v in losses.items()}

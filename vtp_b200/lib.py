@@ -106,7 +106,13 @@ def load() -> C.CDLL:
     return _lib
 
 
+LAUNCHES = 0  # number of C-ABI kernel launches issued by this process (every entry point launches exactly one kernel)
+
+
 def check(status: int, what: str = "") -> None:
+    global LAUNCHES
+    if what != "vtp_check_device":
+        LAUNCHES += 1
     if status != 0:
         msg = load().vtp_last_error()
         raise VtpError(f"{what} failed with status {status}: {msg.decode() if msg else ''}")
