@@ -97,7 +97,10 @@ def cpu_baseline(args, steps: int, warmup: int):
     from vtp_b200.model import VTPModel
     from vtp_b200.synthetic import make_batch
 
-    cores = os.cpu_count() or 1
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # the GPU boxes expose 128 logical CPUs; intra-op threading of these small CPU GEMMs stops scaling (and, under a
+    # cgroup CPU quota, collapses) long before that — use at most 32 threads and report the number actually used
+    cores = int(os.environ.get("VTP_CPU_THREADS", min(avail, 32)))
     torch.set_num_threads(cores)
     cfg = preset(args.model)
     m = VTPModel(cfg)
@@ -123,6 +126,11 @@ def cpu_baseline(args, steps: int, warmup: int):
     return {"value": Bc / dt, "unit": "images/sec", "cores": cores, "kind": "port",
             "sample": f"{steps} step(s) of the same 3-loss step at batch {Bc} (bf16-autocast emulation, torch CPU, "
                       f"{cores} threads), {dt:.2f} s/step"}, dt
+
+
+def log(msg):
+    if os.environ.get("RANK", "0") == "0":
+        print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
 
 
 def main():
@@ -161,9 +169,11 @@ def main():
     cfg = preset(args.model)
     tc = TrainConfig(head_out_dim=args.prototypes)
     tr = VTPTrainer(cfg, tc, device=dev)
+    log(f"trainer built: {tr.store.n / 1e6:.1f}M params")
     B = args.batch
     host = make_batch(B, vocab=cfg.text_vocab_size, seed=1234 + rank, pin=True)
     resident = to_device(host, dev, non_blocking=False)
+    log(f"batch ready: {batch_bytes(host) / 2**20:.0f} MiB/step")
 
     def barrier():
         if world > 1:
@@ -177,8 +187,10 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for _ in range(args.warmup):
+    for i in range(args.warmup):
         tr.train_step(resident)
+        torch.cuda.synchronize()
+        log(f"warmup {i} done, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -194,6 +206,7 @@ def main():
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
     launches = lib.LAUNCHES - l0
+    log(f"device-resident: {ms / args.steps:.1f} ms/step")
     # ---- end-to-end timing: pinned host inputs -> H2D -> step -> D2H of the loss vector, every step
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -206,6 +219,7 @@ def main():
     e3.record()
     barrier()
     ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+    log(f"end-to-end: {ms_e2e / args.steps:.1f} ms/step")
     clocks = sampler.stop() if rank == 0 else None
     # ---- dominant kernel: the tcgen05 GEMM, timed live on its largest recurring shape (SSL student FFN fc1)
     Mg, Ng, Kg = 2 * B * 257, 2 * tr.hs, tr.D
@@ -266,6 +280,7 @@ def main():
         "loss": [round(float(x), 5) for x in loss_host[:5]],
     }
     if world == 1 and not args.no_cpu_baseline:
+        log("cpu baseline ...")
         cb, _ = cpu_baseline(args, steps=1, warmup=0)
         out["cpu_baseline"] = cb
     print(json.dumps(out))
