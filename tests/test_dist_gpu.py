@@ -1,0 +1,76 @@
+"""2-GPU NCCL test of the data-parallel training step (skipped on a 1-GPU box): sharded CLIP+REC gradients after the
+flat all-reduce equal the single-process global-batch gradients; parameters stay bit-identical across ranks."""
+import os
+import socket
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, out):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from oracle.seeded import seeded_captions, seeded_images, seeded_state_dict
+    from tests.util import load_golden
+    from vtp_b200.config import VTPConfig
+    from vtp_b200.train import TrainConfig, VTPTrainer
+
+    meta, _ = load_golden("tiny")
+    cfg = VTPConfig(**meta["config"])
+    sd = seeded_state_dict(meta["spec"], seed=0)
+    tc = TrainConfig(head_out_dim=512, head_hidden=256, head_bottleneck=64, n_local_crops=2)
+    Bg = 8
+    B = Bg // world
+    x = seeded_images(Bg, 64, 64).cuda()
+    ids = seeded_captions(Bg, 77, 1000).cuda()
+    tr = VTPTrainer(cfg, tc, device=f"cuda:{rank}")
+    tr.import_state_dict(sd)
+    sl = slice(rank * B, (rank + 1) * B)
+    tr.clip_fwd_bwd(x[sl].contiguous(), ids[sl].contiguous(), 1.0)
+    tr.rec_fwd_bwd(x[sl].contiguous(), 1.0)
+    tr.allreduce_grads()
+    g = (tr.store.g / world).cpu()
+    loss = tr.loss_acc.clone()
+    dist.all_reduce(loss)
+    loss = (loss / world).cpu()
+    # single-process global-batch reference on the same device
+    ref = VTPTrainer(cfg, tc, device=f"cuda:{rank}")
+    ref.world, ref.rank = 1, 0
+    ref.import_state_dict(sd)
+    ref.clip_fwd_bwd(x, ids, 1.0)
+    ref.rec_fwd_bwd(x, 1.0)
+    gr = ref.store.g.cpu()
+    rel = ((g - gr).norm() / gr.norm()).item()
+    # one optimiser step on both ranks: parameters must remain identical across ranks
+    tr.optimizer_step()
+    p = tr.store.p.clone()
+    p0 = p.clone()
+    dist.broadcast(p0, src=0)
+    out[rank] = (rel, float((p - p0).abs().max()), loss.tolist(), ref.loss_acc.cpu().tolist())
+    dist.destroy_process_group()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_rank_step_equals_global_batch():
+    import torch.multiprocessing as mp
+
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    for r in range(world):
+        rel, pdiff, loss, loss_ref = out[r]
+        assert rel < 2e-2, rel                 # bf16 noise: different batch tiling of the same math
+        assert pdiff == 0.0
+        assert abs(loss[0] - loss_ref[0]) < 2e-2 * abs(loss_ref[0]) and abs(loss[4] - loss_ref[4]) < 2e-2 * loss_ref[4]
