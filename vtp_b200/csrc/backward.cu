@@ -100,25 +100,56 @@ __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restric
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < D; i += blockDim.x) {
-        atomicAdd(dw + i, sred[i]);
-        if (is_ln && db) atomicAdd(db + i, sred[D + i]);
+    for (int i = threadIdx.x * 4; i < D; i += blockDim.x * 4) {
+        atomicAdd(reinterpret_cast<float4*>(dw + i), make_float4(sred[i], sred[i + 1], sred[i + 2], sred[i + 3]));
+        if (is_ln && db)
+            atomicAdd(reinterpret_cast<float4*>(db + i),
+                      make_float4(sred[D + i], sred[D + i + 1], sred[D + i + 2], sred[D + i + 3]));
     }
 }
 
 // ------------------------------------------------------------------------------------------------ SwiGLU / GELU backward
-// pre packed [M][2Hs] (8-interleaved x1|x2, bf16), dhid [M][Hs] bf16 -> dpre [M][2Hs] bf16 ; dbias[2Hs] += colsum(dpre)
-__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dhid,
-                                  __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int Hs,
-                                  int rows_per_block) {
-    // thread -> group of 8 hidden columns; loops over the block's rows
-    const int G = Hs / 8;
-    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-    for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < G; gidx += gridDim.x * blockDim.x) {
-        float b1[8], b2[8];
+// Column-sum (bias-gradient) kernels: 2-D blocks (x = groups of columns, y = row lanes), each thread walks its rows of a
+// ROWS_PER_BLOCK strip with several independent loads in flight, partial sums are reduced across y in shared memory
+// and leave the block as ONE float4 atomic per 4 columns (same-address fp32 atomics serialise in a single L2 slice:
+// the first version issued one per 32 rows and spent 2-4x the HBM time waiting on them).
+static constexpr int CS_X = 128, CS_Y = 4, CS_ROWS = 256;
+
+template <int NF>  // NF floats of partial sums per thread
+__device__ __forceinline__ void block_colsum_flush(float (&acc)[NF], float* sh /*[CS_Y][CS_X][NF]*/, float* dst, bool active) {
+    float* mine = sh + ((threadIdx.y * CS_X + threadIdx.x) * NF);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b1[i] = 0.f, b2[i] = 0.f;
-        for (int row = r0; row < r1; ++row) {
+    for (int i = 0; i < NF; ++i) mine[i] = acc[i];
+    __syncthreads();
+    if (threadIdx.y == 0 && active) {
+#pragma unroll
+        for (int i = 0; i < NF; i += 4) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int y = 0; y < CS_Y; ++y) {
+                const float* o = sh + ((y * CS_X + threadIdx.x) * NF) + i;
+                t.x += o[0], t.y += o[1], t.z += o[2], t.w += o[3];
+            }
+            atomicAdd(reinterpret_cast<float4*>(dst + i), t);
+        }
+    }
+}
+
+// pre packed [M][2Hs] (8-interleaved x1|x2, bf16), dhid [M][Hs] bf16 -> dpre [M][2Hs] bf16 ; dbias[2Hs] += colsum(dpre)
+__global__ void __launch_bounds__(CS_X * CS_Y)
+swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dhid,
+                  __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int Hs) {
+    __shared__ float sh[CS_Y * CS_X * 16];
+    const int G = Hs / 8;
+    const int gidx = blockIdx.x * CS_X + threadIdx.x;
+    const bool active = gidx < G;
+    const int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    if (active) {
+#pragma unroll 2
+        for (int row = r0 + threadIdx.y; row < r1; row += CS_Y) {
             const uint4 x1p = *reinterpret_cast<const uint4*>(pre + (long)row * 2 * Hs + 16 * gidx);
             const uint4 x2p = *reinterpret_cast<const uint4*>(pre + (long)row * 2 * Hs + 16 * gidx + 8);
             const uint4 dhp = *reinterpret_cast<const uint4*>(dhid + (long)row * Hs + 8 * gidx);
@@ -134,34 +165,34 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const _
                     const float x2 = hlf ? bf16_hi(x2w[k]) : bf16_lo(x2w[k]);
                     const float dh = hlf ? bf16_hi(dhw[k]) : bf16_lo(dhw[k]);
                     const float sg = 1.f / (1.f + __expf(-x1));
-                    const float silu = x1 * sg;
                     d1[hlf] = dh * x2 * (sg * (1.f + x1 * (1.f - sg)));
-                    d2[hlf] = dh * silu;
-                    b1[2 * k + hlf] += d1[hlf], b2[2 * k + hlf] += d2[hlf];
+                    d2[hlf] = dh * (x1 * sg);
+                    acc[2 * k + hlf] += d1[hlf], acc[8 + 2 * k + hlf] += d2[hlf];
                 }
                 o1[k] = pack_bf16x2(d1[0], d1[1]), o2[k] = pack_bf16x2(d2[0], d2[1]);
             }
             *reinterpret_cast<uint4*>(dpre + (long)row * 2 * Hs + 16 * gidx) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
             *reinterpret_cast<uint4*>(dpre + (long)row * 2 * Hs + 16 * gidx + 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
         }
-        if (dbias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(dbias + 16 * gidx + i, b1[i]), atomicAdd(dbias + 16 * gidx + 8 + i, b2[i]);
-        }
     }
+    if (dbias) block_colsum_flush<16>(acc, sh, dbias + 16 * gidx, active);
 }
 
 // pre [M][N] bf16, dhid [M][N] bf16 -> dpre = dhid * gelu'(pre) ; dbias[N] += colsum(dpre)
-__global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dhid,
-                                __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int N,
-                                int rows_per_block) {
+__global__ void __launch_bounds__(CS_X * CS_Y)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dhid,
+                __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int N) {
+    __shared__ float sh[CS_Y * CS_X * 8];
     const int G = N / 8;
-    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-    for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < G; gidx += gridDim.x * blockDim.x) {
-        float bs[8];
+    const int gidx = blockIdx.x * CS_X + threadIdx.x;
+    const bool active = gidx < G;
+    const int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
+    float acc[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) bs[i] = 0.f;
-        for (int row = r0; row < r1; ++row) {
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    if (active) {
+#pragma unroll 2
+        for (int row = r0 + threadIdx.y; row < r1; row += CS_Y) {
             const uint4 xp = *reinterpret_cast<const uint4*>(pre + (long)row * N + 8 * gidx);
             const uint4 dp = *reinterpret_cast<const uint4*>(dhid + (long)row * N + 8 * gidx);
             const uint32_t xw[4] = {xp.x, xp.y, xp.z, xp.w}, dw[4] = {dp.x, dp.y, dp.z, dp.w};
@@ -176,43 +207,42 @@ __global__ void gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __n
                     const float cdf = 0.5f * (1.f + erff(xv * 0.70710678118654752f));
                     const float pdf = 0.3989422804014327f * __expf(-0.5f * xv * xv);
                     r[hlf] = dv * (cdf + xv * pdf);
-                    bs[2 * k + hlf] += r[hlf];
+                    acc[2 * k + hlf] += r[hlf];
                 }
                 o[k] = pack_bf16x2(r[0], r[1]);
             }
             *reinterpret_cast<uint4*>(dpre + (long)row * N + 8 * gidx) = make_uint4(o[0], o[1], o[2], o[3]);
         }
-        if (dbias) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) atomicAdd(dbias + 8 * gidx + i, bs[i]);
-        }
     }
+    if (dbias) block_colsum_flush<8>(acc, sh, dbias + 8 * gidx, active);
 }
 
 // ------------------------------------------------------------------------------------------------ cast + column sum
 // y bf16 [M][N] = (bf16) x[M][N] (TX fp32|bf16, row stride ldx) ; colsum[N] += Σ_m x  (bias gradient)
 template <typename TX>
-__global__ void cast_colsum_kernel(const TX* __restrict__ x, long ldx, __nv_bfloat16* __restrict__ y,
-                                   float* __restrict__ colsum, int M, int N, int rows_per_block) {
+__global__ void __launch_bounds__(CS_X * CS_Y)
+cast_colsum_kernel(const TX* __restrict__ x, long ldx, __nv_bfloat16* __restrict__ y, float* __restrict__ colsum, int M,
+                   int N) {
+    __shared__ float sh[CS_Y * CS_X * 4];
     const int G = N / 4;
-    const int r0 = blockIdx.y * rows_per_block, r1 = min(M, r0 + rows_per_block);
-    for (int gidx = blockIdx.x * blockDim.x + threadIdx.x; gidx < G; gidx += gridDim.x * blockDim.x) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int row = r0; row < r1; ++row) {
+    const int gidx = blockIdx.x * CS_X + threadIdx.x;
+    const bool active = gidx < G;
+    const int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (active) {
+#pragma unroll 4
+        for (int row = r0 + threadIdx.y; row < r1; row += CS_Y) {
             float v[4];
             ld4<TX>(x + (long)row * ldx + 4 * gidx, v);
-            s[0] += v[0], s[1] += v[1], s[2] += v[2], s[3] += v[3];
+            acc[0] += v[0], acc[1] += v[1], acc[2] += v[2], acc[3] += v[3];
             if (y) {
                 uint2 t;
                 t.x = pack_bf16x2(v[0], v[1]), t.y = pack_bf16x2(v[2], v[3]);
                 *reinterpret_cast<uint2*>(y + (long)row * N + 4 * gidx) = t;
             }
         }
-        if (colsum) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) atomicAdd(colsum + 4 * gidx + i, s[i]);
-        }
     }
+    if (colsum) block_colsum_flush<4>(acc, sh, colsum + 4 * gidx, active);
 }
 
 // ------------------------------------------------------------------------------------------------ L2-normalise backward
@@ -307,7 +337,9 @@ extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const
     VTP_CHECK_ARG(x && rstd && w && dy && g && dw && M > 0, "norm_bwd: bad args");
     VTP_CHECK_ARG(D % 4 == 0 && D <= 2048, "norm_bwd: D %% 4 == 0 and D <= 2048");
     VTP_CHECK_ARG(!is_ln || mean, "norm_bwd: LayerNorm needs mean");
-    const int threads = 256, rows_per_block = 64;
+    VTP_CHECK_ARG((reinterpret_cast<uintptr_t>(dw) & 15) == 0 && (!db || (reinterpret_cast<uintptr_t>(db) & 15) == 0),
+                  "norm_bwd: dw/db must be 16B aligned");
+    const int threads = D <= 512 ? 512 : 256, rows_per_block = 256;  // register budget of the wider variants
     const int grid = ceil_div(M, rows_per_block);
     const size_t smem = 2 * (size_t)D * sizeof(float);
     cudaStream_t s = (cudaStream_t)st;
@@ -330,20 +362,20 @@ extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const
 
 extern "C" int vtp_swiglu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int Hs, vtp_stream_t st) {
     VTP_CHECK_ARG(pre && dhid && dpre && M > 0 && Hs % 8 == 0, "swiglu_bwd: bad args");
-    const int rpb = 32;
-    dim3 grid(ceil_div(Hs / 8, 128), ceil_div(M, rpb));
-    swiglu_bwd_kernel<<<grid, 128, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
-                                                          (__nv_bfloat16*)dpre, dbias, M, Hs, rpb);
+    VTP_CHECK_ARG(!dbias || (reinterpret_cast<uintptr_t>(dbias) & 15) == 0, "swiglu_bwd: dbias must be 16B aligned");
+    dim3 grid(ceil_div(Hs / 8, CS_X), ceil_div(M, CS_ROWS)), block(CS_X, CS_Y);
+    swiglu_bwd_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
+                                                            (__nv_bfloat16*)dpre, dbias, M, Hs);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }
 
 extern "C" int vtp_gelu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int N, vtp_stream_t st) {
     VTP_CHECK_ARG(pre && dhid && dpre && M > 0 && N % 8 == 0, "gelu_bwd: bad args");
-    const int rpb = 32;
-    dim3 grid(ceil_div(N / 8, 128), ceil_div(M, rpb));
-    gelu_bwd_kernel<<<grid, 128, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
-                                                        (__nv_bfloat16*)dpre, dbias, M, N, rpb);
+    VTP_CHECK_ARG(!dbias || (reinterpret_cast<uintptr_t>(dbias) & 15) == 0, "gelu_bwd: dbias must be 16B aligned");
+    dim3 grid(ceil_div(N / 8, CS_X), ceil_div(M, CS_ROWS)), block(CS_X, CS_Y);
+    gelu_bwd_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
+                                                          (__nv_bfloat16*)dpre, dbias, M, N);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }
@@ -351,14 +383,14 @@ extern "C" int vtp_gelu_bwd(const void* pre, const void* dhid, void* dpre, float
 extern "C" int vtp_cast_colsum(const void* x, int x_dtype, long ldx, void* y_bf16, float* colsum, int M, int N,
                                vtp_stream_t st) {
     VTP_CHECK_ARG(x && M > 0 && N % 4 == 0 && (y_bf16 || colsum), "cast_colsum: bad args");
-    const int rpb = 32;
-    dim3 grid(ceil_div(N / 4, 128), ceil_div(M, rpb));
+    VTP_CHECK_ARG(!colsum || (reinterpret_cast<uintptr_t>(colsum) & 15) == 0, "cast_colsum: colsum must be 16B aligned");
+    dim3 grid(ceil_div(N / 4, CS_X), ceil_div(M, CS_ROWS)), block(CS_X, CS_Y);
     if (x_dtype == VTP_F32)
-        cast_colsum_kernel<float><<<grid, 128, 0, (cudaStream_t)st>>>((const float*)x, ldx, (__nv_bfloat16*)y_bf16, colsum,
-                                                                     M, N, rpb);
+        cast_colsum_kernel<float><<<grid, block, 0, (cudaStream_t)st>>>((const float*)x, ldx, (__nv_bfloat16*)y_bf16, colsum,
+                                                                       M, N);
     else
-        cast_colsum_kernel<__nv_bfloat16><<<grid, 128, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, ldx,
-                                                                             (__nv_bfloat16*)y_bf16, colsum, M, N, rpb);
+        cast_colsum_kernel<__nv_bfloat16><<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)x, ldx,
+                                                                               (__nv_bfloat16*)y_bf16, colsum, M, N);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

@@ -19,7 +19,7 @@ namespace vtp {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_BYTES = BM * BK * 2;
-static constexpr int NUM_THREADS = 192;
+static constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 
 struct GemmDev {
     int M, N, K;
@@ -44,37 +44,64 @@ struct GemmDev {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 
 // ---------------------------------------------------------------------------------------------------- epilogue
-// A 64-column unit of a 32-row warp slab is processed in two phases:
+// 8 epilogue warps (2 per SM sub-partition: with one warp per scheduler every TMEM/shared/global latency of the
+// epilogue was exposed and small-K GEMMs ran at 15 % of tensor peak).  Warp w owns TMEM lane quarter (w & 3) and the
+// 64-column units of parity (w >> 2).  A unit is processed in two phases:
 //   A (row owner: lane = TMEM lane = output row)  TMEM -> registers, +bias, rounding point, activation / RoPE
-//   B (cooperative)  the slab goes through a per-warp XOR-swizzled fp32 staging tile in shared memory so that every
-//     global access is a full, contiguous 128-byte line per half-warp: residual read, dtype conversion, store /
-//     red.add / PixelShuffle scatter.  (Writing rows straight from phase A costs one 16-byte access per row per
-//     instruction — measured 15 % of tensor peak on the FFN GEMMs.)
-static constexpr int STG_FLOATS = 32 * 64;  // per epilogue warp
+//   B (cooperative)  the slab goes, 32 columns at a time, through a per-warp XOR-swizzled fp32 staging tile (4 KB) so
+//     that every global access is a contiguous 128-byte line per quarter-warp: residual read (prefetched into registers
+//     before the accumulator is even waited for), dtype conversion, store / red.add / PixelShuffle scatter.
+static constexpr int STG_FLOATS = 32 * 32;  // per epilogue warp
+static constexpr int NUM_EPI_WARPS = 8;
 
-__device__ __forceinline__ int stg_off(int r, int chunk) { return r * 64 + ((chunk ^ (r & 15)) << 2); }
+__device__ __forceinline__ int stg_off(int r, int chunk /*0..7*/) { return r * 32 + ((chunk ^ (r & 7)) << 2); }
 
-__device__ __forceinline__ void stage_rows(float* stg, int lane, const float (&v)[64], int ncols) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c)
-        if (4 * c < ncols)
-            *reinterpret_cast<float4*>(stg + stg_off(lane, c)) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+__device__ __forceinline__ long out_row(const GemmDev& p, int grow) {
+    if (grow >= p.M) return -1;
+    if (p.rr_group <= 0) return grow;
+    if (p.rr_skip >= 0)  // expansion: leave rr_skip rows free in front of every group (cls slot)
+        return (long)(grow / p.rr_group) * (p.rr_group + p.rr_skip) + p.rr_skip + grow % p.rr_group;
+    const int tok = grow % p.rr_group;  // compaction: drop the first -rr_skip rows of every group
+    return tok < -p.rr_skip ? -1 : (long)(grow / p.rr_group) * (p.rr_group + p.rr_skip) + tok + p.rr_skip;
 }
 
-// cooperative store of the staged slab.  which = 0: main output (residual / accumulate / pixel shuffle apply),
-// which = 1: secondary bf16 output (pre-activation).
-__device__ __forceinline__ void store_slab(const GemmDev& p, const float* stg, int lane, int grow_l, long orow_l,
-                                           int ocol0, int ncols, int Nout, int which) {
-    const int cidx = lane & 15;
-    const int c4 = 4 * cidx;
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-        const int R = 2 * it + (lane >> 4);
-        const long orow = __shfl_sync(0xffffffffu, orow_l, R);
-        const int grow = __shfl_sync(0xffffffffu, grow_l, R);
-        if (orow < 0 || c4 >= ncols || ocol0 + c4 + 4 > Nout) continue;
+// residual prefetch for one 64-column unit in the cooperative layout: rp[h][it] = 4 values of row (4*it + lane/8),
+// columns ocol0 + 32*h + 4*(lane%8)
+__device__ __forceinline__ void prefetch_resid(const GemmDev& p, int lane, int grow0, int ocol0, int ncols, int Nout,
+                                               float4 (&rp)[2][8]) {
+    const int c4 = 4 * (lane & 7);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            rp[h][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+            const long orow = out_row(p, grow0 + 4 * it + (lane >> 3));
+            const int col = ocol0 + 32 * h + c4;
+            if (orow < 0 || 32 * h + c4 >= ncols || col + 4 > Nout) continue;
+            if (p.resid_dtype == VTP_F32) {
+                rp[h][it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + orow * p.ldr + col);
+            } else {
+                const uint2 r2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + orow * p.ldr + col);
+                rp[h][it] = make_float4(bf16_lo(r2.x), bf16_hi(r2.x), bf16_lo(r2.y), bf16_hi(r2.y));
+            }
+        }
+    }
+}
+
+// cooperative store of one staged 32-column half.  which = 0: main output, 1: secondary bf16 output (pre-activation)
+__device__ __forceinline__ void store_half(const GemmDev& p, const float* stg, int lane, int grow0, int ocol0, int h,
+                                           int ncols, int Nout, int which, const float4 (&rp)[2][8], bool has_resid) {
+    const int cidx = lane & 7;
+    const int c4 = 32 * h + 4 * cidx;
+    const int col = ocol0 + c4;
+    const bool col_ok = c4 < ncols && col + 4 <= Nout;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int R = 4 * it + (lane >> 3);
+        const int grow = grow0 + R;
+        const long orow = out_row(p, grow);
+        if (orow < 0 || !col_ok) continue;
         float4 v = *reinterpret_cast<const float4*>(stg + stg_off(R, cidx));
-        const int col = ocol0 + c4;
         if (which == 1) {
             uint2 w;
             w.x = pack_bf16x2(v.x, v.y), w.y = pack_bf16x2(v.z, v.w);
@@ -95,22 +122,11 @@ __device__ __forceinline__ void store_slab(const GemmDev& p, const float* stg, i
             }
             continue;
         }
-        if (p.resid) {
-            if (p.resid_dtype == VTP_F32) {
-                const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + orow * p.ldr + col);
-                v.x += r4.x, v.y += r4.y, v.z += r4.z, v.w += r4.w;
-            } else {
-                const uint2 r2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + orow * p.ldr + col);
-                v.x += bf16_lo(r2.x), v.y += bf16_hi(r2.x), v.z += bf16_lo(r2.y), v.w += bf16_hi(r2.y);
-            }
-        }
+        if (has_resid) v.x += rp[h][it].x, v.y += rp[h][it].y, v.z += rp[h][it].z, v.w += rp[h][it].w;
         if (p.out_dtype == VTP_F32) {
             float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
-            if (p.accumulate) {
-                atomicAdd(op, v.x), atomicAdd(op + 1, v.y), atomicAdd(op + 2, v.z), atomicAdd(op + 3, v.w);
-            } else {
-                *reinterpret_cast<float4*>(op) = v;
-            }
+            if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(op), v);
+            else *reinterpret_cast<float4*>(op) = v;
         } else {
             uint2 w;
             w.x = pack_bf16x2(v.x, v.y), w.y = pack_bf16x2(v.z, v.w);
@@ -119,20 +135,18 @@ __device__ __forceinline__ void store_slab(const GemmDev& p, const float* stg, i
     }
 }
 
-// one 64-column unit of a 32-row slab.  grow = this lane's logical row (may be >= M), v = its accumulators.
-__device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int lane, float (&v)[64], int grow, int col0) {
+__device__ __forceinline__ void stage_half(float* stg, int lane, const float (&v)[64], int h) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<float4*>(stg + stg_off(lane, c)) =
+            make_float4(v[32 * h + 4 * c], v[32 * h + 4 * c + 1], v[32 * h + 4 * c + 2], v[32 * h + 4 * c + 3]);
+}
+
+// one 64-column unit of a 32-row slab.  grow0 = first row of the slab, lane's own row = grow0 + lane.
+__device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int lane, float (&v)[64], int grow0, int col0,
+                                              const float4 (&rp)[2][8], bool has_resid) {
     const int N = p.N;
-    const bool valid = grow < p.M;
-    // ---- output row (cls slot remap / compaction); -1 = row not stored
-    long orow = valid ? grow : -1;
-    if (valid && p.rr_group > 0) {
-        if (p.rr_skip >= 0) {  // expansion: leave rr_skip rows free in front of every group (cls slot)
-            orow = (long)(grow / p.rr_group) * (p.rr_group + p.rr_skip) + p.rr_skip + grow % p.rr_group;
-        } else {  // compaction: drop the first -rr_skip rows of every group of rr_group input rows
-            const int tok = grow % p.rr_group;
-            orow = tok < -p.rr_skip ? -1 : (long)(grow / p.rr_group) * (p.rr_group + p.rr_skip) + tok + p.rr_skip;
-        }
-    }
+    const int grow = grow0 + lane;
     // ---- bias
     if (p.bias) {
         if (col0 + 64 <= N) {
@@ -153,10 +167,13 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
     }
     // ---- secondary output: pre-activation, bf16
     if (p.out2) {
-        stage_rows(stg, lane, v, 64);
-        __syncwarp();
-        store_slab(p, stg, lane, grow, orow, col0, 64, N, 1);
-        __syncwarp();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            stage_half(stg, lane, v, h);
+            __syncwarp();
+            store_half(p, stg, lane, grow0, col0, h, 64, N, 1, rp, false);
+            __syncwarp();
+        }
     }
 
     int ncols = 64;        // number of output columns produced by this unit
@@ -193,7 +210,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
 #pragma unroll
             for (int i = 0; i < 64; ++i) v[i] = bf16_round(v[i]);
         }
-        if (col0 < p.rope_cols && pos >= 0 && valid) {
+        if (col0 < p.rope_cols && pos >= 0 && grow < p.M) {
             const uint4* sp = reinterpret_cast<const uint4*>(p.rope_sin + (long)pos * 64);
             const uint4* cp = reinterpret_cast<const uint4*>(p.rope_cos + (long)pos * 64);
             // reference: x.to(bf16); (x*cos) + (rotate_half(x)*sin), every op rounded to bf16
@@ -216,10 +233,15 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
             }
         }
     }
-    stage_rows(stg, lane, v, ncols);
-    __syncwarp();
-    store_slab(p, stg, lane, grow, orow, ocol0, ncols, Nout, 0);
-    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (32 * h < ncols) {
+            stage_half(stg, lane, v, h);
+            __syncwarp();
+            store_half(p, stg, lane, grow0, ocol0, h, ncols, Nout, 0, rp, has_resid);
+            __syncwarp();
+        }
+    }
 }
 
 template <int BN, int STAGES>
@@ -231,8 +253,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // 4 epilogue warps x 8 KB
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + 4 * STG_FLOATS * 4);
+    float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // 8 epilogue warps x 4 KB
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_FLOATS * 4);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -245,7 +267,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
-        for (int s = 0; s < 2; ++s) mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], 4);
+        for (int s = 0; s < 2; ++s) mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], NUM_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -331,23 +353,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
         }
     } else {
-        // ============================== epilogue (warps 2..5) ==============================
-        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        // ============================== epilogue (warps 2..9) ==============================
+        const int q = warp & 3;            // TMEM lane quarter this warp may access
+        const int hsel = (warp - 2) >> 2;  // parity of the 64-column units this warp handles
         float* stg = stg_base + (warp - 2) * STG_FLOATS;
+        const bool has_resid = p.resid != nullptr;
         int as = 0;
         uint32_t aph = 0;
         for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
             const int n_blk = t % p.num_n_blocks;
             const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
             const int m0 = m_blk * BM, n0 = n_blk * BN;
-            mbar_wait(&tfull_bar[as], aph);
-            tc_fence_after();
-            const int grow = m0 + q * 32 + lane;
+            const int grow0 = m0 + q * 32;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+            bool waited = false;
 #pragma unroll 1
-            for (int u = 0; u < BN / 64; ++u) {
+            for (int u = hsel; u < BN / 64; u += 2) {
                 const int col0 = n0 + u * 64;
                 if (col0 >= p.N) break;  // warp-uniform
+                float4 rp[2][8];
+                if (has_resid) {  // issue the residual reads before the accumulator is needed
+                    const bool sw = p.act == VTP_ACT_SWIGLU8;
+                    prefetch_resid(p, lane, grow0, sw ? col0 >> 1 : col0, sw ? 32 : 64, sw ? p.N >> 1 : p.N, rp);
+                }
+                if (!waited) {
+                    mbar_wait(&tfull_bar[as], aph);
+                    tc_fence_after();
+                    waited = true;
+                }
                 uint32_t r0[32], r1[32];
                 tmem_ld_32x32(taddr + u * 64, r0);
                 tmem_ld_32x32(taddr + u * 64 + 32, r1);
@@ -355,7 +388,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float v[64];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]), v[32 + i] = __uint_as_float(r1[i]);
-                epilogue_unit(p, stg, lane, v, grow, col0);
+                epilogue_unit(p, stg, lane, v, grow0, col0, rp, has_resid);
+            }
+            if (!waited) {  // this warp had no unit in the tile (N tail): still consume the phase
+                mbar_wait(&tfull_bar[as], aph);
+                tc_fence_after();
             }
             tc_fence_before();
             __syncwarp();
@@ -374,7 +411,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 template <int BN, int STAGES>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream) {
-    constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + 4 * STG_FLOATS * 4 + 1024 + 256;
+    constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 + 1024 + 256;
     static bool configured = false;
     if (!configured) {
         VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
