@@ -31,6 +31,11 @@ struct AttnDev {
     float scale;
 };
 
+__device__ __forceinline__ float ex2f(float x) {  // ex2.approx.ftz (ex2f() carries a 4-instruction denormal slow path)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t sw128_off(int row, int col /*bf16 element 0..63*/) {
     return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
 }
@@ -169,7 +174,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
         float p_pre[MAX_PREFIX];
 #pragma unroll
         for (int j = 0; j < MAX_PREFIX; ++j) {
-            p_pre[j] = (s_pre[j] == -INFINITY) ? 0.f : exp2f(s_pre[j] * p.scale_log2 - msc);
+            p_pre[j] = (s_pre[j] == -INFINITY) ? 0.f : ex2f(s_pre[j] * p.scale_log2 - msc);
             l += p_pre[j];
             p_pre[j] = bf16_round(p_pre[j]);
         }
@@ -184,8 +189,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                 uint32_t pk[16];
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
-                    float e0 = (c + i < kmax) ? exp2f(__uint_as_float(rr[i]) * p.scale_log2 - msc) : 0.f;
-                    float e1 = (c + i + 1 < kmax) ? exp2f(__uint_as_float(rr[i + 1]) * p.scale_log2 - msc) : 0.f;
+                    float e0 = (c + i < kmax) ? ex2f(__uint_as_float(rr[i]) * p.scale_log2 - msc) : 0.f;
+                    float e1 = (c + i + 1 < kmax) ? ex2f(__uint_as_float(rr[i + 1]) * p.scale_log2 - msc) : 0.f;
                     l += e0 + e1;
                     pk[i >> 1] = pack_bf16x2(e0, e1);
                 }
@@ -289,7 +294,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                 float l = 0.f, e[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    e[i] = (s[i] == -INFINITY) ? 0.f : exp2f(s[i] * p.scale_log2 - msc);
+                    e[i] = (s[i] == -INFINITY) ? 0.f : ex2f(s[i] * p.scale_log2 - msc);
                     l += e[i];
                     e[i] = bf16_round(e[i]);
                 }
@@ -298,7 +303,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
 #pragma unroll
                 for (int t = 0; t < MAX_PREFIX; ++t) {
                     if (t < prefix && sp[t] != -INFINITY) {
-                        const float pe = exp2f(sp[t] * p.scale_log2 - msc);
+                        const float pe = ex2f(sp[t] * p.scale_log2 - msc);
                         l += pe;
                         const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p.qkv + (seq_row0 + t) * 3 * D + 2 * D + h * 64) + lane);
                         a0 += bf16_round(pe) * bf16_lo(w), a1 += bf16_round(pe) * bf16_hi(w);

@@ -18,10 +18,10 @@
 
 namespace vtp {
 
-static constexpr int AB_THREADS = 192;
+static constexpr int AB_THREADS = 320;  // 8 row warps (2 per scheduler) + TMA/MMA warp + cls warp
 static constexpr int BQ = 0, BK_ = 32768, BV = 65536, BDO = 98304, BP = 131072, BDS = 163840, BX = 196608;
-// extras after BX: p0[264] | ds0[264] | dk0[64] | dv0[64] | barriers
-static constexpr int X_P0 = 0, X_DS0 = 1056, X_DK0 = 2112, X_DV0 = 2368, X_BAR = 2624;
+// extras after BX: p0[264] | ds0[264] | dk0[64] | dv0[64] | pcol[2][128] | dscol[2][128] | barriers
+static constexpr int X_P0 = 0, X_DS0 = 1056, X_DK0 = 2112, X_DV0 = 2368, X_PCOL = 2624, X_DSCOL = 3648, X_BAR = 4672;
 static constexpr int AB_SMEM = BX + X_BAR + 128;
 
 struct AttnBwdDev {
@@ -36,6 +36,11 @@ struct AttnBwdDev {
     float scale, scale_log2;
 };
 
+__device__ __forceinline__ float ex2f(float x) {  // ex2.approx.ftz: no denormal slow path (exp2f() costs 4 extra instr)
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 __device__ __forceinline__ uint32_t sw_off(int row, int col) {
     return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
 }
@@ -87,6 +92,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     float* ds0 = reinterpret_cast<float*>(smem + BX + X_DS0);
     float* dk0 = reinterpret_cast<float*>(smem + BX + X_DK0);
     float* dv0 = reinterpret_cast<float*>(smem + BX + X_DV0);
+    float* pcol = reinterpret_cast<float*>(smem + BX + X_PCOL);
+    float* dscol = reinterpret_cast<float*>(smem + BX + X_DSCOL);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BX + X_BAR);
     uint64_t* bar_ld = bars + 0;       // [2] tile loads
     uint64_t* bar_sdp = bars + 2;      // S,dP in TMEM
@@ -106,12 +113,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_qkv);
         tma_prefetch_desc(&tm_do);
-        mbar_init(&bar_ld[0], 1), mbar_init(&bar_ld[1], 1), mbar_init(bar_sdp, 1), mbar_init(bar_pds, 128);
-        mbar_init(bar_mma2, 1), mbar_init(bar_accfree, 128), mbar_init(bar_cls, 1);
+        mbar_init(&bar_ld[0], 1), mbar_init(&bar_ld[1], 1), mbar_init(bar_sdp, 1), mbar_init(bar_pds, 256);
+        mbar_init(bar_mma2, 1), mbar_init(bar_accfree, 256), mbar_init(bar_cls, 1);
         fence_barrier_init();
     }
     if (threadIdx.x < 128) dk0[threadIdx.x & 63] = 0.f, dv0[threadIdx.x & 63] = 0.f;
-    if (warp == 4) {
+    if (warp == 8) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
@@ -122,7 +129,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     // TMEM columns
     const uint32_t C_DV = 0, C_DK = 64, C_DQ = 128 /* + 64*t */, C_S = 256, C_DP = 384;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             // ------------------------------------------------ TMA: tile i = rows [128i, 128i+128) of Q,K,V,dO
             for (int i = 0; i < nkt; ++i) {
@@ -184,11 +191,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 umma_commit(bar_mma2);
             }
         }
-    } else if (warp < 4) {
-        // ---------------------------------------------------- row threads
-        const int r = warp * 32 + lane;
-        const uint32_t trow = tmem + (uint32_t(warp * 32) << 16);
-        float lse_i[2], delta_i[2], p_i0[2], ds_i0[2];
+    } else if (warp < 8) {
+        // ---------------------------------------------------- row threads: 2 groups x 128 (one TMEM lane each).
+        // group g builds the P/dS columns of 64-key chunk g in every step, owns query tile g (cls-key column terms,
+        // dQ epilogue) and one of the two accumulators in the key-half epilogue (g=0: dV, g=1: dK).
+        const int g = warp >> 2, q4 = warp & 3;
+        const int r = q4 * 32 + lane;
+        const uint32_t trow = tmem + (uint32_t(q4 * 32) << 16);
+        const int my_tile = (nkt == 2) ? g : 0;
+        const bool owns_tile = (nkt == 2) || (g == 0);
+        float lse_i[2], delta_i[2];
+        float ds_own = 0.f;
         const __nv_bfloat16* kcls = p.qkv + row0 * 3 * D + D + h * 64;
         const __nv_bfloat16* vcls = p.qkv + row0 * 3 * D + 2 * D + h * 64;
 
@@ -197,9 +210,12 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             const int qi = 128 * t + r;  // patch index of my query row in this step
             const bool qvalid = qi < HW;
             if (kh == 0) {
-                // per-query-tile scalars (first visit of tile t): lse, delta = dO·O, and the cls-key column
+                // per-query-tile scalars (first visit of tile t): lse, delta = dO·O; the owner group also does the
+                // cls-key column
                 mbar_wait(&bar_ld[t], 0);
-                lse_i[t] = 0.f, delta_i[t] = 0.f, p_i0[t] = 0.f, ds_i0[t] = 0.f;
+                lse_i[t] = 0.f, delta_i[t] = 0.f;
+                const bool mine = owns_tile && t == my_tile && prefix > 0;
+                float p0v = 0.f, ds0v = 0.f;
                 if (qvalid) {
                     const long grow = row0 + prefix + qi;
                     lse_i[t] = p.lse[((long)b * p.H + h) * T + prefix + qi];
@@ -210,34 +226,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
                     for (int d = 0; d < 64; ++d) dl += dof[d] * tmpf[d];
                     delta_i[t] = dl;
-                    if (prefix > 0) {
-                        float qf[64];
-                        load_row64(smem + BQ + t * 16384, r, qf);
-                        load_grow64(kcls, tmpf);
-                        float s0 = 0.f;
-#pragma unroll
-                        for (int d = 0; d < 64; ++d) s0 += qf[d] * tmpf[d];
+                    if (mine) {
                         load_grow64(vcls, tmpf);
                         float dp0 = 0.f;
 #pragma unroll
                         for (int d = 0; d < 64; ++d) dp0 += dof[d] * tmpf[d];
-                        const float pp = exp2f(s0 * p.scale_log2 - lse_i[t] * lse_l2);
-                        p_i0[t] = pp;
-                        ds_i0[t] = p.scale * pp * (dp0 - dl);
+                        load_row64(smem + BQ + t * 16384, r, dof);  // q row
+                        load_grow64(kcls, tmpf);
+                        float s0 = 0.f;
+#pragma unroll
+                        for (int d = 0; d < 64; ++d) s0 += dof[d] * tmpf[d];
+                        p0v = ex2f(s0 * p.scale_log2 - lse_i[t] * lse_l2);
+                        ds0v = p.scale * p0v * (dp0 - dl);
                     }
                 }
-                if (prefix > 0) {
-                    // column reductions for the cls key: dV_0 += Σ_i p_i0 dO_i ;  dK_0 += Σ_i ds_i0 q_i
-                    float dof[64], qf[64];
-                    load_row64(smem + BDO + t * 16384, r, dof);
-                    load_row64(smem + BQ + t * 16384, r, qf);
-                    const float pb = bf16_round(p_i0[t]), db = bf16_round(ds_i0[t]);
-#pragma unroll
-                    for (int d = 0; d < 64; ++d) {
-                        const float a = warp_sum(pb * dof[d]);
-                        const float c = warp_sum(db * qf[d]);
-                        if (lane == (d & 31)) atomicAdd(&dv0[d], a), atomicAdd(&dk0[d], c);
+                if (mine) {
+                    // column reductions for the cls key: dV_0 += Σ_i p_i0 dO_i ; dK_0 += Σ_i ds_i0 q_i.  The per-row
+                    // scalars go through smem, then thread (which, d) walks the 128 rows of the dO / Q tile.
+                    ds_own = ds0v;
+                    pcol[g * 128 + r] = p0v, dscol[g * 128 + r] = ds0v;
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                    const int d = r & 63;
+                    const bool isk = r >= 64;
+                    const uint8_t* tile = smem + (isk ? BQ : BDO) + t * 16384;
+                    const float* colv = (isk ? dscol : pcol) + g * 128;
+                    float acc = 0.f;
+#pragma unroll 8
+                    for (int i = 0; i < 128; ++i) {
+                        const __nv_bfloat16 e = *reinterpret_cast<const __nv_bfloat16*>(tile + sw_off(i, d));
+                        acc += colv[i] * __bfloat162float(e);
                     }
+                    atomicAdd(isk ? &dk0[d] : &dv0[d], acc);
                 }
             }
             mbar_wait(bar_sdp, n & 1);
@@ -246,7 +265,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             const int kmax = p.causal ? min(HW, qi + 1) : HW;
             const float lsc = lse_i[t] * lse_l2, dl = delta_i[t];
 #pragma unroll 1
-            for (int c32 = 0; c32 < 4; ++c32) {
+            for (int cc = 0; cc < 2; ++cc) {
+                const int c32 = 2 * g + cc;
                 uint32_t rs[32], rd[32];
                 tmem_ld_32x32(trow + C_S + c32 * 32, rs);
                 tmem_ld_32x32(trow + C_DP + c32 * 32, rd);
@@ -257,21 +277,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 for (int i = 0; i < 32; i += 2) {
                     float pa = 0.f, pb = 0.f, da = 0.f, db = 0.f;
                     if (qvalid && kbase + i < kmax) {
-                        pa = exp2f(__uint_as_float(rs[i]) * p.scale_log2 - lsc);
+                        pa = ex2f(__uint_as_float(rs[i]) * p.scale_log2 - lsc);
                         da = p.scale * pa * (__uint_as_float(rd[i]) - dl);
                     }
                     if (qvalid && kbase + i + 1 < kmax) {
-                        pb = exp2f(__uint_as_float(rs[i + 1]) * p.scale_log2 - lsc);
+                        pb = ex2f(__uint_as_float(rs[i + 1]) * p.scale_log2 - lsc);
                         db = p.scale * pb * (__uint_as_float(rd[i + 1]) - dl);
                     }
                     pk[i >> 1] = pack_bf16x2(pa, pb);
                     dk[i >> 1] = pack_bf16x2(da, db);
                 }
-                uint8_t* pb_ = smem + BP + (c32 >> 1) * 16384;
-                uint8_t* db_ = smem + BDS + (c32 >> 1) * 16384;
+                uint8_t* pb_ = smem + BP + g * 16384;   // 64-key chunk g of the P / dS tiles
+                uint8_t* db_ = smem + BDS + g * 16384;
 #pragma unroll
                 for (int v4 = 0; v4 < 4; ++v4) {
-                    const uint32_t off = sw_off(r, (c32 & 1) * 32 + v4 * 8);
+                    const uint32_t off = sw_off(r, cc * 32 + v4 * 8);
                     *reinterpret_cast<uint4*>(pb_ + off) = make_uint4(pk[v4 * 4], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
                     *reinterpret_cast<uint4*>(db_ + off) = make_uint4(dk[v4 * 4], dk[v4 * 4 + 1], dk[v4 * 4 + 2], dk[v4 * 4 + 3]);
                 }
@@ -281,75 +301,69 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             mbar_arrive(bar_pds);
 
             if (t == nkt - 1) {
-                // ------------ epilogue of key half kh: I own key row kj = 128*kh + r
+                // ------------ epilogue of key half kh: I own key row kj = 128*kh + r; group 0 -> dV, group 1 -> dK
                 mbar_wait(bar_mma2, n & 1);
                 tc_fence_after();
                 const int kj = 128 * kh + r;
                 uint32_t a0[32], a1[32];
-                float g[64];
+                float gq[64];
                 if (prefix > 0) mbar_wait(bar_cls, 0);
-                // dV
-                tmem_ld_32x32(trow + C_DV, a0);
-                tmem_ld_32x32(trow + C_DV + 32, a1);
+                tmem_ld_32x32(trow + (g == 0 ? C_DV : C_DK), a0);
+                tmem_ld_32x32(trow + (g == 0 ? C_DV : C_DK) + 32, a1);
                 tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(a0[i]), g[32 + i] = __uint_as_float(a1[i]);
-                if (kj < HW) {
-                    if (prefix > 0) {
-                        float f[64];
-                        load_grow64(p.dout + row0 * D + h * 64, f);  // dO of the cls query
-                        const float pc = bf16_round(p0[kj]);
-#pragma unroll
-                        for (int d = 0; d < 64; ++d) g[d] += pc * f[d];
-                    }
-                    store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + 2 * D + h * 64, g);
-                }
-                // dK
-                tmem_ld_32x32(trow + C_DK, a0);
-                tmem_ld_32x32(trow + C_DK + 32, a1);
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(a0[i]), g[32 + i] = __uint_as_float(a1[i]);
+                for (int i = 0; i < 32; ++i) gq[i] = __uint_as_float(a0[i]), gq[32 + i] = __uint_as_float(a1[i]);
                 tc_fence_before();
                 mbar_arrive(bar_accfree);
                 if (kj < HW) {
-                    if (prefix > 0) {
-                        float f[64];
-                        load_grow64(p.qkv + row0 * 3 * D + h * 64, f);  // q of the cls query
-                        const float dc = bf16_round(ds0[kj]);
+                    if (g == 0) {
+                        if (prefix > 0) {
+                            float f[64];
+                            load_grow64(p.dout + row0 * D + h * 64, f);  // dO of the cls query
+                            const float pc = p0[kj];
 #pragma unroll
-                        for (int d = 0; d < 64; ++d) g[d] += dc * f[d];
+                            for (int d = 0; d < 64; ++d) gq[d] += pc * f[d];
+                        }
+                        store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + 2 * D + h * 64, gq);
+                    } else {
+                        if (prefix > 0) {
+                            float f[64];
+                            load_grow64(p.qkv + row0 * 3 * D + h * 64, f);  // q of the cls query
+                            const float dc = ds0[kj];
+#pragma unroll
+                            for (int d = 0; d < 64; ++d) gq[d] += dc * f[d];
+                        }
+                        if (p.rope_sin) rope_bwd64(gq, p.rope_sin + (long)kj * 64, p.rope_cos + (long)kj * 64);
+                        store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + D + h * 64, gq);
                     }
-                    if (p.rope_sin) rope_bwd64(g, p.rope_sin + (long)kj * 64, p.rope_cos + (long)kj * 64);
-                    store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + D + h * 64, g);
                 }
             }
         }
-        // ------------ dQ epilogue (all steps done; last bar_mma2 phase already observed above)
-        for (int t = 0; t < nkt; ++t) {
+        // ------------ dQ epilogue of my query tile (all steps done; last bar_mma2 phase already observed above)
+        if (owns_tile) {
+            const int t = my_tile;
             const int qi = 128 * t + r;
             uint32_t a0[32], a1[32];
             tmem_ld_32x32(trow + C_DQ + 64 * t, a0);
             tmem_ld_32x32(trow + C_DQ + 64 * t + 32, a1);
             tmem_ld_wait();
             if (qi < HW) {
-                float g[64];
+                float gq[64];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) g[i] = __uint_as_float(a0[i]), g[32 + i] = __uint_as_float(a1[i]);
+                for (int i = 0; i < 32; ++i) gq[i] = __uint_as_float(a0[i]), gq[32 + i] = __uint_as_float(a1[i]);
                 if (prefix > 0) {
                     float f[64];
                     load_grow64(kcls, f);
-                    const float dc = bf16_round(ds_i0[t]);
 #pragma unroll
-                    for (int d = 0; d < 64; ++d) g[d] += dc * f[d];
+                    for (int d = 0; d < 64; ++d) gq[d] += ds_own * f[d];
                 }
-                if (p.rope_sin) rope_bwd64(g, p.rope_sin + (long)qi * 64, p.rope_cos + (long)qi * 64);
-                store_row64(p.dqkv + (row0 + prefix + qi) * 3 * D + h * 64, g);
+                if (p.rope_sin) rope_bwd64(gq, p.rope_sin + (long)qi * 64, p.rope_cos + (long)qi * 64);
+                store_row64(p.dqkv + (row0 + prefix + qi) * 3 * D + h * 64, gq);
             }
         }
         tc_fence_before();
     } else {
-        // ---------------------------------------------------- warp 5: the cls query row (prefix == 1)
+        // ---------------------------------------------------- warp 9: the cls query row (prefix == 1)
         if (prefix > 0) {
             for (int i = 0; i < nkt; ++i) mbar_wait(&bar_ld[i], 0);
             float q0[64], do0[64];
@@ -377,7 +391,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                         float dp = 0.f;
 #pragma unroll
                         for (int d = 0; d < 64; ++d) dp += do0[d] * f[d];
-                        pv = exp2f(s * p.scale_log2 - lse0);
+                        pv = ex2f(s * p.scale_log2 - lse0);
                         dsv = p.scale * pv * (dp - delta0);
                     }
                     p0[kj] = pv, ds0[kj] = dsv;
@@ -392,7 +406,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             float s00 = 0.f, dp00 = 0.f;
 #pragma unroll
             for (int d = 0; d < 64; ++d) s00 += q0[d] * kc[d], dp00 += do0[d] * vc[d];
-            const float p00 = exp2f(s00 * p.scale_log2 - lse0);
+            const float p00 = ex2f(s00 * p.scale_log2 - lse0);
             const float ds00 = p.scale * p00 * (dp00 - delta0);
             // dQ_0[d] = Σ_j ds_0j k_j[d] + ds_00 k_0[d]; lane owns dims 2*lane, 2*lane+1
             float a0 = 0.f, a1 = 0.f;
@@ -412,7 +426,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     }
 
     __syncthreads();
-    if (warp == 5 && prefix > 0) {
+    if (warp == 9 && prefix > 0) {
         // dV_0 = Σ_i p_i0 dO_i (+ p_00 dO_0) ;  dK_0 = Σ_i ds_i0 q_i (+ ds_00 q_0)   — cls key row, no RoPE
         const float p00 = p0[260], ds00 = ds0[260];
         const uint32_t wdo = __ldg(reinterpret_cast<const uint32_t*>(p.dout + row0 * D + h * 64) + lane);
@@ -422,7 +436,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         *reinterpret_cast<uint32_t*>(p.dqkv + row0 * 3 * D + 2 * D + h * 64 + 2 * lane) = pack_bf16x2(v0, v1);
         *reinterpret_cast<uint32_t*>(p.dqkv + row0 * 3 * D + D + h * 64 + 2 * lane) = pack_bf16x2(k0, k1);
     }
-    if (warp == 4) {
+    if (warp == 8) {
         tc_fence_after();
         tmem_dealloc(tmem, 512);
     }

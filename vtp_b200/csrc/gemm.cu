@@ -88,6 +88,62 @@ __device__ __forceinline__ void prefetch_resid(const GemmDev& p, int lane, int g
     }
 }
 
+// ---- bf16 outputs: the whole 64-column unit is staged as bf16 (32 rows x 128 B, 16-byte chunks XOR-swizzled) so that
+// every store instruction writes four complete 128-byte lines (64-byte partial-line writes ran ~2.5x slower).
+__device__ __forceinline__ int stgb_off(int r, int chunk /*0..7, 16 B each*/) { return r * 128 + ((chunk ^ (r & 7)) << 4); }
+
+__device__ __forceinline__ void stage_bf16(uint8_t* stg, int lane, const float (&v)[64], int c0, int nvals) {
+    // packs v[0..nvals) (nvals = 32 or 64) into columns c0.. of this lane's staged row
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        if (8 * c < nvals) {
+            uint4 w;
+            w.x = pack_bf16x2(v[8 * c], v[8 * c + 1]), w.y = pack_bf16x2(v[8 * c + 2], v[8 * c + 3]);
+            w.z = pack_bf16x2(v[8 * c + 4], v[8 * c + 5]), w.w = pack_bf16x2(v[8 * c + 6], v[8 * c + 7]);
+            *reinterpret_cast<uint4*>(stg + stgb_off(lane, (c0 >> 3) + c)) = w;
+        }
+    }
+}
+
+// residual prefetch (bf16 residual stream) for a 64-column bf16 unit: rb[it] = 8 values of row (4*it + lane/8)
+__device__ __forceinline__ void prefetch_resid_bf16(const GemmDev& p, int lane, int grow0, int ocol0, int ncols, int Nout,
+                                                    uint4 (&rb)[8]) {
+    const int c8 = 8 * (lane & 7);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        rb[it] = make_uint4(0u, 0u, 0u, 0u);
+        const long orow = out_row(p, grow0 + 4 * it + (lane >> 3));
+        if (orow < 0 || c8 >= ncols || ocol0 + c8 + 8 > Nout) continue;
+        rb[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + orow * p.ldr + ocol0 + c8);
+    }
+}
+
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+    return pack_bf16x2(bf16_lo(a) + bf16_lo(b), bf16_hi(a) + bf16_hi(b));
+}
+
+// cooperative store of a staged bf16 unit: dst = p.out (which=0) or p.out2 (which=1); ncols valid columns (32|64)
+__device__ __forceinline__ void store_bf16(const GemmDev& p, const uint8_t* stg, int lane, int grow0, int ocol0, int ncols,
+                                           int Nout, int which, const uint4 (&rb)[8], bool has_resid) {
+    const int cidx = lane & 7;
+    const int c8 = 8 * cidx;
+    const bool col_ok = c8 < ncols && ocol0 + c8 + 8 <= Nout;
+    __nv_bfloat16* base = which ? p.out2 : reinterpret_cast<__nv_bfloat16*>(p.out);
+    const long ld = which ? p.ldo2 : p.ldo;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int R = 4 * it + (lane >> 3);
+        const long orow = out_row(p, grow0 + R);
+        if (orow < 0 || !col_ok) continue;
+        uint4 w = *reinterpret_cast<const uint4*>(stg + stgb_off(R, cidx));
+        if (has_resid && which == 0) {
+            w.x = add_bf16x2(w.x, rb[it].x), w.y = add_bf16x2(w.y, rb[it].y);
+            w.z = add_bf16x2(w.z, rb[it].z), w.w = add_bf16x2(w.w, rb[it].w);
+        }
+        *reinterpret_cast<uint4*>(base + orow * ld + ocol0 + c8) = w;
+    }
+}
+
 // cooperative store of one staged 32-column half.  which = 0: main output, 1: secondary bf16 output (pre-activation)
 __device__ __forceinline__ void store_half(const GemmDev& p, const float* stg, int lane, int grow0, int ocol0, int h,
                                            int ncols, int Nout, int which, const float4 (&rp)[2][8], bool has_resid) {
@@ -143,8 +199,10 @@ __device__ __forceinline__ void stage_half(float* stg, int lane, const float (&v
 }
 
 // one 64-column unit of a 32-row slab.  grow0 = first row of the slab, lane's own row = grow0 + lane.
+// sw_half: for SwiGLU with bf16 output two adjacent packed units fill one 64-column hidden line; 0 = first, 1 = second
 __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int lane, float (&v)[64], int grow0, int col0,
-                                              const float4 (&rp)[2][8], bool has_resid) {
+                                              const float4 (&rp)[2][8], const uint4 (&rb)[8], bool has_resid, int sw_half,
+                                              uint32_t (&hold)[16]) {
     const int N = p.N;
     const int grow = grow0 + lane;
     // ---- bias
@@ -166,14 +224,12 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
         for (int i = 0; i < 64; ++i) v[i] = bf16_round(v[i]);
     }
     // ---- secondary output: pre-activation, bf16
+    uint8_t* stgb = reinterpret_cast<uint8_t*>(stg);
     if (p.out2) {
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            stage_half(stg, lane, v, h);
-            __syncwarp();
-            store_half(p, stg, lane, grow0, col0, h, 64, N, 1, rp, false);
-            __syncwarp();
-        }
+        stage_bf16(stgb, lane, v, 0, 64);
+        __syncwarp();
+        store_bf16(p, stgb, lane, grow0, col0, 64, N, 1, rb, false);
+        __syncwarp();
     }
 
     int ncols = 64;        // number of output columns produced by this unit
@@ -233,6 +289,33 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
             }
         }
     }
+    if (p.out_dtype == VTP_BF16 && p.ps_r == 0) {
+        if (p.act == VTP_ACT_SWIGLU8) {
+            // 32 hidden columns per packed unit: the pair (sw_half 0,1) forms one 64-column (128-byte) output line.
+            // The first half waits in registers (the staging tile is reused by the partner's pre-activation store).
+            if (sw_half == 0 && col0 + 64 < N) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) hold[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            } else {
+                if (sw_half == 1) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(stgb + stgb_off(lane, c)) =
+                            make_uint4(hold[4 * c], hold[4 * c + 1], hold[4 * c + 2], hold[4 * c + 3]);
+                }
+                stage_bf16(stgb, lane, v, 32 * sw_half, 32);
+                __syncwarp();
+                store_bf16(p, stgb, lane, grow0, ocol0 - 32 * sw_half, 32 * (sw_half + 1), Nout, 0, rb, false);
+                __syncwarp();
+            }
+        } else {
+            stage_bf16(stgb, lane, v, 0, 64);
+            __syncwarp();
+            store_bf16(p, stgb, lane, grow0, ocol0, 64, Nout, 0, rb, has_resid);
+            __syncwarp();
+        }
+        return;
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
         if (32 * h < ncols) {
@@ -245,7 +328,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __maxnreg__(200)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -367,14 +450,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int grow0 = m0 + q * 32;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
             bool waited = false;
+            const bool sw = p.act == VTP_ACT_SWIGLU8;
+            // unit assignment: parity-interleaved, except SwiGLU where a warp takes ADJACENT packed units (2k, 2k+1) so
+            // that their 32+32 hidden columns form one full 128-byte output line
+            uint32_t hold[16];  // first half of a SwiGLU hidden line, kept in registers until its partner unit is done
 #pragma unroll 1
-            for (int u = hsel; u < BN / 64; u += 2) {
+            for (int j = 0; j < BN / 64; ++j) {
+                const int u = sw ? (BN >= 256 ? 2 * hsel + j : (hsel == 0 ? j : BN / 64)) : hsel + 2 * j;
+                if (u >= BN / 64) break;
                 const int col0 = n0 + u * 64;
                 if (col0 >= p.N) break;  // warp-uniform
                 float4 rp[2][8];
+                uint4 rb[8];
                 if (has_resid) {  // issue the residual reads before the accumulator is needed
-                    const bool sw = p.act == VTP_ACT_SWIGLU8;
-                    prefetch_resid(p, lane, grow0, sw ? col0 >> 1 : col0, sw ? 32 : 64, sw ? p.N >> 1 : p.N, rp);
+                    if (p.out_dtype == VTP_BF16 && p.resid_dtype == VTP_BF16 && p.ps_r == 0 && !sw)
+                        prefetch_resid_bf16(p, lane, grow0, col0, 64, p.N, rb);
+                    else
+                        prefetch_resid(p, lane, grow0, sw ? col0 >> 1 : col0, sw ? 32 : 64, sw ? p.N >> 1 : p.N, rp);
                 }
                 if (!waited) {
                     mbar_wait(&tfull_bar[as], aph);
@@ -388,7 +480,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float v[64];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]), v[32 + i] = __uint_as_float(r1[i]);
-                epilogue_unit(p, stg, lane, v, grow0, col0, rp, has_resid);
+                epilogue_unit(p, stg, lane, v, grow0, col0, rp, rb, has_resid, sw ? (u & 1) : 0, hold);
             }
             if (!waited) {  // this warp had no unit in the tile (N tail): still consume the phase
                 mbar_wait(&tfull_bar[as], aph);
