@@ -27,7 +27,7 @@ enum {
     VTP_ERR_ARCH = -3,  /* device is not sm_100 */
 };
 enum { VTP_F32 = 0, VTP_BF16 = 1 };
-enum { VTP_ACT_NONE = 0, VTP_ACT_GELU = 1, VTP_ACT_SWIGLU8 = 2, VTP_ACT_ROPE = 3 };
+enum { VTP_ACT_NONE = 0, VTP_ACT_GELU = 1, VTP_ACT_SWIGLU8 = 2, VTP_ACT_ROPE = 3, VTP_ACT_RELU = 4 };
 
 const char* vtp_last_error(void);
 int vtp_version(void);
@@ -65,6 +65,12 @@ typedef struct {
     int ps_r, ps_gh, ps_gw, ps_cout;         /* ps_r>0: PixelShuffle(ps_r) NCHW store, grid gh x gw, cout channels */
     void* out2;             /* optional bf16 copy of (acc+bias) before activation (saved for backward), [M][ldo2] */
     int ldo2;
+    /* implicit 3x3 / pad-1 convolution (utils/lpips.py:127-167 VGG16 features and their dgrad): conv_C > 0 makes A an
+     * NHWC bf16 activation [B][conv_H][conv_W][conv_C] loaded by 4-D TMA (OOB zero fill = padding); then M = B*H*W,
+     * K = 9*conv_C with k = (3*dy+dx)*conv_C + c, B = weights [N][9*conv_C], out = NHWC [B*H*W][ldo] */
+    int conv_C, conv_H, conv_W;
+    const void* mask_pos;   /* optional bf16 [M][ldm]: out *= (mask_pos > 0) — ReLU backward fused in the epilogue */
+    int ldm;
 } vtp_gemm_args;
 
 int vtp_gemm_bf16(const vtp_gemm_args* args, vtp_stream_t stream);
@@ -165,6 +171,23 @@ int vtp_recon_l1_grad(const void* rec, int rec_dtype, const float* tgt, const fl
 int vtp_weight_norm_fwd(const float* v, const float* g, void* w_bf16, float* vnorm, int K, int D, vtp_stream_t stream);
 int vtp_weight_norm_bwd(const float* v, const float* g, const float* vnorm, const float* dW, float* dv, float* dg, int K,
                         int D, vtp_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * LPIPS perceptual loss (utils/lpips.py:61-171); the VGG16 convolutions run on vtp_gemm_bf16 (conv_C > 0)
+ * ------------------------------------------------------------------------------------------------------------ */
+/* ScalingLayer (lpips.py:103-114) + 3x3 im2col of the 3-channel image: NCHW (fp32|bf16) -> bf16 [B*H*W][32], k=tap*3+c */
+int vtp_lpips_prep(const void* img, int img_dtype, void* out_bf16, int B, int H, int W, vtp_stream_t stream);
+/* nn.MaxPool2d(2,2) on NHWC bf16 (lpips.py:127-149 via torchvision vgg16.features) */
+int vtp_maxpool2_fwd(const void* x, void* y, int B, int H, int W, int C, vtp_stream_t stream);
+/* dual of MaxPool2d(2,2) fused with the tap-gradient add and the ReLU mask: dz = (gtap + route(dpool)) * (y > 0) */
+int vtp_pool_relu_bwd(const void* y, const void* dpool, const void* gtap, void* dz, int B, int H, int W, int C,
+                      vtp_stream_t stream);
+/* one LPIPS tap (lpips.py:88-100,169-175): normalize_tensor, squared diff, lin 1x1, spatial mean: loss += and gradient
+ * w.r.t. the reconstruction features f0 (bf16 [P][C]) */
+int vtp_lpips_tap(const void* f0, const void* f1, const float* w, void* g0, long P, int C, float coef, float* loss_acc,
+                  vtp_stream_t stream);
+/* col2im of the conv1_1 input gradient + ScalingLayer backward: bf16 [B*H*W][32] -> fp32 NCHW d(image) */
+int vtp_lpips_img_grad(const void* dcol, float* dimg, int B, int H, int W, vtp_stream_t stream);
 
 #ifdef __cplusplus
 }

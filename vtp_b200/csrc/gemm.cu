@@ -39,6 +39,10 @@ struct GemmDev {
     int ps_r, ps_gh, ps_gw, ps_cout;
     __nv_bfloat16* out2;
     int ldo2;
+    // implicit 3x3 / pad-1 convolution over an NHWC activation (A operand loaded by 4-D TMA, zero fill = padding)
+    int conv_C, conv_H, conv_W, conv_TW, conv_TH, conv_tiles_h, conv_tiles_w;
+    const __nv_bfloat16* mask_pos;  // optional: out *= (mask_pos[row][col] > 0)   (ReLU backward in the dgrad epilogue)
+    int ldm;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -57,6 +61,13 @@ static constexpr int NUM_EPI_WARPS = 8;
 __device__ __forceinline__ int stg_off(int r, int chunk /*0..7*/) { return r * 32 + ((chunk ^ (r & 7)) << 2); }
 
 __device__ __forceinline__ long out_row(const GemmDev& p, int grow) {
+    if (p.conv_C) {  // grow = m_blk * 128 + r : tile (b, ty, tx), pixel r of a conv_TH x conv_TW patch
+        const int m_blk = grow >> 7, r = grow & 127;
+        const int tx = m_blk % p.conv_tiles_w, ty = (m_blk / p.conv_tiles_w) % p.conv_tiles_h;
+        const int b = m_blk / (p.conv_tiles_w * p.conv_tiles_h);
+        const int h = ty * p.conv_TH + r / p.conv_TW, w = tx * p.conv_TW + r % p.conv_TW;
+        return (h < p.conv_H && w < p.conv_W) ? ((long)b * p.conv_H + h) * p.conv_W + w : -1;
+    }
     if (grow >= p.M) return -1;
     if (p.rr_group <= 0) return grow;
     if (p.rr_skip >= 0)  // expansion: leave rr_skip rows free in front of every group (cls slot)
@@ -139,6 +150,15 @@ __device__ __forceinline__ void store_bf16(const GemmDev& p, const uint8_t* stg,
         if (has_resid && which == 0) {
             w.x = add_bf16x2(w.x, rb[it].x), w.y = add_bf16x2(w.y, rb[it].y);
             w.z = add_bf16x2(w.z, rb[it].z), w.w = add_bf16x2(w.w, rb[it].w);
+        }
+        if (p.mask_pos && which == 0) {  // keep x where the forward activation was > 0 (bf16: sign bit clear, non-zero)
+            const uint4 m = *reinterpret_cast<const uint4*>(p.mask_pos + orow * p.ldm + ocol0 + c8);
+            auto keep = [](uint32_t x, uint32_t mm) {
+                const uint32_t lo = ((mm & 0x7FFFu) != 0u && (mm & 0x8000u) == 0u) ? 0x0000FFFFu : 0u;
+                const uint32_t hi = ((mm & 0x7FFF0000u) != 0u && (mm & 0x80000000u) == 0u) ? 0xFFFF0000u : 0u;
+                return x & (lo | hi);
+            };
+            w.x = keep(w.x, m.x), w.y = keep(w.y, m.y), w.z = keep(w.z, m.z), w.w = keep(w.w, m.w);
         }
         *reinterpret_cast<uint4*>(base + orow * ld + ocol0 + c8) = w;
     }
@@ -242,6 +262,9 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
             float g = gelu_erf(v[i]);
             v[i] = p.round_bf16 ? bf16_round(g) : g;
         }
+    } else if (p.act == VTP_ACT_RELU) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
     } else if (p.act == VTP_ACT_SWIGLU8) {
         // packed columns: [16g, 16g+8) = x1, [16g+8, 16g+16) = x2  ->  hidden[8g + i] = silu(x1) * x2
 #pragma unroll
@@ -328,7 +351,8 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
 }
 
 template <int BN, int STAGES>
-__global__ void __maxnreg__(200)
+// 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168
+__global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -383,7 +407,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     uint8_t* sb = sa + A_BYTES;
                     mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                     const int k0 = kb * BK;
-                    if (!p.a_mn) {
+                    if (p.conv_C) {
+                        const int tx = m_blk % p.conv_tiles_w, ty = (m_blk / p.conv_tiles_w) % p.conv_tiles_h;
+                        const int bimg = m_blk / (p.conv_tiles_w * p.conv_tiles_h);
+                        const int cpk = p.conv_C >> 6, tap = kb / cpk, c0 = (kb % cpk) << 6;
+                        tma_load_4d(sa, &tmA, &full_bar[s], c0, tx * p.conv_TW + tap % 3 - 1, ty * p.conv_TH + tap / 3 - 1,
+                                    bimg);
+                    } else if (!p.a_mn) {
                         tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
                     } else {
                         tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
@@ -545,6 +575,13 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     if (a->resid) VTP_CHECK_ARG(a->ldr % (a->resid_dtype == VTP_F32 ? 4 : 8) == 0, "gemm: ldr alignment");
     if (a->out2) VTP_CHECK_ARG(a->ldo2 % 8 == 0, "gemm: ldo2 alignment");
 
+    const bool conv = a->conv_C > 0;
+    if (conv) {
+        VTP_CHECK_ARG(a->conv_C % 64 == 0 && a->conv_H > 0 && a->conv_W % 4 == 0 && !a->a_mn_major && a->K == 9 * a->conv_C &&
+                          a->M % (a->conv_H * a->conv_W) == 0 && a->rr_group == 0 && a->ps_r == 0,
+                      "gemm(conv): need C %% 64 == 0, W %% 4 == 0, K == 9*C, M == B*H*W");
+    }
+    if (a->mask_pos) VTP_CHECK_ARG(a->out_dtype == VTP_BF16 && a->ldm % 8 == 0, "gemm: mask_pos needs bf16 out");
     // tile-N choice: minimise padded N, ties -> 256 (lower smem bandwidth per MMA)
     const int pad128 = ceil_div(a->N, 128) * 128, pad256 = ceil_div(a->N, 256) * 256;
     const int BN = (pad256 <= pad128) ? 256 : 128;
@@ -568,9 +605,23 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     p.rope_tokens = a->rope_tokens, p.rope_prefix = a->rope_prefix, p.rope_cols = a->rope_cols;
     p.ps_r = a->ps_r, p.ps_gh = a->ps_gh, p.ps_gw = a->ps_gw, p.ps_cout = a->ps_cout;
     p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2), p.ldo2 = a->ldo2;
+    p.mask_pos = reinterpret_cast<const __nv_bfloat16*>(a->mask_pos), p.ldm = a->ldm;
 
     CUtensorMap tmA, tmB;
-    {
+    if (conv) {
+        const int W = a->conv_W, H = a->conv_H, Cc = a->conv_C, Bimg = a->M / (H * W);
+        p.conv_C = Cc, p.conv_H = H, p.conv_W = W;
+        p.conv_TW = (W % 16 == 0) ? 16 : (W % 8 == 0 ? 8 : 4);
+        p.conv_TH = 128 / p.conv_TW;
+        p.conv_tiles_w = W / p.conv_TW, p.conv_tiles_h = ceil_div(H, p.conv_TH);
+        p.num_m_blocks = Bimg * p.conv_tiles_h * p.conv_tiles_w;
+        p.M = p.num_m_blocks * 128;  // virtual rows (tile-local addressing, see out_row)
+        uint64_t dims[4] = {(uint64_t)Cc, (uint64_t)W, (uint64_t)H, (uint64_t)Bimg};
+        uint64_t strides[3] = {(uint64_t)Cc * 2, (uint64_t)W * Cc * 2, (uint64_t)H * W * Cc * 2};
+        uint32_t box[4] = {64, (uint32_t)p.conv_TW, (uint32_t)p.conv_TH, 1};
+        int rc = make_tmap_bf16(&tmA, a->A, 4, dims, strides, box);
+        if (rc) return rc;
+    } else {
         uint64_t dims[2], strides[1] = {(uint64_t)a->lda * 2};
         uint32_t box[2];
         if (!p.a_mn) dims[0] = a->K, dims[1] = a->M, box[0] = 64, box[1] = 128;

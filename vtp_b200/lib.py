@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvtp_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU, ACT_SWIGLU8, ACT_ROPE = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_SWIGLU8, ACT_ROPE, ACT_RELU = 0, 1, 2, 3, 4
 
 
 class VtpError(RuntimeError):
@@ -35,6 +35,8 @@ class GemmArgs(C.Structure):
         ("rope_tokens", C.c_int), ("rope_prefix", C.c_int), ("rope_cols", C.c_int),
         ("ps_r", C.c_int), ("ps_gh", C.c_int), ("ps_gw", C.c_int), ("ps_cout", C.c_int),
         ("out2", C.c_void_p), ("ldo2", C.c_int),
+        ("conv_C", C.c_int), ("conv_H", C.c_int), ("conv_W", C.c_int),
+        ("mask_pos", C.c_void_p), ("ldm", C.c_int),
     ]
 
 
@@ -86,6 +88,13 @@ SIGNATURES: dict[str, tuple] = {
                                       C.c_float, C.c_void_p, C.c_void_p]),
     "vtp_weight_norm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vtp_weight_norm_bwd": (C.c_int, [C.c_void_p] * 6 + [C.c_int, C.c_int, C.c_void_p]),
+    "vtp_lpips_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_maxpool2_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "vtp_pool_relu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                    C.c_void_p]),
+    "vtp_lpips_tap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_float, C.c_void_p,
+                                C.c_void_p]),
+    "vtp_lpips_img_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vtp_recon_l1_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
 }
@@ -142,7 +151,7 @@ def gemm(A, B, out, *, M: int, N: int, K: int, lda: int | None = None, ldb: int 
          a_mn: bool = False, b_mn: bool = False, bias=None, act: int = ACT_NONE, round_bf16: bool = True,
          resid=None, ldr: int | None = None, accumulate: bool = False, split_k: int = 1,
          rr_group: int = 0, rr_skip: int = 0, rope=None, pixel_shuffle=None, out2=None, ldo2: int | None = None,
-         stream: int | None = None) -> None:
+         conv=None, mask_pos=None, stream: int | None = None) -> None:
     """out = epi(A · Bᵀ). A/B bf16 tensors (any shape; leading dims given explicitly or inferred from stride(-2))."""
     a = GemmArgs()
     a.M, a.N, a.K = M, N, K
@@ -165,6 +174,10 @@ def gemm(A, B, out, *, M: int, N: int, K: int, lda: int | None = None, ldb: int 
         a.ps_r, a.ps_gh, a.ps_gw, a.ps_cout = pixel_shuffle
     if out2 is not None:
         a.out2, a.ldo2 = _ptr(out2), (ldo2 if ldo2 is not None else out2.stride(-2))
+    if conv is not None:
+        a.conv_C, a.conv_H, a.conv_W = conv
+    if mask_pos is not None:
+        a.mask_pos, a.ldm = _ptr(mask_pos), mask_pos.stride(-2)
     check(load().vtp_gemm_bf16(C.byref(a), stream if stream is not None else current_stream()), "vtp_gemm_bf16")
 
 
@@ -319,3 +332,26 @@ def weight_norm_fwd(v, g, w, vnorm, K: int, D: int, stream=None):
 def weight_norm_bwd(v, g, vnorm, dW, dv, dg, K: int, D: int, stream=None):
     check(load().vtp_weight_norm_bwd(_ptr(v), _ptr(g), _ptr(vnorm), _ptr(dW), _ptr(dv), _ptr(dg), K, D, _st(stream)),
           "vtp_weight_norm_bwd")
+
+
+# ------------------------------------------------------------------------------------------------ LPIPS
+def lpips_prep(img, out, B: int, H: int, W: int, stream=None):
+    check(load().vtp_lpips_prep(_ptr(img), _dt(img), _ptr(out), B, H, W, _st(stream)), "vtp_lpips_prep")
+
+
+def maxpool2_fwd(x, y, B: int, H: int, W: int, Cc: int, stream=None):
+    check(load().vtp_maxpool2_fwd(_ptr(x), _ptr(y), B, H, W, Cc, _st(stream)), "vtp_maxpool2_fwd")
+
+
+def pool_relu_bwd(y, dpool, gtap, dz, B: int, H: int, W: int, Cc: int, stream=None):
+    check(load().vtp_pool_relu_bwd(_ptr(y), _ptr(dpool), _ptr(gtap), _ptr(dz), B, H, W, Cc, _st(stream)),
+          "vtp_pool_relu_bwd")
+
+
+def lpips_tap(f0, f1, w, g0, P: int, Cc: int, coef: float, loss_acc, stream=None):
+    check(load().vtp_lpips_tap(_ptr(f0), _ptr(f1), _ptr(w), _ptr(g0), P, Cc, coef, _ptr(loss_acc), _st(stream)),
+          "vtp_lpips_tap")
+
+
+def lpips_img_grad(dcol, dimg, B: int, H: int, W: int, stream=None):
+    check(load().vtp_lpips_img_grad(_ptr(dcol), _ptr(dimg), B, H, W, _st(stream)), "vtp_lpips_img_grad")
