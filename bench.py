@@ -36,6 +36,7 @@ def parse():
     ap.add_argument("--prototypes", type=int, default=65536)
     ap.add_argument("--cpu-batch", type=int, default=2, help="source images per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lpips", action="store_true", help="reconstruction loss = L1 only")
     return ap.parse_args()
 
 
@@ -169,6 +170,8 @@ def main():
     cfg = preset(args.model)
     tc = TrainConfig(head_out_dim=args.prototypes)
     tr = VTPTrainer(cfg, tc, device=dev)
+    if not args.no_lpips:
+        tr.enable_lpips(seed=0, chunk=32)
     log(f"trainer built: {tr.store.n / 1e6:.1f}M params")
     B = args.batch
     host = make_batch(B, vocab=cfg.text_vocab_size, seed=1234 + rank, pin=True)
@@ -253,7 +256,7 @@ def main():
     peak_burst = peaks.get("bf16_tflops", 1590.0)
     peak_sust = peaks.get("bf16_tflops_sustained", 1400.0)
     src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
-    fl = train_step_flops_per_image(cfg, K=args.prototypes)
+    fl = train_step_flops_per_image(cfg, K=args.prototypes, lpips=not args.no_lpips)
     imgs = B * world * args.steps
     value = imgs / (ms * 1e-3)
     step_tflops = fl["total"] * B / (ms / args.steps * 1e-3) / 1e12  # per GPU
@@ -264,8 +267,8 @@ def main():
         "config": {"workload": f"VTP-{args.model} f16d64 full 3-loss training step (contrastive+SSL+recon), batch={B}/GPU",
                    "model": "VTP-Small 384/12/6 x3 towers (ASSUMED, SURVEY.md §8d)" if args.model == "small" else args.model,
                    "global_batch": B * world, "image": 256, "crops": "2 global 256 + 8 local 96 per image",
-                   "prototypes": args.prototypes, "losses": ["clip", "dino_local", "dino_global", "ibot", "rec_l1"],
-                   "lpips": False, "optimizer": "fused AdamW + EMA teacher, in the timed region",
+                   "prototypes": args.prototypes, "losses": ["clip", "dino_local", "dino_global", "ibot", "rec_l1"] + ([] if args.no_lpips else ["rec_lpips"]),
+                   "lpips": (not args.no_lpips) and "VGG16 (frozen, seeded-random weights: pretrained ones need network), weight 1.0", "optimizer": "fused AdamW + EMA teacher, in the timed region",
                    "l2": "inputs (>1 GB/step) and activations far exceed the 126 MB L2; no reuse across steps",
                    "parallelism": f"dp{world}", "flops_per_image": fl["total"]},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
@@ -277,7 +280,7 @@ def main():
                      "peak_source": src + " burst (kernel timed alone)", "traffic": None,
                      "step": {"achieved": step_tflops, "peak": peak_sust, "frac": step_tflops / peak_sust,
                               "note": "whole-step algorithmic FLOPs (vtp_b200/flops.py) / step time vs sustained bf16 peak"}},
-        "loss": [round(float(x), 5) for x in loss_host[:5]],
+        "loss": [round(float(x), 5) for x in loss_host[:6]],
     }
     if world == 1 and not args.no_cpu_baseline:
         log("cpu baseline ...")

@@ -1,0 +1,51 @@
+"""GPU parity of the LPIPS loss + image gradient (tcgen05 implicit-conv VGG16) against the CPU oracle restatement of
+vtp/utils/lpips.py with identical (seeded random) VGG/lin weights."""
+import pytest
+import torch
+
+from oracle import vtp_oracle as vo
+from tests.util import rel
+from vtp_b200 import lib
+from vtp_b200.lpips import LPIPSLoss, random_weights
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,H", [(2, 64), (1, 128)])
+def test_lpips_loss_and_grad(B, H):
+    vw, vb, lw = random_weights(0)
+    g = torch.Generator().manual_seed(3)
+    rec = (torch.randn(B, 3, H, H, generator=g) * 0.5).to(torch.bfloat16)
+    tgt = torch.randn(B, 3, H, H, generator=g) * 0.5
+    r = rec.float().requires_grad_(True)
+    val = vo.lpips(r, tgt, vw, vb, lw, mode="bf16")          # [B,1,1,1]
+    loss = val.mean()
+    loss.backward()
+    mod = LPIPSLoss(vw, vb, lw, device="cuda", chunk=1)
+    acc = torch.zeros(1, device="cuda")
+    dimg = mod.loss_and_grad(rec.cuda(), tgt.cuda(), 1.0 / B, acc)
+    torch.cuda.synchronize()
+    assert torch.isfinite(dimg).all()
+    assert abs(acc.item() - loss.item()) < 3e-2 * abs(loss.item()), (acc.item(), loss.item())
+    e = rel(dimg, r.grad)
+    assert e < 8e-2, e
+
+
+def test_conv_mode_gemm_matches_conv2d():
+    B, H, W, Ci, Co = 2, 16, 16, 64, 128
+    x = (torch.randn(B, H, W, Ci, device="cuda") * 0.5).to(torch.bfloat16)
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda") * 0.05).to(torch.bfloat16)
+    b = torch.randn(Co, device="cuda") * 0.1
+    wk = w.permute(0, 2, 3, 1).reshape(Co, 9 * Ci).contiguous()
+    y = torch.empty(B, H, W, Co, device="cuda", dtype=torch.bfloat16)
+    lib.gemm(x, wk, y, M=B * H * W, N=Co, K=9 * Ci, lda=Ci, ldb=9 * Ci, bias=b, act=lib.ACT_RELU, ldo=Co, conv=(Ci, H, W))
+    ref = torch.relu(torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1)).permute(0, 2, 3, 1)
+    assert rel(y, ref) < 5e-3
+    # small feature map (W = 4 -> 4x32 tiles, mostly out of bounds) and the ReLU-mask epilogue
+    x2 = (torch.randn(3, 4, 4, 64, device="cuda")).to(torch.bfloat16)
+    m2 = torch.randn(3, 4, 4, 128, device="cuda").to(torch.bfloat16)
+    y2 = torch.empty(3, 4, 4, Co, device="cuda", dtype=torch.bfloat16)
+    lib.gemm(x2, wk, y2, M=48, N=Co, K=9 * Ci, lda=Ci, ldb=9 * Ci, ldo=Co, conv=(Ci, 4, 4), round_bf16=False, mask_pos=m2)
+    ref2 = torch.nn.functional.conv2d(x2.float().permute(0, 3, 1, 2), w.float(), None, padding=1).permute(0, 2, 3, 1)
+    ref2 = ref2 * (m2.float() > 0)
+    assert rel(y2, ref2) < 5e-3

@@ -272,7 +272,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 float x1 = v[16 * g + i], x2 = v[16 * g + 8 + i];
-                float s = x1 / (1.0f + __expf(-x1));
+                float s = __fdividef(x1, 1.0f + __expf(-x1));
                 if (p.round_bf16) s = bf16_round(s);
                 float h = s * x2;
                 v[8 * g + i] = p.round_bf16 ? bf16_round(h) : h;

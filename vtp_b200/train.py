@@ -245,6 +245,7 @@ class VTPTrainer:
         self.store = st
         self._build_towers()
         self.step_count = 0
+        self.lpips = None  # perceptual term of the reconstruction loss, see enable_lpips()
         self.loss_acc = torch.zeros(8, dtype=F32, device=self.device)  # clip, dino_local, dino_global, ibot, rec
         self.center_dino = torch.zeros(K, dtype=F32, device=self.device)
         self.center_ibot = torch.zeros(K, dtype=F32, device=self.device)
@@ -255,6 +256,13 @@ class VTPTrainer:
         from .rope import rope_periods
         self._periods_v = rope_periods(64)
         self.reset_parameters()
+
+    def enable_lpips(self, module=None, seed: int = 0, chunk: int = 32):
+        """Attach the LPIPS term (utils/lpips.py) to the reconstruction loss: rec = L1 + lpips_weight * LPIPS.  Without
+        a supplied module, frozen seeded-random VGG16/lin weights are used (the trained ones need network access)."""
+        from .lpips import LPIPSLoss
+        self.lpips = module if module is not None else LPIPSLoss.random_init(seed, device=self.device, chunk=chunk)
+        return self.lpips
 
     # -------------------------------------------------------------- towers as views of the flat buffers
     def _build_towers(self):
