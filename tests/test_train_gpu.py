@@ -207,3 +207,29 @@ def test_full_step_runs_and_learns():
         rec_m = m.get_latents_decoded_images(m.get_reconstruction_latents(batch["rec_image"]))
     rec_t = tr.rec_fwd_bwd(batch["rec_image"], 1.0, return_image=True)
     assert rel(rec_m, rec_t) < 2e-2
+
+
+def test_rec_objective_with_lpips_gradients():
+    """recon = L1 + 1.0 * LPIPS (frozen seeded-random VGG16): loss terms and trunk/decoder gradients vs oracle autograd."""
+    from vtp_b200.lpips import LPIPSLoss, random_weights
+
+    cfg, sd, hsd, tr = _setup()
+    vw, vb, lw = random_weights(0)
+    tr.enable_lpips(LPIPSLoss(vw, vb, lw, device="cuda", chunk=2))
+    x = seeded_images(3, 64, 64) * 0.5
+    p = _leafs(sd)
+    lat = vo.reconstruction_latents(x, p, depth=2, heads=2, mode="bf16")
+    rec = vo.decode_latents(lat, p, depth=2, heads=2, mode="bf16")
+    lp = vo.lpips(rec, x, vw, vb, lw, mode="bf16")
+    loss = vo.recon_loss(rec, x, lp, 1.0)
+    loss.backward()
+    tr.rec_fwd_bwd(x.cuda(), 1.0)
+    torch.cuda.synchronize()
+    l1, lpv = tr.loss_acc[4].item(), tr.loss_acc[5].item()
+    assert abs(lpv - lp.mean().item()) < 3e-2 * abs(lp.mean().item()), (lpv, lp.mean().item())
+    assert abs(l1 + lpv - loss.item()) < TOL_L * loss.item()
+    errs = _vit_checks(tr, p, "pixel_decoder.", "decoder.", [0, 1], True)
+    errs.update(_vit_checks(tr, p, "trunk.", "trunk.", [0], False))
+    errs["proj_out.w"] = _check(tr, "decoder.proj_out.w", p["pixel_decoder.proj_out.weight"].grad.flatten(1))
+    errs["bneck"] = _check(tr, "trunk.bneck.w", p["trunk.feature_bottleneck.weight"].grad)
+    print("rec+lpips grad rel errors: max", max(errs.values()))
