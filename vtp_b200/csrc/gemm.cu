@@ -76,26 +76,17 @@ __device__ __forceinline__ long out_row(const GemmDev& p, int grow) {
     return tok < -p.rr_skip ? -1 : (long)(grow / p.rr_group) * (p.rr_group + p.rr_skip) + tok + p.rr_skip;
 }
 
-// residual prefetch for one 64-column unit in the cooperative layout: rp[h][it] = 4 values of row (4*it + lane/8),
-// columns ocol0 + 32*h + 4*(lane%8)
-__device__ __forceinline__ void prefetch_resid(const GemmDev& p, int lane, int grow0, int ocol0, int ncols, int Nout,
-                                               float4 (&rp)[2][8]) {
-    const int c4 = 4 * (lane & 7);
+// warm the residual lines of one unit in L2 (no registers held): row 4*it + lane/8, one 128-byte line per 8 lanes
+__device__ __forceinline__ void prefetch_resid_l2(const GemmDev& p, int lane, const long (&orow8)[8], int ocol0, int ncols,
+                                                  int Nout) {
+    if ((lane & 7) != 0) return;
+    const int esz = p.resid_dtype == VTP_F32 ? 4 : 2;
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-#pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            rp[h][it] = make_float4(0.f, 0.f, 0.f, 0.f);
-            const long orow = out_row(p, grow0 + 4 * it + (lane >> 3));
-            const int col = ocol0 + 32 * h + c4;
-            if (orow < 0 || 32 * h + c4 >= ncols || col + 4 > Nout) continue;
-            if (p.resid_dtype == VTP_F32) {
-                rp[h][it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + orow * p.ldr + col);
-            } else {
-                const uint2 r2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + orow * p.ldr + col);
-                rp[h][it] = make_float4(bf16_lo(r2.x), bf16_hi(r2.x), bf16_lo(r2.y), bf16_hi(r2.y));
-            }
-        }
+    for (int it = 0; it < 8; ++it) {
+        if (orow8[it] < 0 || ocol0 >= Nout) continue;
+        const char* base = reinterpret_cast<const char*>(p.resid) + (orow8[it] * p.ldr + ocol0) * esz;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(base));
+        if (ncols * esz > 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + 128));
     }
 }
 
@@ -116,26 +107,13 @@ __device__ __forceinline__ void stage_bf16(uint8_t* stg, int lane, const float (
     }
 }
 
-// residual prefetch (bf16 residual stream) for a 64-column bf16 unit: rb[it] = 8 values of row (4*it + lane/8)
-__device__ __forceinline__ void prefetch_resid_bf16(const GemmDev& p, int lane, int grow0, int ocol0, int ncols, int Nout,
-                                                    uint4 (&rb)[8]) {
-    const int c8 = 8 * (lane & 7);
-#pragma unroll
-    for (int it = 0; it < 8; ++it) {
-        rb[it] = make_uint4(0u, 0u, 0u, 0u);
-        const long orow = out_row(p, grow0 + 4 * it + (lane >> 3));
-        if (orow < 0 || c8 >= ncols || ocol0 + c8 + 8 > Nout) continue;
-        rb[it] = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + orow * p.ldr + ocol0 + c8);
-    }
-}
-
 __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
     return pack_bf16x2(bf16_lo(a) + bf16_lo(b), bf16_hi(a) + bf16_hi(b));
 }
 
 // cooperative store of a staged bf16 unit: dst = p.out (which=0) or p.out2 (which=1); ncols valid columns (32|64)
-__device__ __forceinline__ void store_bf16(const GemmDev& p, const uint8_t* stg, int lane, int grow0, int ocol0, int ncols,
-                                           int Nout, int which, const uint4 (&rb)[8], bool has_resid) {
+__device__ __forceinline__ void store_bf16(const GemmDev& p, const uint8_t* stg, int lane, const long (&orow8)[8], int ocol0,
+                                           int ncols, int Nout, int which, bool has_resid) {
     const int cidx = lane & 7;
     const int c8 = 8 * cidx;
     const bool col_ok = c8 < ncols && ocol0 + c8 + 8 <= Nout;
@@ -144,12 +122,13 @@ __device__ __forceinline__ void store_bf16(const GemmDev& p, const uint8_t* stg,
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
         const int R = 4 * it + (lane >> 3);
-        const long orow = out_row(p, grow0 + R);
+        const long orow = orow8[it];
         if (orow < 0 || !col_ok) continue;
         uint4 w = *reinterpret_cast<const uint4*>(stg + stgb_off(R, cidx));
         if (has_resid && which == 0) {
-            w.x = add_bf16x2(w.x, rb[it].x), w.y = add_bf16x2(w.y, rb[it].y);
-            w.z = add_bf16x2(w.z, rb[it].z), w.w = add_bf16x2(w.w, rb[it].w);
+            const uint4 rb = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + orow * p.ldr + ocol0 + c8);
+            w.x = add_bf16x2(w.x, rb.x), w.y = add_bf16x2(w.y, rb.y);
+            w.z = add_bf16x2(w.z, rb.z), w.w = add_bf16x2(w.w, rb.w);
         }
         if (p.mask_pos && which == 0) {  // keep x where the forward activation was > 0 (bf16: sign bit clear, non-zero)
             const uint4 m = *reinterpret_cast<const uint4*>(p.mask_pos + orow * p.ldm + ocol0 + c8);
@@ -165,8 +144,9 @@ __device__ __forceinline__ void store_bf16(const GemmDev& p, const uint8_t* stg,
 }
 
 // cooperative store of one staged 32-column half.  which = 0: main output, 1: secondary bf16 output (pre-activation)
-__device__ __forceinline__ void store_half(const GemmDev& p, const float* stg, int lane, int grow0, int ocol0, int h,
-                                           int ncols, int Nout, int which, const float4 (&rp)[2][8], bool has_resid) {
+template <bool PS>
+__device__ __forceinline__ void store_half(const GemmDev& p, const float* stg, int lane, int grow0, const long (&orow8)[8],
+                                           int ocol0, int h, int ncols, int Nout, int which, bool has_resid) {
     const int cidx = lane & 7;
     const int c4 = 32 * h + 4 * cidx;
     const int col = ocol0 + c4;
@@ -175,7 +155,7 @@ __device__ __forceinline__ void store_half(const GemmDev& p, const float* stg, i
     for (int it = 0; it < 8; ++it) {
         const int R = 4 * it + (lane >> 3);
         const int grow = grow0 + R;
-        const long orow = out_row(p, grow);
+        const long orow = orow8[it];
         if (orow < 0 || !col_ok) continue;
         float4 v = *reinterpret_cast<const float4*>(stg + stg_off(R, cidx));
         if (which == 1) {
@@ -184,7 +164,7 @@ __device__ __forceinline__ void store_half(const GemmDev& p, const float* stg, i
             *reinterpret_cast<uint2*>(p.out2 + orow * p.ldo2 + col) = w;
             continue;
         }
-        if (p.ps_r > 0) {  // PixelShuffle store (decoders/pixel_decoder.py:157-160): col = c*r*r + i*r + j
+        if constexpr (PS) {  // PixelShuffle store (decoders/pixel_decoder.py:157-160): col = c*r*r + i*r + j
             const int r = p.ps_r, gw = p.ps_gw, gh = p.ps_gh;
             const int b = grow / (gh * gw), hi = (grow / gw) % gh, wi = grow % gw;
             const int c = col / (r * r), ii = (col / r) % r, jj = col % r;
@@ -198,7 +178,15 @@ __device__ __forceinline__ void store_half(const GemmDev& p, const float* stg, i
             }
             continue;
         }
-        if (has_resid) v.x += rp[h][it].x, v.y += rp[h][it].y, v.z += rp[h][it].z, v.w += rp[h][it].w;
+        if (has_resid) {
+            if (p.resid_dtype == VTP_F32) {
+                const float4 r4 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.resid) + orow * p.ldr + col);
+                v.x += r4.x, v.y += r4.y, v.z += r4.z, v.w += r4.w;
+            } else {
+                const uint2 r2 = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + orow * p.ldr + col);
+                v.x += bf16_lo(r2.x), v.y += bf16_hi(r2.x), v.z += bf16_lo(r2.y), v.w += bf16_hi(r2.y);
+            }
+        }
         if (p.out_dtype == VTP_F32) {
             float* op = reinterpret_cast<float*>(p.out) + orow * p.ldo + col;
             if (p.accumulate) atomicAdd(reinterpret_cast<float4*>(op), v);
@@ -220,8 +208,9 @@ __device__ __forceinline__ void stage_half(float* stg, int lane, const float (&v
 
 // one 64-column unit of a 32-row slab.  grow0 = first row of the slab, lane's own row = grow0 + lane.
 // sw_half: for SwiGLU with bf16 output two adjacent packed units fill one 64-column hidden line; 0 = first, 1 = second
-__device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int lane, float (&v)[64], int grow0, int col0,
-                                              const float4 (&rp)[2][8], const uint4 (&rb)[8], bool has_resid, int sw_half,
+template <int ACT, bool PS>
+__device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int lane, float (&v)[64], int grow0,
+                                              const long (&orow8)[8], int col0, bool has_resid, int sw_half,
                                               uint32_t (&hold)[16]) {
     const int N = p.N;
     const int grow = grow0 + lane;
@@ -248,7 +237,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
     if (p.out2) {
         stage_bf16(stgb, lane, v, 0, 64);
         __syncwarp();
-        store_bf16(p, stgb, lane, grow0, col0, 64, N, 1, rb, false);
+        store_bf16(p, stgb, lane, orow8, col0, 64, N, 1, false);
         __syncwarp();
     }
 
@@ -256,16 +245,16 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
     int ocol0 = col0;      // first output column
     int Nout = N;
     // ---- activation
-    if (p.act == VTP_ACT_GELU) {
+    if constexpr (ACT == VTP_ACT_GELU) {
 #pragma unroll
         for (int i = 0; i < 64; ++i) {
             float g = gelu_erf(v[i]);
             v[i] = p.round_bf16 ? bf16_round(g) : g;
         }
-    } else if (p.act == VTP_ACT_RELU) {
+    } else if constexpr (ACT == VTP_ACT_RELU) {
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = fmaxf(v[i], 0.f);
-    } else if (p.act == VTP_ACT_SWIGLU8) {
+    } else if constexpr (ACT == VTP_ACT_SWIGLU8) {
         // packed columns: [16g, 16g+8) = x1, [16g+8, 16g+16) = x2  ->  hidden[8g + i] = silu(x1) * x2
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -281,7 +270,7 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
         ncols = 32;
         ocol0 = col0 >> 1;
         Nout = N >> 1;
-    } else if (p.act == VTP_ACT_ROPE) {
+    } else if constexpr (ACT == VTP_ACT_ROPE) {
         const int tok = grow % p.rope_tokens;
         const int pos = tok - p.rope_prefix;
         if (col0 < p.rope_cols && pos < 0) {
@@ -312,8 +301,8 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
             }
         }
     }
-    if (p.out_dtype == VTP_BF16 && p.ps_r == 0) {
-        if (p.act == VTP_ACT_SWIGLU8) {
+    if (!PS && p.out_dtype == VTP_BF16) {
+        if constexpr (ACT == VTP_ACT_SWIGLU8) {
             // 32 hidden columns per packed unit: the pair (sw_half 0,1) forms one 64-column (128-byte) output line.
             // The first half waits in registers (the staging tile is reused by the partner's pre-activation store).
             if (sw_half == 0 && col0 + 64 < N) {
@@ -328,13 +317,13 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
                 }
                 stage_bf16(stgb, lane, v, 32 * sw_half, 32);
                 __syncwarp();
-                store_bf16(p, stgb, lane, grow0, ocol0 - 32 * sw_half, 32 * (sw_half + 1), Nout, 0, rb, false);
+                store_bf16(p, stgb, lane, orow8, ocol0 - 32 * sw_half, 32 * (sw_half + 1), Nout, 0, false);
                 __syncwarp();
             }
         } else {
             stage_bf16(stgb, lane, v, 0, 64);
             __syncwarp();
-            store_bf16(p, stgb, lane, grow0, ocol0, 64, Nout, 0, rb, has_resid);
+            store_bf16(p, stgb, lane, orow8, ocol0, 64, Nout, 0, has_resid);
             __syncwarp();
         }
         return;
@@ -344,13 +333,13 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
         if (32 * h < ncols) {
             stage_half(stg, lane, v, h);
             __syncwarp();
-            store_half(p, stg, lane, grow0, ocol0, h, ncols, Nout, 0, rp, has_resid);
+            store_half<PS>(p, stg, lane, grow0, orow8, ocol0, h, ncols, Nout, 0, has_resid);
             __syncwarp();
         }
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int ACT, bool PS>
 // 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
@@ -480,7 +469,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int grow0 = m0 + q * 32;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
             bool waited = false;
-            const bool sw = p.act == VTP_ACT_SWIGLU8;
+            constexpr bool sw = ACT == VTP_ACT_SWIGLU8;
+            long orow8[8];  // output rows of the cooperative store pattern (row 4*it + lane/8 of this warp's slab)
+#pragma unroll
+            for (int it = 0; it < 8; ++it) orow8[it] = out_row(p, grow0 + 4 * it + (lane >> 3));
             // unit assignment: parity-interleaved, except SwiGLU where a warp takes ADJACENT packed units (2k, 2k+1) so
             // that their 32+32 hidden columns form one full 128-byte output line
             uint32_t hold[16];  // first half of a SwiGLU hidden line, kept in registers until its partner unit is done
@@ -490,14 +482,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (u >= BN / 64) break;
                 const int col0 = n0 + u * 64;
                 if (col0 >= p.N) break;  // warp-uniform
-                float4 rp[2][8];
-                uint4 rb[8];
-                if (has_resid) {  // issue the residual reads before the accumulator is needed
-                    if (p.out_dtype == VTP_BF16 && p.resid_dtype == VTP_BF16 && p.ps_r == 0 && !sw)
-                        prefetch_resid_bf16(p, lane, grow0, col0, 64, p.N, rb);
-                    else
-                        prefetch_resid(p, lane, grow0, sw ? col0 >> 1 : col0, sw ? 32 : 64, sw ? p.N >> 1 : p.N, rp);
-                }
+                if (has_resid)  // pull the residual lines into L2 while the accumulator is still being produced
+                    prefetch_resid_l2(p, lane, orow8, sw ? col0 >> 1 : col0, sw ? 32 : 64, sw ? p.N >> 1 : p.N);
                 if (!waited) {
                     mbar_wait(&tfull_bar[as], aph);
                     tc_fence_after();
@@ -510,7 +496,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 float v[64];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]), v[32 + i] = __uint_as_float(r1[i]);
-                epilogue_unit(p, stg, lane, v, grow0, col0, rp, rb, has_resid, sw ? (u & 1) : 0, hold);
+                epilogue_unit<ACT, PS>(p, stg, lane, v, grow0, orow8, col0, has_resid, sw ? (u & 1) : 0, hold);
             }
             if (!waited) {  // this warp had no unit in the tile (N tail): still consume the phase
                 mbar_wait(&tfull_bar[as], aph);
@@ -531,17 +517,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int ACT, bool PS>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream) {
     constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
     const int tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;
     const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_kernel<BN, STAGES><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
+    gemm_kernel<BN, STAGES, ACT, PS><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }
@@ -637,6 +623,20 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         int rc = make_tmap_bf16(&tmB, a->B, 2, dims, strides, box);
         if (rc) return rc;
     }
-    if (BN == 256) return launch_gemm<256, 4>(tmA, tmB, p, stream);
-    return launch_gemm<128, 6>(tmA, tmB, p, stream);
+    // one instantiation per epilogue family keeps each kernel's code (and register pressure) small
+#define VTP_LAUNCH(ACT_, PS_) \
+    return (BN == 256) ? launch_gemm<256, 4, ACT_, PS_>(tmA, tmB, p, stream) : launch_gemm<128, 6, ACT_, PS_>(tmA, tmB, p, stream)
+    if (a->ps_r > 0) {
+        VTP_CHECK_ARG(a->act == VTP_ACT_NONE, "gemm: pixel shuffle has no activation");
+        VTP_LAUNCH(VTP_ACT_NONE, true);
+    }
+    switch (a->act) {
+        case VTP_ACT_NONE: VTP_LAUNCH(VTP_ACT_NONE, false);
+        case VTP_ACT_GELU: VTP_LAUNCH(VTP_ACT_GELU, false);
+        case VTP_ACT_SWIGLU8: VTP_LAUNCH(VTP_ACT_SWIGLU8, false);
+        case VTP_ACT_ROPE: VTP_LAUNCH(VTP_ACT_ROPE, false);
+        case VTP_ACT_RELU: VTP_LAUNCH(VTP_ACT_RELU, false);
+        default: VTP_FAIL(VTP_ERR_ARG, "gemm: unknown activation %d", a->act);
+    }
+#undef VTP_LAUNCH
 }
