@@ -200,7 +200,7 @@ def test_softmax_ce_and_dino_losses():
 
 
 def test_adamw_weightnorm_recon():
-    n = 10007
+    n = 10008
     p = torch.randn(n, device="cuda")
     g = torch.randn(n, device="cuda")
     m = torch.zeros(n, device="cuda")

@@ -49,7 +49,13 @@ __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restric
         const float rstd = rstd_[row];
         const float mean = is_ln ? mean_[row] : 0.f;
         float xh[MAXV][4], dxh[MAXV][4];
+        float4 gv4[MAXV];  // stream gradient: loaded up front so its latency overlaps the row reductions
         float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int gidx = 0; gidx < MAXV; ++gidx) {
+            const int c = (gidx * 32 + lane) * 4;
+            if (c < D) gv4[gidx] = *reinterpret_cast<const float4*>(g + (long)row * D + c);
+        }
 #pragma unroll
         for (int gidx = 0; gidx < MAXV; ++gidx) {
             const int c = (gidx * 32 + lane) * 4;
@@ -79,7 +85,7 @@ __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restric
             const int c = (gidx * 32 + lane) * 4;
             if (c < D) {
                 float4* gp = reinterpret_cast<float4*>(g + (long)row * D + c);
-                float4 gv = *gp;
+                float4 gv = gv4[gidx];
                 gv.x += rstd * (dxh[gidx][0] - m1 - xh[gidx][0] * m2);
                 gv.y += rstd * (dxh[gidx][1] - m1 - xh[gidx][1] * m2);
                 gv.z += rstd * (dxh[gidx][2] - m1 - xh[gidx][2] * m2);
@@ -279,21 +285,40 @@ __global__ void scatter_add_rows_kernel(const TS* __restrict__ src, long ld_src,
 // gscale (1/world or loss scaling) and zeroed for the next step.
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              __nv_bfloat16* __restrict__ pb, float* __restrict__ tp, __nv_bfloat16* __restrict__ tpb,
-                             long n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
+                             long n4, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
                              float ema_mom) {
-    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
-        const float gi = g[i] * gscale;
-        g[i] = 0.f;
-        float mi = m[i] = b1 * m[i] + (1.f - b1) * gi;
-        float vi = v[i] = b2 * v[i] + (1.f - b2) * gi * gi;
-        float pi = p[i];
-        pi -= lr * ((mi / bc1) / (sqrtf(vi / bc2) + eps) + wd * pi);
-        p[i] = pi;
-        if (pb) pb[i] = __float2bfloat16_rn(pi);
+    // 4 parameters per thread per iteration (all buffers are 128-byte aligned and n % 4 == 0 by construction)
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
+        float4 gi = reinterpret_cast<float4*>(g)[i];
+        float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i], pi = reinterpret_cast<float4*>(p)[i];
+        reinterpret_cast<float4*>(g)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ga[4] = {gi.x * gscale, gi.y * gscale, gi.z * gscale, gi.w * gscale};
+        float ma[4] = {mi.x, mi.y, mi.z, mi.w}, va[4] = {vi.x, vi.y, vi.z, vi.w}, pa[4] = {pi.x, pi.y, pi.z, pi.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            ma[k] = b1 * ma[k] + (1.f - b1) * ga[k];
+            va[k] = b2 * va[k] + (1.f - b2) * ga[k] * ga[k];
+            pa[k] -= lr * ((ma[k] / bc1) / (sqrtf(va[k] / bc2) + eps) + wd * pa[k]);
+        }
+        reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
+        reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
+        reinterpret_cast<float4*>(p)[i] = make_float4(pa[0], pa[1], pa[2], pa[3]);
+        if (pb) {
+            uint2 w;
+            w.x = pack_bf16x2(pa[0], pa[1]), w.y = pack_bf16x2(pa[2], pa[3]);
+            reinterpret_cast<uint2*>(pb)[i] = w;
+        }
         if (tp) {
-            const float ti = ema_mom * tp[i] + (1.f - ema_mom) * pi;
-            tp[i] = ti;
-            if (tpb) tpb[i] = __float2bfloat16_rn(ti);
+            const float4 ti = reinterpret_cast<float4*>(tp)[i];
+            float ta[4] = {ti.x, ti.y, ti.z, ti.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ta[k] = ema_mom * ta[k] + (1.f - ema_mom) * pa[k];
+            reinterpret_cast<float4*>(tp)[i] = make_float4(ta[0], ta[1], ta[2], ta[3]);
+            if (tpb) {
+                uint2 w;
+                w.x = pack_bf16x2(ta[0], ta[1]), w.y = pack_bf16x2(ta[2], ta[3]);
+                reinterpret_cast<uint2*>(tpb)[i] = w;
+            }
         }
     }
 }
@@ -339,7 +364,7 @@ extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const
     VTP_CHECK_ARG(!is_ln || mean, "norm_bwd: LayerNorm needs mean");
     VTP_CHECK_ARG((reinterpret_cast<uintptr_t>(dw) & 15) == 0 && (!db || (reinterpret_cast<uintptr_t>(db) & 15) == 0),
                   "norm_bwd: dw/db must be 16B aligned");
-    const int threads = D <= 512 ? 512 : 256, rows_per_block = 256;  // register budget of the wider variants
+    const int threads = D <= 512 ? 512 : 256, rows_per_block = 128;  // register budget of the wider variants
     const int grid = ceil_div(M, rows_per_block);
     const size_t smem = 2 * (size_t)D * sizeof(float);
     cudaStream_t s = (cudaStream_t)st;
@@ -432,9 +457,11 @@ extern "C" int vtp_adamw_step(float* p, float* g, float* m, float* v, void* p_bf
                               long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
                               float grad_scale, float ema_momentum, vtp_stream_t st) {
     VTP_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adamw_step: bad args");
+    VTP_CHECK_ARG(n % 4 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0,
+                  "adamw_step: n %% 4 == 0 and 16B-aligned buffers required");
     const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
-    adamw_kernel<<<grid_cap(n, 256), 256, 0, (cudaStream_t)st>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, teacher,
-                                                                 (__nv_bfloat16*)teacher_bf16, n, lr, beta1, beta2, eps,
+    adamw_kernel<<<grid_cap(n / 4, 256), 256, 0, (cudaStream_t)st>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, teacher,
+                                                                     (__nv_bfloat16*)teacher_bf16, n / 4, lr, beta1, beta2, eps,
                                                                  weight_decay, bc1, bc2, grad_scale, ema_momentum);
     VTP_LAUNCH_CHECK();
     return VTP_OK;

@@ -228,7 +228,9 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
                 if (col0 + i < N) v[i] += __ldg(p.bias + col0 + i);
         }
     }
-    if (p.round_bf16) {
+    // the explicit rounding point is redundant when the value is only packed to bf16 afterwards (plain / ReLU store)
+    const bool pack_rounds = !PS && p.out_dtype == VTP_BF16 && (ACT == VTP_ACT_NONE || ACT == VTP_ACT_RELU);
+    if (p.round_bf16 && !pack_rounds) {
 #pragma unroll
         for (int i = 0; i < 64; ++i) v[i] = bf16_round(v[i]);
     }
@@ -294,7 +296,8 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
                     const float csl = (k & 1) ? bf16_hi(cl[k >> 1]) : bf16_lo(cl[k >> 1]);
                     const float snh = (k & 1) ? bf16_hi(sh[k >> 1]) : bf16_lo(sh[k >> 1]);
                     const float csh = (k & 1) ? bf16_hi(ch[k >> 1]) : bf16_lo(ch[k >> 1]);
-                    const float a = bf16_round(v[j]), b = bf16_round(v[j + 32]);
+                    const float a = p.round_bf16 ? v[j] : bf16_round(v[j]);  // q.to(bf16); already rounded in bf16 mode
+                    const float b = p.round_bf16 ? v[j + 32] : bf16_round(v[j + 32]);
                     v[j] = bf16_round(bf16_round(a * csl) + bf16_round((-b) * snl));
                     v[j + 32] = bf16_round(bf16_round(b * csh) + bf16_round(a * snh));
                 }
@@ -570,7 +573,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     if (a->mask_pos) VTP_CHECK_ARG(a->out_dtype == VTP_BF16 && a->ldm % 8 == 0, "gemm: mask_pos needs bf16 out");
     // tile-N choice: minimise padded N, ties -> 256 (lower smem bandwidth per MMA)
     const int pad128 = ceil_div(a->N, 128) * 128, pad256 = ceil_div(a->N, 256) * 256;
-    const int BN = (pad256 <= pad128) ? 256 : 128;
+    const int BN = (pad256 * 8 <= pad128 * 9) ? 256 : 128;  // accept <= 12.5 % padding for the higher-intensity tile
 
     GemmDev p;
     memset(&p, 0, sizeof(p));

@@ -58,24 +58,56 @@ __global__ void softmax_ce_kernel(const float* __restrict__ logits, long ld, int
 }
 
 // ------------------------------------------------------------------------------------------------ DINO / iBOT
-// teacher: probs[r,:] = softmax((t[r,:] − center) / temp), in place (bf16).  One block per row, row cached in smem.
+// teacher: probs[r,:] = softmax((t[r,:] − center) / temp), in place (bf16).  One block per row; the row is read from
+// HBM once (16-byte vector loads), cached in shared memory as raw bf16, and written once.  K % 8 == 0.
+__device__ __forceinline__ void unpack8(const uint4& q, float (&f)[8]) {
+    f[0] = bf16_lo(q.x), f[1] = bf16_hi(q.x), f[2] = bf16_lo(q.y), f[3] = bf16_hi(q.y);
+    f[4] = bf16_lo(q.z), f[5] = bf16_hi(q.z), f[6] = bf16_lo(q.w), f[7] = bf16_hi(q.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    uint4 q;
+    q.x = pack_bf16x2(f[0], f[1]), q.y = pack_bf16x2(f[2], f[3]), q.z = pack_bf16x2(f[4], f[5]), q.w = pack_bf16x2(f[6], f[7]);
+    return q;
+}
+
 __global__ void dino_teacher_kernel(__nv_bfloat16* __restrict__ t, const float* __restrict__ center, int K, float inv_temp) {
-    extern __shared__ __nv_bfloat16 rowb[];  // K raw bf16 logits (128 KB at K = 65536)
+    extern __shared__ uint4 rowq[];  // K/8 packed bf16x8 (128 KB at K = 65536)
     __shared__ float sh[32];
-    __nv_bfloat16* tr = t + (long)blockIdx.x * K;
+    uint4* tr = reinterpret_cast<uint4*>(t + (long)blockIdx.x * K);
+    const float4* c4 = reinterpret_cast<const float4*>(center);
+    const int K8 = K >> 3;
     float m = -INFINITY;
-    for (int c = threadIdx.x; c < K; c += blockDim.x) {
-        const __nv_bfloat16 raw = tr[c];
-        rowb[c] = raw;
-        m = fmaxf(m, (__bfloat162float(raw) - center[c]) * inv_temp);
+    for (int c = threadIdx.x; c < K8; c += blockDim.x) {
+        const uint4 q = tr[c];
+        rowq[c] = q;
+        float f[8];
+        unpack8(q, f);
+        const float4 a = __ldg(c4 + 2 * c), b = __ldg(c4 + 2 * c + 1);
+        const float cc[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) m = fmaxf(m, (f[i] - cc[i]) * inv_temp);
     }
     m = block_reduce(m, sh, true);
     float s = 0.f;
-    for (int c = threadIdx.x; c < K; c += blockDim.x) s += __expf((__bfloat162float(rowb[c]) - center[c]) * inv_temp - m);
+    for (int c = threadIdx.x; c < K8; c += blockDim.x) {
+        float f[8];
+        unpack8(rowq[c], f);
+        const float4 a = __ldg(c4 + 2 * c), b = __ldg(c4 + 2 * c + 1);
+        const float cc[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s += __expf((f[i] - cc[i]) * inv_temp - m);
+    }
     s = block_reduce(s, sh, false);
     const float lse = m + logf(s);
-    for (int c = threadIdx.x; c < K; c += blockDim.x)
-        tr[c] = __float2bfloat16_rn(__expf((__bfloat162float(rowb[c]) - center[c]) * inv_temp - lse));
+    for (int c = threadIdx.x; c < K8; c += blockDim.x) {
+        float f[8];
+        unpack8(rowq[c], f);
+        const float4 a = __ldg(c4 + 2 * c), b = __ldg(c4 + 2 * c + 1);
+        const float cc[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = __expf((f[i] - cc[i]) * inv_temp - lse);
+        tr[c] = pack8(f);
+    }
 }
 
 // student: for row r with teacher rows t0[r], t1[r] (−1 = none), weight w[r]:
@@ -83,38 +115,71 @@ __global__ void dino_teacher_kernel(__nv_bfloat16* __restrict__ t, const float* 
 __global__ void dino_student_kernel(__nv_bfloat16* __restrict__ s, const __nv_bfloat16* __restrict__ tprobs,
                                     const int* __restrict__ t0, const int* __restrict__ t1, const float* __restrict__ w,
                                     int K, float inv_temp, float* __restrict__ loss_acc) {
-    extern __shared__ __nv_bfloat16 rowb[];  // K raw bf16 student logits
+    extern __shared__ uint4 rowq[];  // K/8 packed student logits
     __shared__ float sh[32];
     const int r = blockIdx.x;
-    __nv_bfloat16* sr = s + (long)r * K;
+    uint4* sr = reinterpret_cast<uint4*>(s + (long)r * K);
     const int i0 = t0[r], i1 = t1 ? t1[r] : -1;
     const float wr = w[r];
-    const __nv_bfloat16* ta = i0 >= 0 ? tprobs + (long)i0 * K : nullptr;
-    const __nv_bfloat16* tb = i1 >= 0 ? tprobs + (long)i1 * K : nullptr;
+    const uint4* ta = i0 >= 0 ? reinterpret_cast<const uint4*>(tprobs + (long)i0 * K) : nullptr;
+    const uint4* tb = i1 >= 0 ? reinterpret_cast<const uint4*>(tprobs + (long)i1 * K) : nullptr;
     const float nv = (ta ? 1.f : 0.f) + (tb ? 1.f : 0.f);
+    const int K8 = K >> 3;
     float m = -INFINITY, dot = 0.f;
-    for (int c = threadIdx.x; c < K; c += blockDim.x) {
-        const __nv_bfloat16 raw = sr[c];
-        rowb[c] = raw;
-        const float z = __bfloat162float(raw) * inv_temp;
-        m = fmaxf(m, z);
-        float tt = 0.f;
-        if (ta) tt += __bfloat162float(ta[c]);
-        if (tb) tt += __bfloat162float(tb[c]);
-        dot += tt * z;
+    for (int c = threadIdx.x; c < K8; c += blockDim.x) {
+        const uint4 q = sr[c];
+        rowq[c] = q;
+        float z[8], tt[8];
+        unpack8(q, z);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] *= inv_temp, tt[i] = 0.f, m = fmaxf(m, z[i]);
+        if (ta) {
+            float f[8];
+            unpack8(__ldg(ta + c), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tt[i] += f[i];
+        }
+        if (tb) {
+            float f[8];
+            unpack8(__ldg(tb + c), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tt[i] += f[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dot += tt[i] * z[i];
     }
     m = block_reduce(m, sh, true);
     dot = block_reduce(dot, sh, false);
     float se = 0.f;
-    for (int c = threadIdx.x; c < K; c += blockDim.x) se += __expf(__bfloat162float(rowb[c]) * inv_temp - m);
+    for (int c = threadIdx.x; c < K8; c += blockDim.x) {
+        float z[8];
+        unpack8(rowq[c], z);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) se += __expf(z[i] * inv_temp - m);
+    }
     se = block_reduce(se, sh, false);
     const float lse = m + logf(se);
     const float gscale = wr * inv_temp;
-    for (int c = threadIdx.x; c < K; c += blockDim.x) {
-        float tt = 0.f;
-        if (ta) tt += __bfloat162float(ta[c]);
-        if (tb) tt += __bfloat162float(tb[c]);
-        sr[c] = __float2bfloat16_rn(gscale * (nv * __expf(__bfloat162float(rowb[c]) * inv_temp - lse) - tt));
+    for (int c = threadIdx.x; c < K8; c += blockDim.x) {
+        float z[8], tt[8];
+        unpack8(rowq[c], z);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tt[i] = 0.f;
+        if (ta) {
+            float f[8];
+            unpack8(__ldg(ta + c), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tt[i] += f[i];
+        }
+        if (tb) {
+            float f[8];
+            unpack8(__ldg(tb + c), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) tt[i] += f[i];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) z[i] = gscale * (nv * __expf(z[i] * inv_temp - lse) - tt[i]);
+        sr[c] = pack8(z);
     }
     if (threadIdx.x == 0) atomicAdd(loss_acc, wr * (nv * lse - dot));
 }
@@ -168,7 +233,7 @@ extern "C" int vtp_softmax_ce(const float* logits, long ld, int R, int C, int la
 }
 
 extern "C" int vtp_dino_teacher_probs(void* t_bf16, const float* center, int R, int K, float temp, vtp_stream_t st) {
-    VTP_CHECK_ARG(t_bf16 && center && R > 0 && K > 0 && temp > 0, "dino_teacher_probs: bad args");
+    VTP_CHECK_ARG(t_bf16 && center && R > 0 && K > 0 && K % 8 == 0 && temp > 0, "dino_teacher_probs: bad args (K %% 8 == 0)");
     const size_t smem = (size_t)K * sizeof(__nv_bfloat16);
     VTP_CHECK_ARG(smem <= 220 * 1024, "dino_teacher_probs: K=%d too large for the smem-resident row", K);
     static size_t conf = 0;
@@ -183,7 +248,8 @@ extern "C" int vtp_dino_teacher_probs(void* t_bf16, const float* center, int R, 
 
 extern "C" int vtp_dino_student_ce(void* s_bf16, const void* tprobs_bf16, const int* t0, const int* t1, const float* w,
                                    int R, int K, float temp, float* loss_acc, vtp_stream_t st) {
-    VTP_CHECK_ARG(s_bf16 && tprobs_bf16 && t0 && w && loss_acc && R > 0 && K > 0 && temp > 0, "dino_student_ce: bad args");
+    VTP_CHECK_ARG(s_bf16 && tprobs_bf16 && t0 && w && loss_acc && R > 0 && K > 0 && K % 8 == 0 && temp > 0,
+                  "dino_student_ce: bad args (K %% 8 == 0)");
     const size_t smem = (size_t)K * sizeof(__nv_bfloat16);
     VTP_CHECK_ARG(smem <= 220 * 1024, "dino_student_ce: K=%d too large for the smem-resident row", K);
     static size_t conf = 0;
