@@ -102,6 +102,10 @@ int vtp_transpose_batched(const void* in, int in_dtype, long in_bstride, void* o
 /* out[i,:] = in[idx[i],:] (vtp.py:432-439,470-473 iBOT gather; encoders/text_transformer.py:224 argmax pool) */
 int vtp_gather_rows(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, const int64_t* idx,
                     int n, int D, vtp_stream_t stream);
+/* stand-alone SwiGLU gate (layers/ffn.py:77-81) on the 8-interleaved pre-activation: hid = round(round(silu(x1))*x2) */
+int vtp_swiglu_fwd(const void* pre, void* hid, long M, int Hs, vtp_stream_t stream);
+/* stand-alone in-place axial RoPE (layers/attention.py:12-23,70-89, bf16 arithmetic) on the q,k parts of bf16 qkv */
+int vtp_rope_fwd(void* qkv, const void* sin, const void* cos, long rows, int T, int prefix, int D, vtp_stream_t stream);
 /* vtp_hf/modeling_vtp.py:297-298 — out[b*L+l] = token_embedding[ids[b,l]] + positional_embedding[l] (fp32) */
 int vtp_embed_tokens(const int64_t* ids, const float* emb, const float* pos, float* out, long BL, int L, int D,
                      vtp_stream_t stream);

@@ -96,3 +96,20 @@ def test_errors_mirror_reference():
         m.get_clip_image_feature(torch.zeros(1, 3, 64, 64, device="cuda"))
     with pytest.raises(ValueError):
         m.forward(torch.zeros(1, 3, 64, 64, device="cuda"), forward_type="bogus")
+
+
+def test_split_and_fused_epilogues_agree():
+    """bf16 mode: stand-alone RoPE / SwiGLU kernels (default) vs the fused GEMM epilogues — same rounding sequence."""
+    from vtp_b200 import engine
+
+    m, g, x, ids, meta = _build("tiny")
+    outs = {}
+    for flag in (True, False):
+        engine.SPLIT_EPILOGUES = flag
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                lat = m.get_reconstruction_latents(x)
+                outs[flag] = (lat.float().clone(), m.get_latents_decoded_images(lat).float().clone())
+        finally:
+            engine.SPLIT_EPILOGUES = True
+    assert rel(outs[False][0], outs[True][0]) < 2e-3 and rel(outs[False][1], outs[True][1]) < 2e-3

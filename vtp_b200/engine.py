@@ -21,6 +21,10 @@ from .rope import rope_sincos
 
 BF = torch.bfloat16
 F32 = torch.float32
+# bf16 hot path: run the RoPE rotation and the SwiGLU gate as stand-alone full-occupancy kernels after a plain GEMM instead
+# of inside the GEMM epilogue (measured faster at K = 384: see csrc/elementwise.cu).  The fused epilogues stay available
+# (fp32 mode uses them; set False to use them in bf16 mode too — identical numerics, tests cover both).
+SPLIT_EPILOGUES = True
 
 
 def _e(shape, dtype, dev):
@@ -238,7 +242,10 @@ def tower_blocks(W: TowerW, x: torch.Tensor, B: int, T: int, rope, mode: str, *,
         nt = {} if t is not None else None
         h = norm(x, M, D, bw.n1_w, bw.n1_b, W.eps, mode, want="op", tape=nt)
         qkv = _e((M, 3 * D), act, dev)
-        if rope is not None:
+        if rope is not None and mode == "bf16" and SPLIT_EPILOGUES:
+            linear(h, bw.qkv, qkv, M, mode)                 # rounding to bf16 == q.to(bf16) of the reference
+            lib.rope_fwd(qkv, rope[0], rope[1], M, T, W.prefix, D)
+        elif rope is not None:
             linear(h, bw.qkv, qkv, M, mode, act=lib.ACT_ROPE, rope=(rope[0], rope[1], T, W.prefix, 2 * D))
         else:
             linear(h, bw.qkv, qkv, M, mode)
@@ -258,7 +265,13 @@ def tower_blocks(W: TowerW, x: torch.Tensor, B: int, T: int, rope, mode: str, *,
         Hd = bw.hidden
         hid = _e((M, Hd), act, dev)
         pre = None
-        if W.ffn == "swiglu":
+        if W.ffn == "swiglu" and mode == "bf16" and SPLIT_EPILOGUES:
+            pre = _e((M, 2 * Hd), BF, dev)
+            linear(h2, bw.fc1, pre, M, mode)
+            lib.swiglu_fwd(pre, hid, M, Hd)
+            if t is None:
+                pre = None
+        elif W.ffn == "swiglu":
             pre = _e((M, 2 * Hd), BF, dev) if t is not None else None
             linear(h2, bw.fc1, hid, M, mode, act=lib.ACT_SWIGLU8, ldo=Hd, out2=pre)
         else:

@@ -60,6 +60,8 @@ SIGNATURES: dict[str, tuple] = {
                                         C.c_int, C.c_void_p]),
     "vtp_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int,
                                   C.c_int, C.c_void_p]),
+    "vtp_swiglu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]),
+    "vtp_rope_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vtp_embed_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]),
     "vtp_l2norm_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_float,
                                  C.c_void_p]),
@@ -355,3 +357,11 @@ def lpips_tap(f0, f1, w, g0, P: int, Cc: int, coef: float, loss_acc, stream=None
 
 def lpips_img_grad(dcol, dimg, B: int, H: int, W: int, stream=None):
     check(load().vtp_lpips_img_grad(_ptr(dcol), _ptr(dimg), B, H, W, _st(stream)), "vtp_lpips_img_grad")
+
+
+def swiglu_fwd(pre, hid, M: int, Hs: int, stream=None):
+    check(load().vtp_swiglu_fwd(_ptr(pre), _ptr(hid), M, Hs, _st(stream)), "vtp_swiglu_fwd")
+
+
+def rope_fwd(qkv, sin, cos, rows: int, T: int, prefix: int, D: int, stream=None):
+    check(load().vtp_rope_fwd(_ptr(qkv), _ptr(sin), _ptr(cos), rows, T, prefix, D, _st(stream)), "vtp_rope_fwd")
