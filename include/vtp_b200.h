@@ -133,9 +133,12 @@ int vtp_attention_fwd_f32(const float* qkv, float* out, int B, int T, int H, int
 int vtp_attention_bwd(const void* qkv, const void* o, const void* dout, const float* lse, void* dqkv,
                       const void* rope_sin, const void* rope_cos, int B, int T, int H, int prefix, int causal,
                       vtp_stream_t stream);
-/* dual of vtp_norm_fwd: g[M][D] (fp32 stream gradient) += dx ; dw[D] += ; db[D] += (LayerNorm) */
+/* dual of vtp_norm_fwd: g[M][D] (fp32 stream gradient) += dx ; dw[D] += ; db[D] += (LayerNorm).  Optional fused
+ * by-products of the updated g: g_bf16_out [M][D] (the dY operand of the preceding sub-layer) and g_colsum[D] += Σ_m g
+ * (that sub-layer's bias gradient) */
 int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const float* mean, const float* w, const void* dy_bf16,
-                 float* g, float* dw, float* db, int M, int D, int is_ln, vtp_stream_t stream);
+                 float* g, float* dw, float* db, int M, int D, int is_ln, void* g_bf16_out, float* g_colsum,
+                 vtp_stream_t stream);
 /* dual of the SwiGLU gate epilogue (layers/ffn.py:77-81): pre [M][2Hs] 8-interleaved, dhid [M][Hs] -> dpre, dbias */
 int vtp_swiglu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int Hs, vtp_stream_t stream);
 /* dual of the GELU epilogue (text MLP layers/block.py:399-403, DINO head heads/dino_head.py:92-126) */

@@ -79,7 +79,10 @@ def test_norm_bwd(D, ln, xbf):
     g = g0.clone()
     dw = torch.zeros(D, device="cuda")
     db = torch.zeros(D, device="cuda") if ln else None
-    lib.norm_bwd(x, rstd, mean, w, dy, g, dw, db, M, D)
+    gb = torch.empty(M, D, device="cuda", dtype=BF)
+    gs = torch.zeros(D, device="cuda")
+    lib.norm_bwd(x, rstd, mean, w, dy, g, dw, db, M, D, gb_out=gb, g_colsum=gs)
+    assert torch.equal(gb, g.to(BF)) and _rel(gs, g.sum(0)) < 1e-4
     xr = x.float().requires_grad_(True)
     wr = w.clone().requires_grad_(True)
     if ln:

@@ -33,16 +33,17 @@ template <typename TX, int MAXV>
 __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restrict__ rstd_, const float* __restrict__ mean_,
                                 const float* __restrict__ w, const __nv_bfloat16* __restrict__ dy, float* __restrict__ g,
                                 float* __restrict__ dw, float* __restrict__ db, int M, int D, int rows_per_block,
-                                int is_ln, int x_rounded_bf16) {
-    extern __shared__ float sred[];  // [2][D]
+                                int is_ln, int x_rounded_bf16, __nv_bfloat16* __restrict__ gb_out,
+                                float* __restrict__ gsum) {
+    extern __shared__ float sred[];  // [3][D]: dw | db | column sums of the updated g
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-    for (int i = threadIdx.x; i < 2 * D; i += blockDim.x) sred[i] = 0.f;
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) sred[i] = 0.f;
     __syncthreads();
-    float aw[MAXV][4], ab[MAXV][4];
+    float aw[MAXV][4], ab[MAXV][4], ag[MAXV][4];
 #pragma unroll
     for (int gidx = 0; gidx < MAXV; ++gidx)
 #pragma unroll
-        for (int i = 0; i < 4; ++i) aw[gidx][i] = 0.f, ab[gidx][i] = 0.f;
+        for (int i = 0; i < 4; ++i) aw[gidx][i] = 0.f, ab[gidx][i] = 0.f, ag[gidx][i] = 0.f;
     const int r0 = blockIdx.x * rows_per_block;
     const int r1 = min(M, r0 + rows_per_block);
     for (int row = r0 + warp; row < r1; row += nw) {
@@ -91,6 +92,12 @@ __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restric
                 gv.z += rstd * (dxh[gidx][2] - m1 - xh[gidx][2] * m2);
                 gv.w += rstd * (dxh[gidx][3] - m1 - xh[gidx][3] * m2);
                 *gp = gv;
+                if (gb_out) {  // bf16 copy of the updated stream gradient = dY operand of the next (earlier) sub-layer
+                    uint2 t2;
+                    t2.x = pack_bf16x2(gv.x, gv.y), t2.y = pack_bf16x2(gv.z, gv.w);
+                    *reinterpret_cast<uint2*>(gb_out + (long)row * D + c) = t2;
+                }
+                if (gsum) ag[gidx][0] += gv.x, ag[gidx][1] += gv.y, ag[gidx][2] += gv.z, ag[gidx][3] += gv.w;
             }
         }
     }
@@ -102,6 +109,7 @@ __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restric
             for (int i = 0; i < 4; ++i) {
                 atomicAdd(&sred[c + i], aw[gidx][i]);
                 if (is_ln) atomicAdd(&sred[D + c + i], ab[gidx][i]);
+                if (gsum) atomicAdd(&sred[2 * D + c + i], ag[gidx][i]);
             }
         }
     }
@@ -111,6 +119,9 @@ __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restric
         if (is_ln && db)
             atomicAdd(reinterpret_cast<float4*>(db + i),
                       make_float4(sred[D + i], sred[D + i + 1], sred[D + i + 2], sred[D + i + 3]));
+        if (gsum)
+            atomicAdd(reinterpret_cast<float4*>(gsum + i),
+                      make_float4(sred[2 * D + i], sred[2 * D + i + 1], sred[2 * D + i + 2], sred[2 * D + i + 3]));
     }
 }
 
@@ -358,7 +369,8 @@ __global__ void strip_prefix_kernel(const float* __restrict__ g, __nv_bfloat16* 
 using namespace vtp;
 
 extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const float* mean, const float* w, const void* dy,
-                            float* g, float* dw, float* db, int M, int D, int is_ln, vtp_stream_t st) {
+                            float* g, float* dw, float* db, int M, int D, int is_ln, void* g_bf16_out, float* g_colsum,
+                            vtp_stream_t st) {
     VTP_CHECK_ARG(x && rstd && w && dy && g && dw && M > 0, "norm_bwd: bad args");
     VTP_CHECK_ARG(D % 4 == 0 && D <= 2048, "norm_bwd: D %% 4 == 0 and D <= 2048");
     VTP_CHECK_ARG(!is_ln || mean, "norm_bwd: LayerNorm needs mean");
@@ -366,11 +378,12 @@ extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const
                   "norm_bwd: dw/db must be 16B aligned");
     const int threads = D <= 512 ? 512 : 256, rows_per_block = 128;  // register budget of the wider variants
     const int grid = ceil_div(M, rows_per_block);
-    const size_t smem = 2 * (size_t)D * sizeof(float);
+    VTP_CHECK_ARG(!g_colsum || (reinterpret_cast<uintptr_t>(g_colsum) & 15) == 0, "norm_bwd: g_colsum must be 16B aligned");
+    const size_t smem = 3 * (size_t)D * sizeof(float);
     cudaStream_t s = (cudaStream_t)st;
     const int xr = (x_dtype == VTP_BF16 && !is_ln) ? 1 : 0;  // RMSNorm .type_as(x) rounding of xhat
 #define LB(T, MV) \
-    norm_bwd_kernel<T, MV><<<grid, threads, smem, s>>>((const T*)x, rstd, mean, w, (const __nv_bfloat16*)dy, g, dw, db, M, D, rows_per_block, is_ln, xr)
+    norm_bwd_kernel<T, MV><<<grid, threads, smem, s>>>((const T*)x, rstd, mean, w, (const __nv_bfloat16*)dy, g, dw, db, M, D, rows_per_block, is_ln, xr, (__nv_bfloat16*)g_bf16_out, g_colsum)
     if (x_dtype == VTP_F32) {
         if (D <= 512) LB(float, 4);
         else if (D <= 1024) LB(float, 8);

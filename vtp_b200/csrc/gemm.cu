@@ -11,6 +11,8 @@
 // Fused epilogues (all optional): +bias, bf16 rounding point, GELU, SwiGLU gate (8-interleaved w1|w2), axial
 // RoPE on q/k (bf16 arithmetic exactly as layers/attention.py:12-23,70-89), +residual, row remap (cls-token
 // slot), PixelShuffle NCHW store, secondary pre-activation output.
+#include <stdlib.h>
+
 #include "host.h"
 #include "ptx.cuh"
 
@@ -342,7 +344,10 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
     }
 }
 
-template <int BN, int STAGES, int ACT, bool PS>
+// CL2: the CTA pair of a 2-CTA cluster works on two vertically adjacent tiles (same n-block): each CTA loads its own A
+// tile and HALF of the shared B tile, multicast to both — 25-33 % less L2->SMEM traffic, which is what caps this kernel
+// (128x128x64 tiles at 32 KB per k-block = 64 flop/B against ~12 TB/s of L2 is ~0.8 PFLOP/s).
+template <int BN, int STAGES, int ACT, bool PS, bool CL2>
 // 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
@@ -361,11 +366,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
+    const int work_id = CL2 ? (blockIdx.x >> 1) : blockIdx.x;      // CTA pairs share a work item (tile pair)
+    const int work_stride = CL2 ? (gridDim.x >> 1) : gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], CL2 ? 2 : 1);
         for (int s = 0; s < 2; ++s) mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], NUM_EPI_WARPS);
         fence_barrier_init();
     }
@@ -375,9 +383,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     tc_fence_before();
     __syncthreads();
+    if (CL2) cluster_sync_all();  // peer barriers are initialised before anything is multicast into this CTA
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // in CL2 mode num_m_blocks counts tile PAIRS; this CTA's m-block is 2*pair + rank
     const int tiles_mn = p.num_m_blocks * p.num_n_blocks;
     const int num_tiles = tiles_mn * p.num_splits;
 
@@ -386,9 +396,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = work_id; t < num_tiles; t += work_stride) {
                 const int n_blk = t % p.num_n_blocks;
-                const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
+                const int m_blk = ((t / p.num_n_blocks) % p.num_m_blocks) * (CL2 ? 2 : 1) + (int)crank;
                 const int ks = t / tiles_mn;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -411,7 +421,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
                         tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
                     }
-                    if (!p.b_mn) {
+                    if (CL2) {  // my half of B, delivered to both CTAs of the pair
+                        if (!p.b_mn) {
+                            tma_load_2d_mc(sb + crank * (BN / 2) * 128, &tmB, &full_bar[s], k0, n0 + (int)crank * (BN / 2), 3);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BN / 64; ++i)
+                                if ((i & 1) == (int)crank)
+                                    tma_load_2d_mc(sb + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, k0, 3);
+                        }
+                    } else if (!p.b_mn) {
                         tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
                     } else {
 #pragma unroll
@@ -430,7 +449,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = work_id; t < num_tiles; t += work_stride) {
                 const int ks = t / tiles_mn;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -450,7 +469,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                                    : umma_desc_sw128(b_base + j * 32, 0, 1024);
                         umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
                     }
-                    umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+                    // frees the smem slot once these MMAs have read it (in both CTAs: the peer multicasts into mine)
+                    if (CL2) umma_commit_mc(&empty_bar[s], 3);
+                    else umma_commit(&empty_bar[s]);
                     if (++s == STAGES) s = 0, ph ^= 1;
                 }
                 umma_commit(&tfull_bar[as]);  // accumulator complete
@@ -465,9 +486,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const bool has_resid = p.resid != nullptr;
         int as = 0;
         uint32_t aph = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        for (int t = work_id; t < num_tiles; t += work_stride) {
             const int n_blk = t % p.num_n_blocks;
-            const int m_blk = (t / p.num_n_blocks) % p.num_m_blocks;
+            const int m_blk = ((t / p.num_n_blocks) % p.num_m_blocks) * (CL2 ? 2 : 1) + (int)crank;
             const int m0 = m_blk * BM, n0 = n_blk * BN;
             const int grow0 = m0 + q * 32;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
@@ -514,24 +535,39 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
     tc_fence_before();
     __syncthreads();
+    if (CL2) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-template <int BN, int STAGES, int ACT, bool PS>
+template <int BN, int STAGES, int ACT, bool PS, bool CL2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream) {
     constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      smem_bytes));
         configured = true;
     }
-    const int tiles = p.num_m_blocks * p.num_n_blocks * p.num_splits;
-    const int grid = tiles < num_sms() ? tiles : num_sms();
-    gemm_kernel<BN, STAGES, ACT, PS><<<grid, NUM_THREADS, smem_bytes, stream>>>(tmA, tmB, p);
-    VTP_LAUNCH_CHECK();
+    const int work = p.num_m_blocks * p.num_n_blocks * p.num_splits;  // tiles, or tile pairs in CL2 mode
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchAttribute attr[1];
+    if (CL2) {
+        const int pairs = num_sms() / 2;
+        cfg.gridDim = dim3(2 * (work < pairs ? work : pairs));
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr, cfg.numAttrs = 1;
+    } else {
+        cfg.gridDim = dim3(work < num_sms() ? work : num_sms());
+    }
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2>, tmA, tmB, p));
     return VTP_OK;
 }
 
@@ -596,6 +632,10 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2), p.ldo2 = a->ldo2;
     p.mask_pos = reinterpret_cast<const __nv_bfloat16*>(a->mask_pos), p.ldm = a->ldm;
 
+    // 2-CTA multicast variant whenever there are at least two m-blocks (odd counts are padded with an all-OOB tile)
+    static const bool allow_cl2 = getenv("VTP_GEMM_NO_CLUSTER") == nullptr;
+    const bool cl2 = allow_cl2 && !conv && ceil_div(a->M, BM) >= 2;
+
     CUtensorMap tmA, tmB;
     if (conv) {
         const int W = a->conv_W, H = a->conv_H, Cc = a->conv_C, Bimg = a->M / (H * W);
@@ -621,14 +661,21 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     {
         uint64_t dims[2], strides[1] = {(uint64_t)a->ldb * 2};
         uint32_t box[2];
-        if (!p.b_mn) dims[0] = a->K, dims[1] = a->N, box[0] = 64, box[1] = (uint32_t)BN;
+        if (!p.b_mn) dims[0] = a->K, dims[1] = a->N, box[0] = 64, box[1] = (uint32_t)(cl2 ? BN / 2 : BN);
         else dims[0] = a->N, dims[1] = a->K, box[0] = 64, box[1] = 64;
         int rc = make_tmap_bf16(&tmB, a->B, 2, dims, strides, box);
         if (rc) return rc;
     }
+    if (cl2) p.num_m_blocks = ceil_div(p.num_m_blocks, 2);  // tile pairs
     // one instantiation per epilogue family keeps each kernel's code (and register pressure) small
-#define VTP_LAUNCH(ACT_, PS_) \
-    return (BN == 256) ? launch_gemm<256, 4, ACT_, PS_>(tmA, tmB, p, stream) : launch_gemm<128, 6, ACT_, PS_>(tmA, tmB, p, stream)
+#define VTP_LAUNCH(ACT_, PS_)                                                                                          \
+    do {                                                                                                              \
+        if (cl2)                                                                                                      \
+            return (BN == 256) ? launch_gemm<256, 4, ACT_, PS_, true>(tmA, tmB, p, stream)                            \
+                               : launch_gemm<128, 6, ACT_, PS_, true>(tmA, tmB, p, stream);                           \
+        return (BN == 256) ? launch_gemm<256, 4, ACT_, PS_, false>(tmA, tmB, p, stream)                               \
+                           : launch_gemm<128, 6, ACT_, PS_, false>(tmA, tmB, p, stream);                              \
+    } while (0)
     if (a->ps_r > 0) {
         VTP_CHECK_ARG(a->act == VTP_ACT_NONE, "gemm: pixel shuffle has no activation");
         VTP_LAUNCH(VTP_ACT_NONE, true);

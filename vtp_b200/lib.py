@@ -70,7 +70,7 @@ SIGNATURES: dict[str, tuple] = {
     "vtp_attention_fwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vtp_attention_bwd": (C.c_int, [C.c_void_p] * 7 + [C.c_int] * 5 + [C.c_void_p]),
     "vtp_norm_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+                               C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vtp_swiglu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vtp_gelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "vtp_cast_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -260,9 +260,9 @@ def attention_bwd(qkv, o, dout, lse, dqkv, B: int, T: int, H: int, *, prefix: in
                                    prefix, int(causal), _st(stream)), "vtp_attention_bwd")
 
 
-def norm_bwd(x, rstd, mean, w, dy, g, dw, db, M: int, D: int, stream=None):
+def norm_bwd(x, rstd, mean, w, dy, g, dw, db, M: int, D: int, gb_out=None, g_colsum=None, stream=None):
     check(load().vtp_norm_bwd(_ptr(x), _dt(x), _ptr(rstd), _ptr(mean), _ptr(w), _ptr(dy), _ptr(g), _ptr(dw), _ptr(db), M, D,
-                              int(mean is not None), _st(stream)), "vtp_norm_bwd")
+                              int(mean is not None), _ptr(gb_out), _ptr(g_colsum), _st(stream)), "vtp_norm_bwd")
 
 
 def swiglu_bwd(pre, dhid, dpre, dbias, M: int, Hs: int, stream=None):

@@ -142,15 +142,18 @@ def dgrad(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor, Mtok: int, **kw)
 
 
 def tower_blocks_backward(W: TowerW, G: TowerW, tape: list, g: torch.Tensor, B: int, T: int, rope, causal=False):
-    """Reverse of engine.tower_blocks.  g fp32 [B*T, D]: in = dL/d(stream out), out = dL/d(stream in) (in place)."""
+    """Reverse of engine.tower_blocks.  g fp32 [B*T, D]: in = dL/d(stream out), out = dL/d(stream in) (in place).
+    The bf16 copy of g (dY operand of the next sub-layer to differentiate) and its column sums (that sub-layer's bias
+    gradient) are by-products of the preceding norm_bwd; only the first sub-layer needs a stand-alone cast."""
     dev = g.device
     M, D, H = B * T, W.D, W.heads
     gb = _e((M, D), BF, dev)
-    for li in reversed(range(len(W.blocks))):
+    nb = len(W.blocks)
+    lib.cast_colsum(g, gb, G.blocks[nb - 1].fc2.b, M, D)
+    for li in reversed(range(nb)):
         bw, gw, t = W.blocks[li], G.blocks[li], tape[li]
         Hd = bw.hidden
-        # ---- FFN sub-layer
-        lib.cast_colsum(g, gb, gw.fc2.b, M, D)
+        # ---- FFN sub-layer (gb / fc2 bias gradient already produced)
         dhid = _e((M, Hd), BF, dev)
         dgrad(gb, bw.fc2.w, dhid, M)
         wgrad(gb, t["hid"], gw.fc2.w, M)
@@ -162,9 +165,9 @@ def tower_blocks_backward(W: TowerW, G: TowerW, tape: list, g: torch.Tensor, B: 
         dh = _e((M, D), BF, dev)
         dgrad(dpre, bw.fc1.w, dh, M)
         wgrad(dpre, t["h2"], gw.fc1.w, M)
-        lib.norm_bwd(t["x_mid"], t["n2"]["rstd"], t["n2"]["mean"], bw.n2_w, dh, g, gw.n2_w, gw.n2_b, M, D)
+        lib.norm_bwd(t["x_mid"], t["n2"]["rstd"], t["n2"]["mean"], bw.n2_w, dh, g, gw.n2_w, gw.n2_b, M, D,
+                     gb_out=gb, g_colsum=gw.proj.b)
         # ---- attention sub-layer
-        lib.cast_colsum(g, gb, gw.proj.b, M, D)
         do = _e((M, D), BF, dev)
         dgrad(gb, bw.proj.w, do, M)
         wgrad(gb, t["o"], gw.proj.w, M)
@@ -173,7 +176,9 @@ def tower_blocks_backward(W: TowerW, G: TowerW, tape: list, g: torch.Tensor, B: 
         lib.cast_colsum(dqkv, None, gw.qkv.b, M, 3 * D)
         dgrad(dqkv, bw.qkv.w, dh, M)
         wgrad(dqkv, t["h1"], gw.qkv.w, M)
-        lib.norm_bwd(t["x_in"], t["n1"]["rstd"], t["n1"]["mean"], bw.n1_w, dh, g, gw.n1_w, gw.n1_b, M, D)
+        nxt = G.blocks[li - 1].fc2.b if li > 0 else None
+        lib.norm_bwd(t["x_in"], t["n1"]["rstd"], t["n1"]["mean"], bw.n1_w, dh, g, gw.n1_w, gw.n1_b, M, D,
+                     gb_out=gb if li > 0 else None, g_colsum=nxt)
         tape[li] = None  # free the saved activations of this block
     return g
 
