@@ -347,9 +347,10 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
 // CL2: the CTA pair of a 2-CTA cluster works on two vertically adjacent tiles (same n-block): each CTA loads its own A
 // tile and HALF of the shared B tile, multicast to both — 25-33 % less L2->SMEM traffic, which is what caps this kernel
 // (128x128x64 tiles at 32 KB per k-block = 64 flop/B against ~12 TB/s of L2 is ~0.8 PFLOP/s).
-template <int BN, int STAGES, int ACT, bool PS, bool CL2>
-// 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB>
+// 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168 (MINB = 1).
+// MINB = 2 (short-K shapes): two CTAs per SM with a 2-stage ring double the epilogue warps per SM at ~100 registers.
+__global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -542,12 +543,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
-template <int BN, int STAGES, int ACT, bool PS, bool CL2>
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream) {
     constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 + 1024 + 256;
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       smem_bytes));
         configured = true;
     }
@@ -556,18 +557,18 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];
     if (CL2) {
-        const int pairs = num_sms() / 2;
+        const int pairs = MINB * num_sms() / 2;
         cfg.gridDim = dim3(2 * (work < pairs ? work : pairs));
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
     } else {
-        cfg.gridDim = dim3(work < num_sms() ? work : num_sms());
+        cfg.gridDim = dim3(work < MINB * num_sms() ? work : MINB * num_sms());
     }
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2>, tmA, tmB, p));
+    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB>, tmA, tmB, p));
     return VTP_OK;
 }
 
@@ -668,13 +669,20 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     }
     if (cl2) p.num_m_blocks = ceil_div(p.num_m_blocks, 2);  // tile pairs
     // one instantiation per epilogue family keeps each kernel's code (and register pressure) small
+    // short reductions (<= 8 k-blocks) with 128-wide tiles are epilogue/latency bound: run two CTAs per SM
+    static const bool allow_2cta = getenv("VTP_GEMM_NO_2PERSM") == nullptr;
+    const bool two = allow_2cta && BN == 128 && p.num_k_blocks <= 8 && p.num_splits == 1;
 #define VTP_LAUNCH(ACT_, PS_)                                                                                          \
     do {                                                                                                              \
+        if (two) {                                                                                                    \
+            if (cl2) return launch_gemm<128, 2, ACT_, PS_, true, 2>(tmA, tmB, p, stream);                             \
+            return launch_gemm<128, 2, ACT_, PS_, false, 2>(tmA, tmB, p, stream);                                     \
+        }                                                                                                             \
         if (cl2)                                                                                                      \
-            return (BN == 256) ? launch_gemm<256, 4, ACT_, PS_, true>(tmA, tmB, p, stream)                            \
-                               : launch_gemm<128, 6, ACT_, PS_, true>(tmA, tmB, p, stream);                           \
-        return (BN == 256) ? launch_gemm<256, 4, ACT_, PS_, false>(tmA, tmB, p, stream)                               \
-                           : launch_gemm<128, 6, ACT_, PS_, false>(tmA, tmB, p, stream);                              \
+            return (BN == 256) ? launch_gemm<256, 4, ACT_, PS_, true, 1>(tmA, tmB, p, stream)                         \
+                               : launch_gemm<128, 6, ACT_, PS_, true, 1>(tmA, tmB, p, stream);                        \
+        return (BN == 256) ? launch_gemm<256, 4, ACT_, PS_, false, 1>(tmA, tmB, p, stream)                            \
+                           : launch_gemm<128, 6, ACT_, PS_, false, 1>(tmA, tmB, p, stream);                           \
     } while (0)
     if (a->ps_r > 0) {
         VTP_CHECK_ARG(a->act == VTP_ACT_NONE, "gemm: pixel shuffle has no activation");
