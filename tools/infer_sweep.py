@@ -1,0 +1,54 @@
+"""Config 5 of BASELINE.json: encode+decode inference throughput sweep (bf16 autocast mode) + optional parity check of
+the fp32 mode against the CPU oracle at batch 1.  GPU only.
+  python tools/infer_sweep.py --model large --batches 1,8,64,256 [--check]"""
+import argparse
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from vtp_b200.config import preset
+from vtp_b200.flops import encode_decode_flops
+from vtp_b200.model import VTPModel
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--model", default="large")
+ap.add_argument("--batches", default="1,8,64,256")
+ap.add_argument("--check", action="store_true")
+a = ap.parse_args()
+cfg = preset(a.model)
+torch.manual_seed(0)
+m = VTPModel(cfg).cuda()
+fl = encode_decode_flops(cfg)
+out = {"model": a.model, "gflop_per_image": fl / 1e9, "rows": []}
+for B in [int(b) for b in a.batches.split(",")]:
+    x = torch.randn(B, 3, 256, 256, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        for _ in range(3):
+            rec = m.get_latents_decoded_images(m.get_reconstruction_latents(x))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10 if B >= 8 else 30
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            rec = m.get_latents_decoded_images(m.get_reconstruction_latents(x))
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out["rows"].append({"batch": B, "ms": ms, "img_per_s": B / ms * 1e3, "tflops": fl * B / ms / 1e9})
+    print(f"{a.model} B={B:4d}: {ms:8.2f} ms  {B / ms * 1e3:9.1f} img/s  {fl * B / ms / 1e9:7.1f} TFLOP/s", flush=True)
+if a.check:
+    from oracle import vtp_oracle as vo
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    x = torch.randn(1, 3, 256, 256)
+    with torch.no_grad():
+        lat_o = vo.reconstruction_latents(x, sd, depth=cfg.vision_depth, heads=cfg.vision_num_heads)
+        rec_o = vo.decode_latents(lat_o, sd, depth=cfg.decoder_depth, heads=cfg.decoder_num_heads)
+    lat = m.get_reconstruction_latents(x.cuda())
+    rec = m.get_latents_decoded_images(lat)
+    rel = lambda p, q: float((p.float().cpu() - q).norm() / q.norm())
+    out["check_fp32_mode_vs_oracle"] = {"latents": rel(lat, lat_o), "recon": rel(rec, rec_o)}
+    print("fp32-mode vs CPU oracle:", out["check_fp32_mode_vs_oracle"], flush=True)
+print(json.dumps(out))

@@ -610,7 +610,10 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     if (a->mask_pos) VTP_CHECK_ARG(a->out_dtype == VTP_BF16 && a->ldm % 8 == 0, "gemm: mask_pos needs bf16 out");
     // tile-N choice: minimise padded N, ties -> 256 (lower smem bandwidth per MMA)
     const int pad128 = ceil_div(a->N, 128) * 128, pad256 = ceil_div(a->N, 256) * 256;
-    const int BN = (pad256 * 8 <= pad128 * 9) ? 256 : 128;  // accept <= 12.5 % padding for the higher-intensity tile
+    int BN = (pad256 * 8 <= pad128 * 9) ? 256 : 128;  // accept <= 12.5 % padding for the higher-intensity tile
+    static const int two_max_kb = getenv("VTP_GEMM_2PERSM_MAXKB") ? atoi(getenv("VTP_GEMM_2PERSM_MAXKB")) : 16;
+    static const bool short_bn128 = getenv("VTP_GEMM_SHORTK_BN128") != nullptr;
+    if (short_bn128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1 && a->conv_C == 0) BN = 128;
 
     GemmDev p;
     memset(&p, 0, sizeof(p));
@@ -669,9 +672,10 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     }
     if (cl2) p.num_m_blocks = ceil_div(p.num_m_blocks, 2);  // tile pairs
     // one instantiation per epilogue family keeps each kernel's code (and register pressure) small
-    // short reductions (<= 8 k-blocks) with 128-wide tiles are epilogue/latency bound: run two CTAs per SM
+    // short reductions (<= 16 k-blocks) with 128-wide tiles are epilogue/latency bound: run two CTAs per SM
+    // (measured: proj+resid 237 -> 178 us, fc2+resid 244 -> 198 us at M = 131 584)
     static const bool allow_2cta = getenv("VTP_GEMM_NO_2PERSM") == nullptr;
-    const bool two = allow_2cta && BN == 128 && p.num_k_blocks <= 8 && p.num_splits == 1;
+    const bool two = allow_2cta && BN == 128 && p.num_k_blocks <= two_max_kb && p.num_splits == 1;
 #define VTP_LAUNCH(ACT_, PS_)                                                                                          \
     do {                                                                                                              \
         if (two) {                                                                                                    \

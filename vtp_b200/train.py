@@ -257,9 +257,6 @@ class VTPTrainer:
         self.head_wn = _e((K, hb), BF, self.device)       # weight-normed last layer (student), rebuilt every step
         self.head_wn_t = _e((K, hb), BF, self.device)     # teacher
         self.head_vnorm = _e((K,), F32, self.device)
-        self.periods = E.rope_sincos  # table builder; periods are constants (layers/embeddings.py:182-195)
-        from .rope import rope_periods
-        self._periods_v = rope_periods(64)
         self.reset_parameters()
 
     def enable_lpips(self, module=None, seed: int = 0, chunk: int = 32):
