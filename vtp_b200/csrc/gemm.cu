@@ -45,6 +45,7 @@ struct GemmDev {
     int conv_C, conv_H, conv_W, conv_TW, conv_TH, conv_tiles_h, conv_tiles_w;
     const __nv_bfloat16* mask_pos;  // optional: out *= (mask_pos[row][col] > 0)   (ReLU backward in the dgrad epilogue)
     int ldm;
+    int dbg;  // DIAG bits: 1 no global stores, 2 no tmem ld, 4 no epilogue work, 8 no MMA issue
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
@@ -126,6 +127,7 @@ __device__ __forceinline__ void store_bf16(const GemmDev& p, const uint8_t* stg,
         const int R = 4 * it + (lane >> 3);
         const long orow = orow8[it];
         if (orow < 0 || !col_ok) continue;
+        if (p.dbg & 1) continue;
         uint4 w = *reinterpret_cast<const uint4*>(stg + stgb_off(R, cidx));
         if (has_resid && which == 0) {
             const uint4 rb = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.resid) + orow * p.ldr + ocol0 + c8);
@@ -159,6 +161,7 @@ __device__ __forceinline__ void store_half(const GemmDev& p, const float* stg, i
         const int grow = grow0 + R;
         const long orow = orow8[it];
         if (orow < 0 || !col_ok) continue;
+        if (p.dbg & 1) continue;
         float4 v = *reinterpret_cast<const float4*>(stg + stg_off(R, cidx));
         if (which == 1) {
             uint2 w;
@@ -344,22 +347,159 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------- fast epilogue
+// The recurring shapes of the training step (qkv / proj / fc1 / fc2 forward, every dgrad) need only bias, a bf16
+// rounding point, an optional residual of the output's own dtype and a store.  The generic epilogue above spends
+// ~550 instructions per 64-column unit (address math, feature branches, staging read-back), misses the instruction
+// cache and waits on its bias loads: short-K GEMMs ran at a third of what the mainloop sustains (profiles/
+// ncu_gemm_fc1_r1b.md).  This path: lane == accumulator row; one 128-byte output row piece per lane is written into a
+// 4 KB SWIZZLE_128B staging tile and leaves through ONE TMA store (clipped at the M / N tails by the tensor map);
+// bias comes from a 256-byte per-warp shared tile (broadcast reads), the residual is fetched into registers one chunk
+// ahead, before the accumulator is waited for.
+//   FAST: 1 bf16 out, 2 bf16 out + bf16 residual, 3 fp32 out, 4 fp32 out + fp32 residual.   ACT: NONE | RELU.
+template <int BN, int ACT, int FAST>
+__device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUtensorMap* tmO, uint8_t* stg, float* bias_s,
+                                                   int lane, int q, int hsel, uint32_t taddr, int m0, int n0,
+                                                   uint64_t* tfull, uint32_t aph, uint64_t* tempty) {
+    constexpr bool OF32 = FAST >= 3;
+    constexpr bool RES = FAST == 2 || FAST == 4;
+    constexpr int CW = OF32 ? 32 : 64;   // accumulator columns per 128-byte output chunk
+    constexpr int NCH = BN / CW / 2;     // chunks per warp and tile (the two warps of a lane quarter interleave)
+    constexpr int PW = OF32 ? 4 : 8;     // columns per 16-byte piece
+    const int N = p.N;
+    const long row = (long)m0 + q * 32 + lane;
+    const bool row_ok = row < p.M;
+    const char* rrow = RES ? reinterpret_cast<const char*>(p.resid) + row * (long)p.ldr * (OF32 ? 4 : 2) : nullptr;
+
+    float b0n = 0.f, b1n = 0.f;
+    uint4 rr[8];
+    auto load_bias = [&](int col0) {
+        if (p.bias) {
+            b0n = (col0 + lane < N) ? __ldg(p.bias + col0 + lane) : 0.f;
+            if (!OF32) b1n = (col0 + 32 + lane < N) ? __ldg(p.bias + col0 + 32 + lane) : 0.f;
+        }
+    };
+    auto load_resid = [&](int col0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int col = col0 + PW * i;
+            rr[i] = (row_ok && col + PW <= N) ? *reinterpret_cast<const uint4*>(rrow + (long)col * (OF32 ? 4 : 2))
+                                              : make_uint4(0, 0, 0, 0);
+        }
+    };
+    bool waited = false;
+    if (n0 + hsel * CW < N) {
+        load_bias(n0 + hsel * CW);
+        if (RES) {
+            load_resid(n0 + hsel * CW);  // first chunk: in registers before the accumulator is waited for
+#pragma unroll
+            for (int j = 1; j < NCH; ++j) {  // later chunks: warm this lane's 128-byte row piece in L2
+                const int col = n0 + (hsel + 2 * j) * CW;
+                if (row_ok && col < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + (long)col * (OF32 ? 4 : 2)));
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+        const int c = hsel + 2 * j;
+        const int col0 = n0 + c * CW;
+        if (col0 >= N) break;  // warp-uniform
+        const bool last = (j == NCH - 1) || (col0 + 2 * CW >= N);
+        const float b0 = b0n, b1 = b1n;
+        if (!last) load_bias(col0 + 2 * CW);
+        if (!waited) {
+            mbar_wait(tfull, aph);
+            tc_fence_after();
+            waited = true;
+        }
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(taddr + c * CW, r0);
+        if (!OF32) tmem_ld_32x32(taddr + c * CW + 32, r1);
+        bias_s[lane] = b0;
+        if (!OF32) bias_s[32 + lane] = b1;
+        if (lane == 0) bulk_wait_read0();  // the previous TMA store has finished reading the staging tile
+        __syncwarp();
+        tmem_ld_wait();
+        if (last) {  // accumulator fully in registers: hand the TMEM buffer back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty);
+        }
+        if (!(p.dbg & 4)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if constexpr (OF32) {
+                    const float4 b = *reinterpret_cast<const float4*>(bias_s + 4 * i);
+                    float4 v = make_float4(__uint_as_float(r0[4 * i]) + b.x, __uint_as_float(r0[4 * i + 1]) + b.y,
+                                           __uint_as_float(r0[4 * i + 2]) + b.z, __uint_as_float(r0[4 * i + 3]) + b.w);
+                    if (p.round_bf16) v.x = bf16_round(v.x), v.y = bf16_round(v.y), v.z = bf16_round(v.z), v.w = bf16_round(v.w);
+                    if (ACT == VTP_ACT_RELU) v.x = fmaxf(v.x, 0.f), v.y = fmaxf(v.y, 0.f), v.z = fmaxf(v.z, 0.f), v.w = fmaxf(v.w, 0.f);
+                    if (RES)
+                        v.x += __uint_as_float(rr[i].x), v.y += __uint_as_float(rr[i].y), v.z += __uint_as_float(rr[i].z),
+                            v.w += __uint_as_float(rr[i].w);
+                    *reinterpret_cast<float4*>(stg + stgb_off(lane, i)) = v;
+                } else {
+                    const float4 ba = *reinterpret_cast<const float4*>(bias_s + 8 * i);
+                    const float4 bb = *reinterpret_cast<const float4*>(bias_s + 8 * i + 4);
+                    const uint32_t* r = i < 4 ? r0 + 8 * i : r1 + 8 * (i - 4);
+                    float v[8] = {__uint_as_float(r[0]) + ba.x, __uint_as_float(r[1]) + ba.y, __uint_as_float(r[2]) + ba.z,
+                                  __uint_as_float(r[3]) + ba.w, __uint_as_float(r[4]) + bb.x, __uint_as_float(r[5]) + bb.y,
+                                  __uint_as_float(r[6]) + bb.z, __uint_as_float(r[7]) + bb.w};
+                    if (ACT == VTP_ACT_RELU) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = fmaxf(v[k], 0.f);
+                    }
+                    uint4 w;
+                    w.x = pack_bf16x2(v[0], v[1]), w.y = pack_bf16x2(v[2], v[3]);
+                    w.z = pack_bf16x2(v[4], v[5]), w.w = pack_bf16x2(v[6], v[7]);
+                    if (RES)
+                        w.x = add_bf16x2(w.x, rr[i].x), w.y = add_bf16x2(w.y, rr[i].y), w.z = add_bf16x2(w.z, rr[i].z),
+                        w.w = add_bf16x2(w.w, rr[i].w);
+                    *reinterpret_cast<uint4*>(stg + stgb_off(lane, i)) = w;
+                }
+            }
+            if (RES && !last) load_resid(col0 + 2 * CW);  // in flight across the store and the next TMEM read
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 1)) {
+                tma_store_2d(tmO, stg, col0, m0 + q * 32);
+                bulk_commit();
+            }
+        }
+    }
+    if (!waited) {  // no chunk of this warp inside N: still consume the phase
+        mbar_wait(tfull, aph);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(tempty);
+    }
+}
+
 // CL2: the CTA pair of a 2-CTA cluster works on two vertically adjacent tiles (same n-block): each CTA loads its own A
 // tile and HALF of the shared B tile, multicast to both — 25-33 % less L2->SMEM traffic, which is what caps this kernel
 // (128x128x64 tiles at 32 KB per k-block = 64 flop/B against ~12 TB/s of L2 is ~0.8 PFLOP/s).
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB>
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST>
 // 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168 (MINB = 1).
 // MINB = 2 (short-K shapes): two CTAs per SM with a 2-stage ring double the epilogue warps per SM at ~100 registers.
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
-gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmDev p) {
+gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ CUtensorMap tmO, const GemmDev p) {
     constexpr int B_BYTES = BN * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
 
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // FAST kernels use every byte (ring + staging + bias tiles + barriers = 226 KB at BN = 256): they rely on the declared
+    // 1024-byte alignment of the dynamic segment (checked below) instead of carrying a 1 KB alignment pad
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = FAST ? smem_raw
+                         : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    if (FAST && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
     float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // 8 epilogue warps x 4 KB
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_FLOATS * 4);
+    float* bias_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_FLOATS * 4);  // FAST only
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_FLOATS * 4 +
+                                                     (FAST ? NUM_EPI_WARPS * 256 : 0));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -374,6 +514,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
+        if (FAST) tma_prefetch_desc(&tmO);
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], CL2 ? 2 : 1);
         for (int s = 0; s < 2; ++s) mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], NUM_EPI_WARPS);
         fence_barrier_init();
@@ -468,7 +609,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                                    : umma_desc_sw128(a_base + j * 32, 0, 1024);
                         const uint64_t bd = p.b_mn ? umma_desc_sw128(b_base + j * 2048, 8192, 1024)
                                                    : umma_desc_sw128(b_base + j * 32, 0, 1024);
-                        umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                        if (!(p.dbg & 8)) umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
                     }
                     // frees the smem slot once these MMAs have read it (in both CTAs: the peer multicasts into mine)
                     if (CL2) umma_commit_mc(&empty_bar[s], 3);
@@ -493,6 +634,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int m0 = m_blk * BM, n0 = n_blk * BN;
             const int grow0 = m0 + q * 32;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+            if constexpr (FAST != 0) {
+                fast_epilogue_tile<BN, ACT, FAST>(p, &tmO, reinterpret_cast<uint8_t*>(stg), bias_base + (warp - 2) * 64, lane,
+                                                  q, hsel, taddr, m0, n0, &tfull_bar[as], aph, &tempty_bar[as]);
+                if (++as == 2) as = 0, aph ^= 1;
+                continue;
+            }
             bool waited = false;
             constexpr bool sw = ACT == VTP_ACT_SWIGLU8;
             long orow8[8];  // output rows of the cooperative store pattern (row 4*it + lane/8 of this warp's slab)
@@ -514,10 +661,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     tc_fence_after();
                     waited = true;
                 }
+                if (p.dbg & 4) continue;
                 uint32_t r0[32], r1[32];
-                tmem_ld_32x32(taddr + u * 64, r0);
-                tmem_ld_32x32(taddr + u * 64 + 32, r1);
-                tmem_ld_wait();
+                if (!(p.dbg & 2)) {
+                    tmem_ld_32x32(taddr + u * 64, r0);
+                    tmem_ld_32x32(taddr + u * 64 + 32, r1);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r0[i] = r1[i] = 0;
+                }
                 float v[64];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r0[i]), v[32 + i] = __uint_as_float(r1[i]);
@@ -534,6 +687,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     }
 
+    if (FAST && warp >= 2 && lane == 0) bulk_wait0();  // outstanding TMA stores of this warp
     tc_fence_before();
     __syncthreads();
     if (CL2) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on its barriers
@@ -543,13 +697,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB>
-static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream) {
-    constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 + 1024 + 256;
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0>
+static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream,
+                       const CUtensorMap* tmO = nullptr) {
+    constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 +
+                               (FAST ? NUM_EPI_WARPS * 256 + 256 : 1024 + 256);
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      smem_bytes));
+        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
     const int work = p.num_m_blocks * p.num_n_blocks * p.num_splits;  // tiles, or tile pairs in CL2 mode
@@ -568,7 +724,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB>, tmA, tmB, p));
+    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST>, tmA, tmB, tmO ? *tmO : tmA, p));
     return VTP_OK;
 }
 
@@ -611,8 +767,8 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     // tile-N choice: minimise padded N, ties -> 256 (lower smem bandwidth per MMA)
     const int pad128 = ceil_div(a->N, 128) * 128, pad256 = ceil_div(a->N, 256) * 256;
     int BN = (pad256 * 8 <= pad128 * 9) ? 256 : 128;  // accept <= 12.5 % padding for the higher-intensity tile
-    static const int two_max_kb = getenv("VTP_GEMM_2PERSM_MAXKB") ? atoi(getenv("VTP_GEMM_2PERSM_MAXKB")) : 16;
-    static const bool short_bn128 = getenv("VTP_GEMM_SHORTK_BN128") != nullptr;
+    const int two_max_kb = getenv("VTP_GEMM_2PERSM_MAXKB") ? atoi(getenv("VTP_GEMM_2PERSM_MAXKB")) : 16;
+    const bool short_bn128 = getenv("VTP_GEMM_SHORTK_BN128") != nullptr;
     if (short_bn128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1 && a->conv_C == 0) BN = 128;
 
     GemmDev p;
@@ -635,9 +791,10 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     p.ps_r = a->ps_r, p.ps_gh = a->ps_gh, p.ps_gw = a->ps_gw, p.ps_cout = a->ps_cout;
     p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2), p.ldo2 = a->ldo2;
     p.mask_pos = reinterpret_cast<const __nv_bfloat16*>(a->mask_pos), p.ldm = a->ldm;
+    p.dbg = getenv("VTP_GEMM_DBG") ? atoi(getenv("VTP_GEMM_DBG")) : 0;
 
     // 2-CTA multicast variant whenever there are at least two m-blocks (odd counts are padded with an all-OOB tile)
-    static const bool allow_cl2 = getenv("VTP_GEMM_NO_CLUSTER") == nullptr;
+    const bool allow_cl2 = getenv("VTP_GEMM_NO_CLUSTER") == nullptr;
     const bool cl2 = allow_cl2 && !conv && ceil_div(a->M, BM) >= 2;
 
     CUtensorMap tmA, tmB;
@@ -674,8 +831,43 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     // one instantiation per epilogue family keeps each kernel's code (and register pressure) small
     // short reductions (<= 16 k-blocks) with 128-wide tiles are epilogue/latency bound: run two CTAs per SM
     // (measured: proj+resid 237 -> 178 us, fc2+resid 244 -> 198 us at M = 131 584)
-    static const bool allow_2cta = getenv("VTP_GEMM_NO_2PERSM") == nullptr;
+    const bool allow_2cta = getenv("VTP_GEMM_NO_2PERSM") == nullptr;
     const bool two = allow_2cta && BN == 128 && p.num_k_blocks <= two_max_kb && p.num_splits == 1;
+    // lean TMA-store epilogue for the recurring shapes (see fast_epilogue_tile)
+    const bool allow_fast = getenv("VTP_GEMM_NO_FAST") == nullptr;
+    const bool fast = allow_fast && !conv && a->rr_group == 0 && a->ps_r == 0 && !a->out2 && !a->mask_pos && !a->accumulate &&
+                      split_k == 1 && (a->act == VTP_ACT_NONE || a->act == VTP_ACT_RELU) &&
+                      (!a->resid || a->resid_dtype == a->out_dtype);
+    if (fast) {
+        CUtensorMap tmO;
+        const int esz = a->out_dtype == VTP_F32 ? 4 : 2;
+        uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldo * esz};
+        uint32_t box[2] = {(uint32_t)(128 / esz), 32};
+        int rc = make_tmap(&tmO, a->out, a->out_dtype, 2, dims, strides, box);
+        if (rc) return rc;
+        const int mode = (a->out_dtype == VTP_F32 ? 3 : 1) + (a->resid ? 1 : 0);
+#define VTP_FAST_CFG(ACT_, MODE_)                                                                                     \
+    do { /* one CTA per SM with the deep ring: measured faster than 2 x (2-stage) once the epilogue is lean */        \
+        if (cl2)                                                                                                      \
+            return (BN == 256) ? launch_gemm<256, 4, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO)          \
+                               : launch_gemm<128, 6, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO);         \
+        return (BN == 256) ? launch_gemm<256, 4, ACT_, false, false, 1, MODE_>(tmA, tmB, p, stream, &tmO)             \
+                           : launch_gemm<128, 6, ACT_, false, false, 1, MODE_>(tmA, tmB, p, stream, &tmO);            \
+    } while (0)
+#define VTP_FAST_ACT(ACT_)                                 \
+    do {                                                   \
+        switch (mode) {                                    \
+            case 1: VTP_FAST_CFG(ACT_, 1);                 \
+            case 2: VTP_FAST_CFG(ACT_, 2);                 \
+            case 3: VTP_FAST_CFG(ACT_, 3);                 \
+            default: VTP_FAST_CFG(ACT_, 4);                \
+        }                                                  \
+    } while (0)
+        if (a->act == VTP_ACT_RELU) VTP_FAST_ACT(VTP_ACT_RELU);
+        VTP_FAST_ACT(VTP_ACT_NONE);
+#undef VTP_FAST_ACT
+#undef VTP_FAST_CFG
+    }
 #define VTP_LAUNCH(ACT_, PS_)                                                                                          \
     do {                                                                                                              \
         if (two) {                                                                                                    \

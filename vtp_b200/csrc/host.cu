@@ -38,6 +38,11 @@ static PFN_tmapEncodeTiled get_encode_fn() {
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box) {
+    return make_tmap(out, base, VTP_BF16, rank, dims, strides_bytes, box);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box) {
     PFN_tmapEncodeTiled fn = get_encode_fn();
     if (!fn) VTP_FAIL(VTP_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
     cuuint64_t gdim[5];
@@ -45,7 +50,7 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
     cuuint32_t bx[5], es[5];
     for (int i = 0; i < rank; ++i) gdim[i] = dims[i], bx[i] = box[i], es[i] = 1;
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+    CUresult r = fn(out, dtype == VTP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)

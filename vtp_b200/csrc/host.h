@@ -38,6 +38,9 @@ int num_sms();
 // box[] in elements. 128B swizzle (box[0]*2 bytes must be 128).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box);
+// same for VTP_F32 | VTP_BF16 elements (box[0] * element size must be 128 bytes)
+int make_tmap(CUtensorMap* out, const void* base, int dtype, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+              const uint32_t* box);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
