@@ -24,7 +24,9 @@ def _rope_ref(x, sin, cos, prefix):  # x [B,T,H,64] float; rotate tokens >= pref
 
 @pytest.mark.parametrize("B,T,H,prefix,causal,rope", [(3, 257, 2, 1, False, True), (2, 256, 3, 0, False, True),
                                                        (4, 37, 2, 1, False, True), (3, 77, 2, 0, True, False),
-                                                       (2, 197, 2, 1, False, True), (16, 257, 6, 1, False, True)])
+                                                       (2, 197, 2, 1, False, True), (16, 257, 6, 1, False, True),
+                                                       (7, 50, 2, 0, False, True), (5, 64, 2, 1, False, True),
+                                                       (50, 37, 6, 1, False, True)])
 def test_attention_bwd(B, T, H, prefix, causal, rope):
     g = torch.Generator(device="cuda").manual_seed(T * 7 + B)
     D, HW = H * 64, T - prefix

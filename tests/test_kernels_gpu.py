@@ -103,7 +103,8 @@ def _sdpa_ref(qkv, B, T, H, causal):
 
 @pytest.mark.parametrize("B,T,H,prefix,causal", [(3, 257, 6, 1, False), (2, 256, 2, 0, False), (5, 37, 6, 1, False),
                                                   (4, 77, 6, 0, True), (2, 197, 12, 1, False), (2, 130, 2, 2, False),
-                                                  (64, 257, 6, 1, False)])
+                                                  (64, 257, 6, 1, False), (7, 50, 2, 0, False), (3, 64, 2, 1, False),
+                                                  (100, 37, 6, 1, False)])
 def test_attention_fwd(B, T, H, prefix, causal):
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T)
     qkv = (torch.randn(B * T, 3 * H * 64, device="cuda", generator=g) * 1.5).to(BF)

@@ -11,6 +11,8 @@
 // The `prefix` (cls / storage) tokens — 1 in the encoder, 0 in the decoder/text — would cost a third 128-row tile for
 // one row, so they are handled on CUDA cores: their key columns are folded into every row's softmax by the row
 // threads, and their query rows are computed by a spare warp from the K/V tiles already in smem.
+#include <stdlib.h>
+
 #include "host.h"
 #include "ptx.cuh"
 
@@ -20,13 +22,15 @@ static constexpr int ATT_THREADS = 192;
 static constexpr int MAX_PREFIX = 4;
 // smem: Q 16K | K 32K | V 32K | P 32K | barriers
 static constexpr int SQ = 0, SK = 16384, SV = SK + 32768, SP = SV + 32768, SBAR = SP + 32768;
-static constexpr int ATT_SMEM = SBAR + 128;  // 114816 B -> 2 CTAs/SM
+static constexpr int SPCLS = SBAR + 128;      // bf16 [256]: softmax numerators of the cls query row (warp 5)
+static constexpr int ATT_SMEM = SPCLS + 512;  // 115328 B -> 2 CTAs/SM
 
 struct AttnDev {
     const __nv_bfloat16* qkv;  // [B*T][3D]
     __nv_bfloat16* out;        // [B*T][D]
     float* lse;                // [B][H][T] or null
     int B, T, H, D, prefix, HW, causal, nkt;  // nkt = number of 128-key tiles (1|2)
+    int pack;  // > 0: `pack` whole sequences (T <= 64 tokens, prefix tokens included as ordinary rows) share one 128-row tile
     float scale_log2;                         // scale * log2(e)
     float scale;
 };
@@ -54,7 +58,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    // packed mode (short sequences, e.g. the 37-token local crops): the tile holds `pack` consecutive sequences, every
+    // token (cls included) is an ordinary query row / key column and the softmax is masked block-diagonally
+    const int qt = blockIdx.x, h = blockIdx.y, b = p.pack ? blockIdx.z * p.pack : blockIdx.z;
     const int D = p.D, T = p.T, prefix = p.prefix, HW = p.HW;
     const long seq_row0 = (long)b * T;
     const int kvrows = 128 * p.nkt;
@@ -117,7 +123,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
         const int r = q4 * 32 + lane;             // row within the tile == TMEM lane
         const int qpos = 128 * qt + r;            // patch index of this query
         const int qtok = prefix + qpos;           // token index within the sequence
-        const bool row_valid = qpos < HW;
+        const int pseq = p.pack ? r / T : 0;  // packed mode: my sequence within the tile
+        const bool row_valid = p.pack ? (pseq < p.pack && b + pseq < p.B) : (qpos < HW);
         const uint32_t trow = tmem + (uint32_t(q4 * 32) << 16);
 
         // scores against the prefix keys (CUDA cores): q row from smem (swizzled), k rows from global
@@ -159,14 +166,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
         float m = -INFINITY;
 #pragma unroll
         for (int j = 0; j < MAX_PREFIX; ++j) m = fmaxf(m, s_pre[j]);
-        const int kmax = p.causal ? min(HW, qpos + 1) : HW;  // keys [0,kmax) are visible
+        // keys [kmin,kmax) are visible
+        const int kmin = p.pack ? (row_valid ? pseq * T : 0) : 0;
+        const int kmax = p.pack ? (row_valid ? kmin + T : 0) : (p.causal ? min(HW, qpos + 1) : HW);
         for (int c = 0; c < kvrows; c += 32) {
+            // tcgen05.ld is warp-collective: a chunk is skipped only when no lane of the warp needs it
+            if (__all_sync(0xffffffffu, c + 32 <= kmin || c >= kmax)) continue;
             uint32_t rr[32];
             tmem_ld_32x32(trow + c, rr);
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i)
-                if (c + i < kmax) m = fmaxf(m, __uint_as_float(rr[i]));
+                if (c + i >= kmin && c + i < kmax) m = fmaxf(m, __uint_as_float(rr[i]));
         }
         const float msc = (m == -INFINITY) ? 0.f : m * p.scale_log2;
         // pass 2: p = exp2(s*scale*log2e - m*scale*log2e), written as bf16 to the swizzled P tile, half by half
@@ -183,16 +194,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
 #pragma unroll 1
             for (int c32 = 0; c32 < 4; ++c32) {
                 const int c = half * 128 + c32 * 32;
-                uint32_t rr[32];
-                tmem_ld_32x32(trow + c, rr);
-                tmem_ld_wait();
                 uint32_t pk[16];
+                if (__all_sync(0xffffffffu, c + 32 <= kmin || c >= kmax)) {  // masked for the whole warp: zeros (PV sums over all keys)
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                    float e0 = (c + i < kmax) ? ex2f(__uint_as_float(rr[i]) * p.scale_log2 - msc) : 0.f;
-                    float e1 = (c + i + 1 < kmax) ? ex2f(__uint_as_float(rr[i + 1]) * p.scale_log2 - msc) : 0.f;
-                    l += e0 + e1;
-                    pk[i >> 1] = pack_bf16x2(e0, e1);
+                    for (int i = 0; i < 16; ++i) pk[i] = 0u;
+                } else {
+                    uint32_t rr[32];
+                    tmem_ld_32x32(trow + c, rr);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const bool v0 = c + i >= kmin && c + i < kmax, v1 = c + i + 1 >= kmin && c + i + 1 < kmax;
+                        float e0 = v0 ? ex2f(__uint_as_float(rr[i]) * p.scale_log2 - msc) : 0.f;
+                        float e1 = v1 ? ex2f(__uint_as_float(rr[i + 1]) * p.scale_log2 - msc) : 0.f;
+                        l += e0 + e1;
+                        pk[i >> 1] = pack_bf16x2(e0, e1);
+                    }
                 }
                 // 32 keys = 4 x 16B chunks into chunk-region (c32>>1), columns (c32&1)*32 ..
                 uint8_t* pb = smem + SP + (c32 >> 1) * 16384;
@@ -241,7 +258,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                 w.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv), w.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
                 *reinterpret_cast<uint4*>(op + c * 8) = w;
             }
-            if (p.lse) p.lse[((long)b * p.H + h) * T + qtok] = m * p.scale + logf(l);
+            if (p.lse) {
+                if (p.pack) p.lse[((long)(b + pseq) * p.H + h) * T + (r - pseq * T)] = m * p.scale + logf(l);
+                else p.lse[((long)b * p.H + h) * T + qtok] = m * p.scale + logf(l);
+            }
         }
         tc_fence_before();
     } else {
@@ -291,15 +311,18 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                 }
                 m = warp_max(m);
                 const float msc = m * p.scale_log2;
-                float l = 0.f, e[8];
+                float l = 0.f;
+                __nv_bfloat16* pcls = reinterpret_cast<__nv_bfloat16*>(smem + SPCLS);
+                __syncwarp();  // previous prefix row has finished reading pcls
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    e[i] = (s[i] == -INFINITY) ? 0.f : ex2f(s[i] * p.scale_log2 - msc);
-                    l += e[i];
-                    e[i] = bf16_round(e[i]);
+                    const float e = (s[i] == -INFINITY) ? 0.f : ex2f(s[i] * p.scale_log2 - msc);
+                    l += e;
+                    pcls[lane + 32 * i] = __float2bfloat16_rn(e);  // keys beyond HW / kvrows get 0
                 }
                 l = warp_sum(l);
-                float a0 = 0.f, a1 = 0.f;
+                __syncwarp();
+                float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
 #pragma unroll
                 for (int t = 0; t < MAX_PREFIX; ++t) {
                     if (t < prefix && sp[t] != -INFINITY) {
@@ -309,19 +332,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
                         a0 += bf16_round(pe) * bf16_lo(w), a1 += bf16_round(pe) * bf16_hi(w);
                     }
                 }
+                // O_cls = P V: the lane owns output dims (2 lane, 2 lane + 1); eight keys per iteration, the numerators come
+                // as one broadcast 16-byte read, two independent accumulator pairs (the former per-key shuffle chain cost
+                // ~16k cycles and made this warp the straggler of every qt == 0 CTA)
+                const int kend = min(HW, kvrows);
+                for (int k8 = 0; k8 < kend; k8 += 8) {
+                    const uint4 pw = *reinterpret_cast<const uint4*>(pcls + k8);
+                    const uint32_t pr[4] = {pw.x, pw.y, pw.z, pw.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    if (32 * i < HW && 32 * i < kvrows) {
-                        for (int t = 0; t < 32; ++t) {
-                            const float pk = __shfl_sync(0xffffffffu, e[i], t);
-                            const int kk = 32 * i + t;
-                            if (kk < HW) {
-                                const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + SV + sw128_off(kk, 2 * lane));
-                                a0 += pk * bf16_lo(w), a1 += pk * bf16_hi(w);
-                            }
-                        }
+                    for (int u = 0; u < 8; ++u) {
+                        const float pk = (u & 1) ? bf16_hi(pr[u >> 1]) : bf16_lo(pr[u >> 1]);
+                        const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + SV + sw128_off(k8 + u, 2 * lane));
+                        if (u & 1) c0 += pk * bf16_lo(w), c1 += pk * bf16_hi(w);
+                        else a0 += pk * bf16_lo(w), a1 += pk * bf16_hi(w);
                     }
                 }
+                a0 += c0, a1 += c1;
                 const float inv = 1.f / l;
                 *reinterpret_cast<uint32_t*>(p.out + (seq_row0 + j) * D + h * 64 + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
                 if (p.lse && lane == 0) p.lse[((long)b * p.H + h) * T + j] = m * p.scale + logf(l);
@@ -412,6 +438,12 @@ extern "C" int vtp_attention_fwd(const void* qkv, void* out, float* lse, int B, 
     p.nkt = HW > 128 ? 2 : 1;
     p.scale = 0.125f;
     p.scale_log2 = 0.125f * 1.4426950408889634f;
+    p.pack = 0;
+    if (!causal && T <= 64 && B > 1 && getenv("VTP_ATTN_NO_PACK") == nullptr) {
+        // several whole sequences per 128-row tile; the prefix tokens become ordinary rows / columns
+        p.pack = 128 / T;
+        p.prefix = 0, p.HW = T, p.nkt = 1;
+    }
     CUtensorMap tm;
     uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)B * T}, strides[1] = {(uint64_t)3 * D * 2};
     uint32_t box[2] = {64, 128};
@@ -422,7 +454,7 @@ extern "C" int vtp_attention_fwd(const void* qkv, void* out, float* lse, int B, 
         VTP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         configured = true;
     }
-    dim3 grid(ceil_div(HW, 128), H, B);
+    dim3 grid(p.pack ? 1 : ceil_div(HW, 128), H, p.pack ? ceil_div(B, p.pack) : B);
     attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tm, p);
     VTP_LAUNCH_CHECK();
     return VTP_OK;

@@ -13,6 +13,8 @@
 // TMEM: dK|dV (128) + dQ_0|dQ_1 (128) + S|dP (256) = 512 columns.
 // The cls token (prefix) is handled on CUDA cores as in the forward kernel: as an extra key column by the row threads
 // (rank-1 updates + a warp-reduced column for dK_0/dV_0) and as an extra query row by a spare warp.
+#include <stdlib.h>
+
 #include "host.h"
 #include "ptx.cuh"
 
@@ -34,6 +36,9 @@ struct AttnBwdDev {
     const __nv_bfloat16* rope_cos;
     int B, T, H, D, prefix, HW, causal, nkt;
     float scale, scale_log2;
+    // packed mode (T <= 64): `pack` whole sequences share the 128-row tile, their prefix tokens (`rprefix` per sequence)
+    // are ordinary rows / key columns (prefix == 0 above) and P, dS are masked block-diagonally
+    int pack, rprefix;
 };
 
 __device__ __forceinline__ float ex2f(float x) {  // ex2.approx.ftz: no denormal slow path (exp2f() costs 4 extra instr)
@@ -104,7 +109,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.x, b = blockIdx.y;
+    const int h = blockIdx.x, b = p.pack ? blockIdx.y * p.pack : blockIdx.y;
     const int D = p.D, T = p.T, prefix = p.prefix, HW = p.HW, nkt = p.nkt;
     const long row0 = (long)b * T;
     const int nsteps = nkt * nkt;
@@ -198,6 +203,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         const int g = warp >> 2, q4 = warp & 3;
         const int r = q4 * 32 + lane;
         const uint32_t trow = tmem + (uint32_t(q4 * 32) << 16);
+        // packed mode: row r = token (r % T) of sequence b + r / T; it sees the key columns of its own sequence only
+        const int pseq = p.pack ? r / T : 0;
+        const bool pvalid = p.pack && pseq < p.pack && b + pseq < p.B;
+        const int ptok = r - pseq * T;
         const int my_tile = (nkt == 2) ? g : 0;
         const bool owns_tile = (nkt == 2) || (g == 0);
         float lse_i[2], delta_i[2];
@@ -208,7 +217,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         for (int n = 0; n < nsteps; ++n) {
             const int kh = n / nkt, t = n % nkt;
             const int qi = 128 * t + r;  // patch index of my query row in this step
-            const bool qvalid = qi < HW;
+            const bool qvalid = p.pack ? pvalid : qi < HW;
             if (kh == 0) {
                 // per-query-tile scalars (first visit of tile t): lse, delta = dO·O; the owner group also does the
                 // cls-key column
@@ -218,7 +227,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 float p0v = 0.f, ds0v = 0.f;
                 if (qvalid) {
                     const long grow = row0 + prefix + qi;
-                    lse_i[t] = p.lse[((long)b * p.H + h) * T + prefix + qi];
+                    lse_i[t] = p.pack ? p.lse[((long)(b + pseq) * p.H + h) * T + ptok] : p.lse[((long)b * p.H + h) * T + prefix + qi];
                     float dof[64], tmpf[64];
                     load_row64(smem + BDO + t * 16384, r, dof);
                     load_grow64(p.o + grow * D + h * 64, tmpf);
@@ -262,7 +271,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             mbar_wait(bar_sdp, n & 1);
             tc_fence_after();
             if (n > 0) mbar_wait(bar_mma2, (n - 1) & 1);  // P/dS smem tiles free again
-            const int kmax = p.causal ? min(HW, qi + 1) : HW;
+            const int kmin = p.pack ? pseq * T : 0;
+            const int kmax = p.pack ? kmin + T : (p.causal ? min(HW, qi + 1) : HW);
             const float lsc = lse_i[t] * lse_l2, dl = delta_i[t];
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
@@ -276,11 +286,11 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
                     float pa = 0.f, pb = 0.f, da = 0.f, db = 0.f;
-                    if (qvalid && kbase + i < kmax) {
+                    if (qvalid && kbase + i >= kmin && kbase + i < kmax) {
                         pa = ex2f(__uint_as_float(rs[i]) * p.scale_log2 - lsc);
                         da = p.scale * pa * (__uint_as_float(rd[i]) - dl);
                     }
-                    if (qvalid && kbase + i + 1 < kmax) {
+                    if (qvalid && kbase + i + 1 >= kmin && kbase + i + 1 < kmax) {
                         pb = ex2f(__uint_as_float(rs[i + 1]) * p.scale_log2 - lsc);
                         db = p.scale * pb * (__uint_as_float(rd[i + 1]) - dl);
                     }
@@ -315,7 +325,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 for (int i = 0; i < 32; ++i) gq[i] = __uint_as_float(a0[i]), gq[32 + i] = __uint_as_float(a1[i]);
                 tc_fence_before();
                 mbar_arrive(bar_accfree);
-                if (kj < HW) {
+                if (p.pack ? pvalid : kj < HW) {
                     if (g == 0) {
                         if (prefix > 0) {
                             float f[64];
@@ -333,7 +343,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
                             for (int d = 0; d < 64; ++d) gq[d] += dc * f[d];
                         }
-                        if (p.rope_sin) rope_bwd64(gq, p.rope_sin + (long)kj * 64, p.rope_cos + (long)kj * 64);
+                        const int pos = p.pack ? ptok - p.rprefix : kj;  // patch position (prefix tokens are not rotated)
+                        if (p.rope_sin && pos >= 0) rope_bwd64(gq, p.rope_sin + (long)pos * 64, p.rope_cos + (long)pos * 64);
                         store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + D + h * 64, gq);
                     }
                 }
@@ -347,7 +358,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             tmem_ld_32x32(trow + C_DQ + 64 * t, a0);
             tmem_ld_32x32(trow + C_DQ + 64 * t + 32, a1);
             tmem_ld_wait();
-            if (qi < HW) {
+            if (p.pack ? pvalid : qi < HW) {
                 float gq[64];
 #pragma unroll
                 for (int i = 0; i < 32; ++i) gq[i] = __uint_as_float(a0[i]), gq[32 + i] = __uint_as_float(a1[i]);
@@ -357,7 +368,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
                     for (int d = 0; d < 64; ++d) gq[d] += ds_own * f[d];
                 }
-                if (p.rope_sin) rope_bwd64(gq, p.rope_sin + (long)qi * 64, p.rope_cos + (long)qi * 64);
+                const int pos = p.pack ? ptok - p.rprefix : qi;
+                if (p.rope_sin && pos >= 0) rope_bwd64(gq, p.rope_sin + (long)pos * 64, p.rope_cos + (long)pos * 64);
                 store_row64(p.dqkv + (row0 + prefix + qi) * 3 * D + h * 64, gq);
             }
         }
@@ -464,6 +476,11 @@ extern "C" int vtp_attention_bwd(const void* qkv, const void* o, const void* dou
     p.B = B, p.T = T, p.H = H, p.D = D, p.prefix = prefix, p.HW = HW, p.causal = causal;
     p.nkt = HW > 128 ? 2 : 1;
     p.scale = 0.125f, p.scale_log2 = 0.125f * 1.4426950408889634f;
+    p.pack = 0, p.rprefix = prefix;
+    if (!causal && T <= 64 && B > 1 && getenv("VTP_ATTN_NO_PACK") == nullptr) {
+        p.pack = 128 / T;
+        p.prefix = 0, p.HW = T, p.nkt = 1;
+    }
     CUtensorMap tq, td;
     {
         uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)B * T}, strides[1] = {(uint64_t)3 * D * 2};
@@ -482,7 +499,7 @@ extern "C" int vtp_attention_bwd(const void* qkv, const void* o, const void* dou
         VTP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
         configured = true;
     }
-    attn_bwd_kernel<<<dim3(H, B), AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, p);
+    attn_bwd_kernel<<<dim3(H, p.pack ? ceil_div(B, p.pack) : B), AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, p);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }
