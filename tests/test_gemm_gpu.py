@@ -148,3 +148,33 @@ def test_gemm_pixel_shuffle():
     y = (_ref(A, W, False, False) + bias).view(Bn, g, g, N).permute(0, 3, 1, 2)
     ref = torch.nn.functional.pixel_shuffle(y, r)
     assert _relerr(out, ref) < 2e-5
+
+
+@pytest.mark.parametrize("variant", ["default", "VTP_GEMM_G2", "VTP_GEMM_NO_FAST", "VTP_GEMM_NO_CLUSTER"])
+@pytest.mark.parametrize("out_f32,resid,relu", [(False, False, False), (False, True, False), (True, False, False),
+                                                (True, True, False), (False, False, True)])
+@pytest.mark.parametrize("M,N,K", [(1000, 384, 384), (777, 1160, 200), (260, 2048, 1024), (129, 72, 64)])
+def test_gemm_fast_epilogue_modes(monkeypatch, variant, out_f32, resid, relu, M, N, K):
+    """The lean TMA-store epilogue (bias, rounding point, optional same-dtype residual, ReLU) incl. M / N tails, in place
+    and out of place, on the multicast (default), cta_group::2, generic-epilogue and single-CTA kernel variants."""
+    if variant != "default":
+        monkeypatch.setenv(variant, "1")
+    r8 = lambda v: (v + 7) // 8 * 8
+    A, W = _mk((M, r8(K)), 11)[:, :K], _mk((N, r8(K)), 12, 0.1)[:, :K]
+    bias = torch.randn(N, device="cuda")
+    dt = torch.float32 if out_f32 else torch.bfloat16
+    x = torch.randn(M, N, device="cuda").to(dt)
+    acc = (_ref(A, W, False, False) + bias).to(torch.bfloat16).float()  # bf16 rounding point of the linear (autocast)
+    if relu:
+        acc = acc.clamp_min(0)
+    ref = (acc + x.float()).to(dt) if resid else acc.to(dt)
+    for inplace in ([False, True] if resid else [False]):
+        xin = x.clone()
+        out = xin if inplace else torch.full((M, N), float("nan"), device="cuda", dtype=dt)
+        lib.gemm(A, W, out, M=M, N=N, K=K, bias=bias, resid=xin if resid else None,
+                 act=lib.ACT_RELU if relu else lib.ACT_NONE)
+        torch.cuda.synchronize()
+        assert torch.isfinite(out.float()).all()
+        # one bf16 ulp of slack where the fp32 accumulation order flips the rounding point
+        assert (out.float() - ref.float()).abs().max().item() <= 2.0 ** -7 * ref.float().abs().max().item() + 1e-6
+        assert _relerr(out, ref) < 2e-3

@@ -50,11 +50,9 @@ cases = [
     ("fc2+res    N384  K1024 f32", 2 * M * D * Hs, lambda: lib.gemm(xh, W3, stream, M=M, N=D, K=Hs, bias=bd, resid=stream),
      lambda: torch.mm(xh, W3.t(), out=o_d)),
 ]
-variants = [("default (fast)", {}), ("generic epilogue", {"VTP_GEMM_NO_FAST": "1"}), ("no-cluster", {"VTP_GEMM_NO_CLUSTER": "1"}),
-            ("no-2perSM", {"VTP_GEMM_NO_2PERSM": "1"}),
-            ("dbg1 nostore", {"VTP_GEMM_DBG": "1"}), ("dbg4 noepi", {"VTP_GEMM_DBG": "4"}),
-            ("dbg8 nomma", {"VTP_GEMM_DBG": "8"}), ("dbg12 neither", {"VTP_GEMM_DBG": "12"})]
-KEYS = ["VTP_GEMM_DBG", "VTP_GEMM_NO_CLUSTER", "VTP_GEMM_NO_2PERSM", "VTP_GEMM_NO_FAST"]
+variants = [("default (g2)", {}), ("no-g2 (multicast)", {"VTP_GEMM_NO_G2": "1"}),
+            ("g2 dbg4 noepi", {"VTP_GEMM_DBG": "4"}), ("g2 dbg12 neither", {"VTP_GEMM_DBG": "12"})]
+KEYS = ["VTP_GEMM_DBG", "VTP_GEMM_NO_CLUSTER", "VTP_GEMM_NO_2PERSM", "VTP_GEMM_NO_FAST", "VTP_GEMM_NO_G2"]
 print(f"M = {M}   (us per launch; TFLOP/s in brackets for the full-work variants)")
 print(f"{'variant':18s}" + "".join(f"{c[0]:>30s}" for c in cases))
 for vname, env in variants:

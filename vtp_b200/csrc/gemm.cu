@@ -358,14 +358,22 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
 // bias comes from a 256-byte per-warp shared tile (broadcast reads), the residual is fetched into registers one chunk
 // ahead, before the accumulator is waited for.
 //   FAST: 1 bf16 out, 2 bf16 out + bf16 residual, 3 fp32 out, 4 fp32 out + fp32 residual.   ACT: NONE | RELU.
-template <int BN, int ACT, int FAST>
+// hand the accumulator buffer back to the MMA issuer: with cta_group::2 the issuer lives in the leader CTA (rank 0)
+template <bool G2>
+__device__ __forceinline__ void arrive_tempty(uint64_t* bar) {
+    if (G2) mbar_arrive_cluster(mapa_u32(bar, 0));
+    else mbar_arrive(bar);
+}
+
+template <int BN, int ACT, int FAST, bool G2>
 __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUtensorMap* tmO, uint8_t* stg, float* bias_s,
                                                    int lane, int q, int hsel, uint32_t taddr, int m0, int n0,
                                                    uint64_t* tfull, uint32_t aph, uint64_t* tempty) {
     constexpr bool OF32 = FAST >= 3;
     constexpr bool RES = FAST == 2 || FAST == 4;
     constexpr int CW = OF32 ? 32 : 64;   // accumulator columns per 128-byte output chunk
-    constexpr int NCH = BN / CW / 2;     // chunks per warp and tile (the two warps of a lane quarter interleave)
+    constexpr int TCH = BN / CW;         // chunks per tile row
+    constexpr int NCH = (TCH + 1) / 2;   // chunks per warp and tile (the two warps of a lane quarter interleave)
     constexpr int PW = OF32 ? 4 : 8;     // columns per 16-byte piece
     const int N = p.N;
     const long row = (long)m0 + q * 32 + lane;
@@ -396,7 +404,7 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
 #pragma unroll
             for (int j = 1; j < NCH; ++j) {  // later chunks: warm this lane's 128-byte row piece in L2
                 const int col = n0 + (hsel + 2 * j) * CW;
-                if (row_ok && col < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + (long)col * (OF32 ? 4 : 2)));
+                if (row_ok && col < N && hsel + 2 * j < TCH) asm volatile("prefetch.global.L2 [%0];" ::"l"(rrow + (long)col * (OF32 ? 4 : 2)));
             }
         }
     }
@@ -404,8 +412,8 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
     for (int j = 0; j < NCH; ++j) {
         const int c = hsel + 2 * j;
         const int col0 = n0 + c * CW;
-        if (col0 >= N) break;  // warp-uniform
-        const bool last = (j == NCH - 1) || (col0 + 2 * CW >= N);
+        if (c >= TCH || col0 >= N) break;  // warp-uniform
+        const bool last = (j == NCH - 1) || (c + 2 >= TCH) || (col0 + 2 * CW >= N);
         const float b0 = b0n, b1 = b1n;
         if (!last) load_bias(col0 + 2 * CW);
         if (!waited) {
@@ -424,7 +432,7 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
         if (last) {  // accumulator fully in registers: hand the TMEM buffer back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty);
+            if (lane == 0) arrive_tempty<G2>(tempty);
         }
         if (!(p.dbg & 4)) {
 #pragma unroll
@@ -473,22 +481,28 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(tempty);
+        if (lane == 0) arrive_tempty<G2>(tempty);
     }
 }
 
 // CL2: the CTA pair of a 2-CTA cluster works on two vertically adjacent tiles (same n-block): each CTA loads its own A
 // tile and HALF of the shared B tile, multicast to both — 25-33 % less L2->SMEM traffic, which is what caps this kernel
 // (128x128x64 tiles at 32 KB per k-block = 64 flop/B against ~12 TB/s of L2 is ~0.8 PFLOP/s).
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST>
+// G2 (implies CL2): ONE tcgen05.mma.cta_group::2 per k-step covers the pair's 256 x BN tile.  Each CTA stages its own A tile
+// and only HALF of B (the MMA reads both halves across the pair), so the shared-memory fill per flop drops by a third
+// against the multicast variant — the L2->SM feed is what caps the 128 x BN kernel at ~1.3 PFLOP/s.  The leader CTA's
+// MMA thread issues for both; full barriers (both CTAs' TMA bytes) and accumulator-empty barriers live in the leader.
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST, bool G2>
 // 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168 (MINB = 1).
 // MINB = 2 (short-K shapes): two CTAs per SM with a 2-stage ring double the epilogue warps per SM at ~100 registers.
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const GemmDev p) {
-    constexpr int B_BYTES = BN * BK * 2;
+    static_assert(!G2 || CL2, "cta_group::2 needs the 2-CTA cluster");
+    constexpr int B_BYTES = (G2 ? BN / 2 : BN) * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    constexpr uint32_t TMEM_COLS = 2 * BN;  // 256 or 512 (power of two)
+    constexpr int ACC_STRIDE = BN == 192 ? 256 : BN;  // column distance of the two accumulator buffers
+    constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;    // 256 or 512 (power of two)
 
     // FAST kernels use every byte (ring + staging + bias tiles + barriers = 226 KB at BN = 256): they rely on the declared
     // 1024-byte alignment of the dynamic segment (checked below) instead of carrying a 1 KB alignment pad
@@ -515,13 +529,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (FAST) tma_prefetch_desc(&tmO);
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], CL2 ? 2 : 1);
-        for (int s = 0; s < 2; ++s) mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], NUM_EPI_WARPS);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], (CL2 && !G2) ? 2 : 1);
+        for (int s = 0; s < 2; ++s)
+            mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], G2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
-        tmem_relinquish();
+        if (G2) tmem_alloc_g2(tmem_slot, TMEM_COLS), tmem_relinquish_g2();
+        else tmem_alloc(tmem_slot, TMEM_COLS), tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
@@ -549,7 +564,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + s * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
-                    mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    if (!G2) mbar_expect_tx(&full_bar[s], STAGE_BYTES);
+                    else if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // both CTAs' bytes land here
+                    const uint32_t lbar = G2 ? mapa_u32(&full_bar[s], 0) : 0u;
                     const int k0 = kb * BK;
                     if (p.conv_C) {
                         const int tx = m_blk % p.conv_tiles_w, ty = (m_blk / p.conv_tiles_w) % p.conv_tiles_h;
@@ -557,13 +574,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         const int cpk = p.conv_C >> 6, tap = kb / cpk, c0 = (kb % cpk) << 6;
                         tma_load_4d(sa, &tmA, &full_bar[s], c0, tx * p.conv_TW + tap % 3 - 1, ty * p.conv_TH + tap / 3 - 1,
                                     bimg);
+                    } else if (G2) {
+                        if (!p.a_mn) {
+                            tma_load_2d_g2(sa, &tmA, lbar, k0, m0);
+                        } else {
+                            tma_load_2d_g2(sa, &tmA, lbar, m0, k0);
+                            tma_load_2d_g2(sa + 8192, &tmA, lbar, m0 + 64, k0);
+                        }
                     } else if (!p.a_mn) {
                         tma_load_2d(sa, &tmA, &full_bar[s], k0, m0);
                     } else {
                         tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
                         tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
                     }
-                    if (CL2) {  // my half of B, delivered to both CTAs of the pair
+                    if (G2) {  // my half of B stays in MY shared memory: the pair's MMA reads both halves
+                        if (!p.b_mn) {
+                            tma_load_2d_g2(sb, &tmB, lbar, k0, n0 + (int)crank * (BN / 2));
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < BN / 128; ++i)
+                                tma_load_2d_g2(sb + i * 8192, &tmB, lbar, n0 + ((int)crank * (BN / 128) + i) * 64, k0);
+                        }
+                    } else if (CL2) {  // my half of B, delivered to both CTAs of the pair
                         if (!p.b_mn) {
                             tma_load_2d_mc(sb + crank * (BN / 2) * 128, &tmB, &full_bar[s], k0, n0 + (int)crank * (BN / 2), 3);
                         } else {
@@ -585,8 +617,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
     } else if (warp == 1) {
         // ============================== UMMA issuer ==============================
-        if (lane == 0) {
-            const uint32_t idesc = umma_idesc_bf16(BM, BN, p.a_mn, p.b_mn);
+        if (lane == 0 && (!G2 || crank == 0)) {
+            const uint32_t idesc = umma_idesc_bf16(G2 ? 2 * BM : BM, BN, p.a_mn, p.b_mn);
             int s = 0;
             uint32_t ph = 0;
             int as = 0;
@@ -597,7 +629,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + as * BN;
+                const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
@@ -609,14 +641,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                                    : umma_desc_sw128(a_base + j * 32, 0, 1024);
                         const uint64_t bd = p.b_mn ? umma_desc_sw128(b_base + j * 2048, 8192, 1024)
                                                    : umma_desc_sw128(b_base + j * 32, 0, 1024);
-                        if (!(p.dbg & 8)) umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                        if (p.dbg & 8) continue;
+                        if (G2) umma_bf16_ss_g2(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
+                        else umma_bf16_ss(d_tmem, ad, bd, idesc, (kb > kb0 || j > 0) ? 1u : 0u);
                     }
                     // frees the smem slot once these MMAs have read it (in both CTAs: the peer multicasts into mine)
-                    if (CL2) umma_commit_mc(&empty_bar[s], 3);
+                    if (G2) umma_commit_mc_g2(&empty_bar[s], 3);
+                    else if (CL2) umma_commit_mc(&empty_bar[s], 3);
                     else umma_commit(&empty_bar[s]);
                     if (++s == STAGES) s = 0, ph ^= 1;
                 }
-                umma_commit(&tfull_bar[as]);  // accumulator complete
+                // accumulator complete (with cta_group::2: in both CTAs, each runs its own epilogue on its 128 rows)
+                if (G2) umma_commit_mc_g2(&tfull_bar[as], 3);
+                else umma_commit(&tfull_bar[as]);
                 if (++as == 2) as = 0, aph ^= 1;
             }
         }
@@ -633,9 +670,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int m_blk = ((t / p.num_n_blocks) % p.num_m_blocks) * (CL2 ? 2 : 1) + (int)crank;
             const int m0 = m_blk * BM, n0 = n_blk * BN;
             const int grow0 = m0 + q * 32;
-            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * BN;
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE;
             if constexpr (FAST != 0) {
-                fast_epilogue_tile<BN, ACT, FAST>(p, &tmO, reinterpret_cast<uint8_t*>(stg), bias_base + (warp - 2) * 64, lane,
+                fast_epilogue_tile<BN, ACT, FAST, G2>(p, &tmO, reinterpret_cast<uint8_t*>(stg), bias_base + (warp - 2) * 64, lane,
                                                   q, hsel, taddr, m0, n0, &tfull_bar[as], aph, &tempty_bar[as]);
                 if (++as == 2) as = 0, aph ^= 1;
                 continue;
@@ -682,7 +719,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) arrive_tempty<G2>(&tempty_bar[as]);
             if (++as == 2) as = 0, aph ^= 1;
         }
     }
@@ -693,18 +730,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (CL2) cluster_sync_all();  // no CTA may exit while its peer can still multicast into it / arrive on its barriers
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (G2) tmem_dealloc_g2(tmem_base, TMEM_COLS);
+        else tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0>
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0, bool G2 = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream,
                        const CUtensorMap* tmO = nullptr) {
-    constexpr int smem_bytes = STAGES * (A_BYTES + BN * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 +
+    constexpr int smem_bytes = STAGES * (A_BYTES + (G2 ? BN / 2 : BN) * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 +
                                (FAST ? NUM_EPI_WARPS * 256 + 256 : 1024 + 256);
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST>,
+        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
@@ -724,7 +762,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST>, tmA, tmB, tmO ? *tmO : tmA, p));
+    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>, tmA, tmB, tmO ? *tmO : tmA, p));
     return VTP_OK;
 }
 
@@ -767,6 +805,21 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     // tile-N choice: minimise padded N, ties -> 256 (lower smem bandwidth per MMA)
     const int pad128 = ceil_div(a->N, 128) * 128, pad256 = ceil_div(a->N, 256) * 256;
     int BN = (pad256 * 8 <= pad128 * 9) ? 256 : 128;  // accept <= 12.5 % padding for the higher-intensity tile
+    // 2-CTA multicast variant whenever there are at least two m-blocks (odd counts are padded with an all-OOB tile)
+    const bool allow_cl2 = getenv("VTP_GEMM_NO_CLUSTER") == nullptr;
+    const bool cl2 = allow_cl2 && !conv && ceil_div(a->M, BM) >= 2;
+    // cta_group::2 (256 x BN pair tiles) wherever the 2-CTA cluster applies
+    // measured (tools/gemm_diag.py): within 3 % of the TMA-multicast variant, slightly behind on every shape (both are
+    // bound by L2->SM reads, which the two variants issue identically), so it is opt-in
+    const bool g2 = cl2 && getenv("VTP_GEMM_G2") != nullptr;
+    // lean TMA-store epilogue for the recurring shapes (see fast_epilogue_tile)
+    const bool allow_fast = getenv("VTP_GEMM_NO_FAST") == nullptr;
+    const bool fast = allow_fast && !conv && a->rr_group == 0 && a->ps_r == 0 && !a->out2 && !a->mask_pos && !a->accumulate &&
+                      split_k == 1 && (a->act == VTP_ACT_NONE || a->act == VTP_ACT_RELU) &&
+                      (!a->resid || a->resid_dtype == a->out_dtype);
+    // N = 384-type widths: 192-wide tiles halve nothing but re-read A twice instead of three times (112 vs 87 flop per
+    // L2 byte for the pair tile) and leave no padding
+    if (fast && !g2 && BN == 128 && a->N % 192 == 0 && getenv("VTP_GEMM_NO_BN192") == nullptr) BN = 192;
     const int two_max_kb = getenv("VTP_GEMM_2PERSM_MAXKB") ? atoi(getenv("VTP_GEMM_2PERSM_MAXKB")) : 16;
     const bool short_bn128 = getenv("VTP_GEMM_SHORTK_BN128") != nullptr;
     if (short_bn128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1 && a->conv_C == 0) BN = 128;
@@ -793,9 +846,6 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     p.mask_pos = reinterpret_cast<const __nv_bfloat16*>(a->mask_pos), p.ldm = a->ldm;
     p.dbg = getenv("VTP_GEMM_DBG") ? atoi(getenv("VTP_GEMM_DBG")) : 0;
 
-    // 2-CTA multicast variant whenever there are at least two m-blocks (odd counts are padded with an all-OOB tile)
-    const bool allow_cl2 = getenv("VTP_GEMM_NO_CLUSTER") == nullptr;
-    const bool cl2 = allow_cl2 && !conv && ceil_div(a->M, BM) >= 2;
 
     CUtensorMap tmA, tmB;
     if (conv) {
@@ -833,11 +883,6 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     // (measured: proj+resid 237 -> 178 us, fc2+resid 244 -> 198 us at M = 131 584)
     const bool allow_2cta = getenv("VTP_GEMM_NO_2PERSM") == nullptr;
     const bool two = allow_2cta && BN == 128 && p.num_k_blocks <= two_max_kb && p.num_splits == 1;
-    // lean TMA-store epilogue for the recurring shapes (see fast_epilogue_tile)
-    const bool allow_fast = getenv("VTP_GEMM_NO_FAST") == nullptr;
-    const bool fast = allow_fast && !conv && a->rr_group == 0 && a->ps_r == 0 && !a->out2 && !a->mask_pos && !a->accumulate &&
-                      split_k == 1 && (a->act == VTP_ACT_NONE || a->act == VTP_ACT_RELU) &&
-                      (!a->resid || a->resid_dtype == a->out_dtype);
     if (fast) {
         CUtensorMap tmO;
         const int esz = a->out_dtype == VTP_F32 ? 4 : 2;
@@ -848,6 +893,13 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         const int mode = (a->out_dtype == VTP_F32 ? 3 : 1) + (a->resid ? 1 : 0);
 #define VTP_FAST_CFG(ACT_, MODE_)                                                                                     \
     do { /* one CTA per SM with the deep ring: measured faster than 2 x (2-stage) once the epilogue is lean */        \
+        if (g2)                                                                                                       \
+            return (BN == 256) ? launch_gemm<256, 6, ACT_, false, true, 1, MODE_, true>(tmA, tmB, p, stream, &tmO)    \
+                               : launch_gemm<128, 8, ACT_, false, true, 1, MODE_, true>(tmA, tmB, p, stream, &tmO);   \
+        if (BN == 192) {                                                                                              \
+            if (cl2) return launch_gemm<192, 4, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO);              \
+            return launch_gemm<192, 4, ACT_, false, false, 1, MODE_>(tmA, tmB, p, stream, &tmO);                      \
+        }                                                                                                             \
         if (cl2)                                                                                                      \
             return (BN == 256) ? launch_gemm<256, 4, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO)          \
                                : launch_gemm<128, 6, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO);         \
@@ -884,6 +936,9 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         VTP_CHECK_ARG(a->act == VTP_ACT_NONE, "gemm: pixel shuffle has no activation");
         VTP_LAUNCH(VTP_ACT_NONE, true);
     }
+    if (g2 && a->act == VTP_ACT_NONE && !(two && getenv("VTP_GEMM_G2_NOT_SHORT")))  // wgrad (split-K), logits, ...
+        return (BN == 256) ? launch_gemm<256, 6, VTP_ACT_NONE, false, true, 1, 0, true>(tmA, tmB, p, stream)
+                           : launch_gemm<128, 8, VTP_ACT_NONE, false, true, 1, 0, true>(tmA, tmB, p, stream);
     switch (a->act) {
         case VTP_ACT_NONE: VTP_LAUNCH(VTP_ACT_NONE, false);
         case VTP_ACT_GELU: VTP_LAUNCH(VTP_ACT_GELU, false);
