@@ -56,7 +56,7 @@ typedef struct {
     const void* resid;      /* residual added after activation, same indexing as out; NULL = none */
     int ldr, resid_dtype;
     int accumulate;         /* 1: atomic fp32 add into out (required when split_k > 1) */
-    int split_k;            /* >=1: split the reduction across CTAs */
+    int split_k;            /* >=1: split the reduction across CTAs; -1: chosen by the library (with accumulate=1) */
     int rr_group, rr_skip;  /* rr_skip>0: out_row = (row/rr_group)*(rr_group+rr_skip) + rr_skip + row%rr_group (cls slot);
                              * rr_skip<0: drop the first -rr_skip rows of every rr_group rows (compaction); 0 = identity */
     const void* rope_sin;   /* VTP_ACT_ROPE: bf16 [rope_tokens-rope_prefix][64] tables (layers/embeddings.py:131-180) */

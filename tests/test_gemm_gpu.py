@@ -68,11 +68,14 @@ def test_gemm_residual_rowremap_inplace():
     assert _relerr(x.view(B_, G + 1, D), exp) < 1e-3
 
 
-def test_gemm_splitk_accumulate():
-    M, N, K = 384, 1152, 8200
+@pytest.mark.parametrize("M,N,K,split", [(384, 1152, 8200, 16), (384, 1152, 8200, -1), (2048, 384, 20000, -1),
+                                         (384, 384, 20000, -1), (1152, 384, 9000, 5), (256, 64, 4100, -1)])
+def test_gemm_splitk_accumulate(M, N, K, split):
+    """wgrad form: TN GEMM, split-K + fp32 red.add into a pre-filled output; split = -1 lets the library choose
+    (192-wide tiles when N % 192 == 0)."""
     A, B = _mk((K, M), 7), _mk((K, N), 8)
     out = torch.ones((M, N), device="cuda")
-    lib.gemm(A, B, out, M=M, N=N, K=K, a_mn=True, b_mn=True, accumulate=True, split_k=16, round_bf16=False)
+    lib.gemm(A, B, out, M=M, N=N, K=K, a_mn=True, b_mn=True, accumulate=True, split_k=split, round_bf16=False)
     torch.cuda.synchronize()
     ref = _ref(A, B, True, True) + 1.0
     assert _relerr(out, ref) < 2e-5

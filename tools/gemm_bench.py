@@ -37,7 +37,7 @@ stream = torch.randn(M, D, device=dev)
 sin = torch.zeros(256, 64, device=dev, dtype=BF); cos = torch.ones(256, 64, device=dev, dtype=BF)
 o_qkv = torch.empty(M, 3 * D, device=dev, dtype=BF); o_d = torch.empty(M, D, device=dev, dtype=BF)
 o_h = torch.empty(M, Hs, device=dev, dtype=BF); o_2h = torch.empty(M, 2 * Hs, device=dev, dtype=BF)
-gW = torch.zeros(2 * Hs, D, device=dev)
+gW = torch.zeros(2 * Hs, D, device=dev); gW3 = torch.zeros(D, Hs, device=dev); gWq = torch.zeros(3 * D, D, device=dev); gWp = torch.zeros(D, D, device=dev)
 cases = [
     ("fwd qkv+rope      ", 2 * M * 3 * D * D, lambda: lib.gemm(x, Wqkv, o_qkv, M=M, N=3 * D, K=D, bias=b3d, act=lib.ACT_ROPE, rope=(sin, cos, 257, 1, 2 * D))),
     ("fwd qkv plain     ", 2 * M * 3 * D * D, lambda: lib.gemm(x, Wqkv, o_qkv, M=M, N=3 * D, K=D, bias=b3d)),
@@ -50,6 +50,11 @@ cases = [
     ("dgrad fc1 (K=2Hs) ", 2 * M * 2 * Hs * D, lambda: lib.gemm(x2h, W12, o_d, M=M, N=D, K=2 * Hs, b_mn=True, ldb=D, round_bf16=False)),
     ("dgrad qkv (K=3D)  ", 2 * M * 3 * D * D, lambda: lib.gemm(xq, Wqkv, o_d, M=M, N=D, K=3 * D, b_mn=True, ldb=D, round_bf16=False)),
     ("wgrad fc1 splitK  ", 2 * M * 2 * Hs * D, lambda: lib.gemm(x2h, x, gW, M=2 * Hs, N=D, K=M, a_mn=True, b_mn=True, lda=2 * Hs, ldb=D, ldo=D, accumulate=True, split_k=8, round_bf16=False)),
+    ("wgrad fc1 auto    ", 2 * M * 2 * Hs * D, lambda: lib.gemm(x2h, x, gW, M=2 * Hs, N=D, K=M, a_mn=True, b_mn=True, lda=2 * Hs, ldb=D, ldo=D, accumulate=True, split_k=-1, round_bf16=False)),
+    ("wgrad fc2 auto    ", 2 * M * Hs * D, lambda: lib.gemm(x, xh, gW3, M=D, N=Hs, K=M, a_mn=True, b_mn=True, lda=D, ldb=Hs, ldo=Hs, accumulate=True, split_k=-1, round_bf16=False)),
+    ("wgrad fc2 splitK8 ", 2 * M * Hs * D, lambda: lib.gemm(x, xh, gW3, M=D, N=Hs, K=M, a_mn=True, b_mn=True, lda=D, ldb=Hs, ldo=Hs, accumulate=True, split_k=8, round_bf16=False)),
+    ("wgrad qkv auto    ", 2 * M * 3 * D * D, lambda: lib.gemm(xq, x, gWq, M=3 * D, N=D, K=M, a_mn=True, b_mn=True, lda=3 * D, ldb=D, ldo=D, accumulate=True, split_k=-1, round_bf16=False)),
+    ("wgrad proj auto   ", 2 * M * D * D, lambda: lib.gemm(x, x, gWp, M=D, N=D, K=M, a_mn=True, b_mn=True, lda=D, ldb=D, ldo=D, accumulate=True, split_k=-1, round_bf16=False)),
     ("wgrad fc1 splitK32", 2 * M * 2 * Hs * D, lambda: lib.gemm(x2h, x, gW, M=2 * Hs, N=D, K=M, a_mn=True, b_mn=True, lda=2 * Hs, ldb=D, ldo=D, accumulate=True, split_k=32, round_bf16=False)),
 ]
 print(f"M = {M}")

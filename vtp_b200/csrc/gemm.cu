@@ -782,7 +782,8 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     VTP_CHECK_ARG(a->N % 8 == 0, "gemm: N must be a multiple of 8");
     VTP_CHECK_ARG(a->out_dtype == VTP_F32 || a->out_dtype == VTP_BF16, "gemm: bad out dtype");
     VTP_CHECK_ARG(a->ldo % (a->out_dtype == VTP_F32 ? 4 : 8) == 0 || a->ps_r > 0, "gemm: ldo alignment");
-    const int split_k = a->split_k < 1 ? 1 : a->split_k;
+    int split_k = a->split_k < 1 ? 1 : a->split_k;  // < 0: chosen below once the tile shape is known (needs accumulate)
+    const bool auto_split = a->split_k < 0 && a->accumulate && a->out_dtype == VTP_F32 && a->act == VTP_ACT_NONE && !a->bias;
     VTP_CHECK_ARG(split_k == 1 || (a->accumulate && a->out_dtype == VTP_F32 && a->act == VTP_ACT_NONE && !a->bias),
                   "gemm: split_k needs accumulate=1, fp32 out, no bias/activation");
     VTP_CHECK_ARG(!a->accumulate || a->out_dtype == VTP_F32, "gemm: accumulate needs fp32 out");
@@ -819,7 +820,25 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
                       (!a->resid || a->resid_dtype == a->out_dtype);
     // N = 384-type widths: 192-wide tiles halve nothing but re-read A twice instead of three times (112 vs 87 flop per
     // L2 byte for the pair tile) and leave no padding
-    if (fast && !g2 && BN == 128 && a->N % 192 == 0 && getenv("VTP_GEMM_NO_BN192") == nullptr) BN = 192;
+    const bool plain_acc = !fast && !g2 && !conv && a->accumulate && a->act == VTP_ACT_NONE && a->ps_r == 0 &&
+                           a->rr_group == 0 && !a->out2 && !a->mask_pos && !a->resid;  // wgrad: split-K + fp32 red.add
+    if ((fast || plain_acc) && !g2 && BN == 128 && a->N % 192 == 0 && getenv("VTP_GEMM_NO_BN192") == nullptr) BN = 192;
+    if (auto_split) {
+        // fill the persistent grid (148 CTAs, or 74 CTA pairs) as evenly as possible: the split with the best wave
+        // efficiency among those that keep >= 8 k-blocks per work item
+        const int grid = cl2 ? num_sms() / 2 : num_sms();
+        const int tiles = (cl2 ? ceil_div(ceil_div(a->M, BM), 2) : ceil_div(a->M, BM)) * ceil_div(a->N, BN);
+        const int nkb = ceil_div(a->K, BK);
+        double best = -1.0;
+        for (int sp = 1; sp <= 64 && sp * 8 <= (nkb > 8 ? nkb : 8); ++sp) {
+            const int kps = ceil_div(nkb, sp);
+            const int real = ceil_div(nkb, kps);  // splits actually produced
+            const long work = (long)tiles * real;
+            if (sp > 1 && work > 3L * grid) break;  // more than three waves only adds pipeline fills and red.add traffic
+            const double eff = (double)work / ((double)ceil_div((int)work, grid) * grid);
+            if (eff > best + 0.02) best = eff, split_k = sp;
+        }
+    }
     const int two_max_kb = getenv("VTP_GEMM_2PERSM_MAXKB") ? atoi(getenv("VTP_GEMM_2PERSM_MAXKB")) : 16;
     const bool short_bn128 = getenv("VTP_GEMM_SHORTK_BN128") != nullptr;
     if (short_bn128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1 && a->conv_C == 0) BN = 128;
@@ -939,6 +958,10 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     if (g2 && a->act == VTP_ACT_NONE && !(two && getenv("VTP_GEMM_G2_NOT_SHORT")))  // wgrad (split-K), logits, ...
         return (BN == 256) ? launch_gemm<256, 6, VTP_ACT_NONE, false, true, 1, 0, true>(tmA, tmB, p, stream)
                            : launch_gemm<128, 8, VTP_ACT_NONE, false, true, 1, 0, true>(tmA, tmB, p, stream);
+    if (BN == 192) {  // only chosen for the fast path (returned above) and the plain split-K accumulate path
+        if (cl2) return launch_gemm<192, 4, VTP_ACT_NONE, false, true, 1>(tmA, tmB, p, stream);
+        return launch_gemm<192, 4, VTP_ACT_NONE, false, false, 1>(tmA, tmB, p, stream);
+    }
     switch (a->act) {
         case VTP_ACT_NONE: VTP_LAUNCH(VTP_ACT_NONE, false);
         case VTP_ACT_GELU: VTP_LAUNCH(VTP_ACT_GELU, false);

@@ -125,59 +125,87 @@ __global__ void pool_relu_bwd_kernel(const __nv_bfloat16* __restrict__ y, const 
     }
 }
 
-// one warp per pixel: f0 (reconstruction) / f1 (target) [P][C] bf16, lin weights w[C] fp32.
+// LPP lanes per pixel, each lane owns V groups of 8 consecutive channels (16-byte loads): C = 8 * LPP * V.
+// f0 (reconstruction) / f1 (target) [P][C] bf16, lin weights w[C] fp32.
 //   d = Σ_c w_c (n0_c − n1_c)^2,  n = f / (||f|| + eps)      loss_acc += coef * Σ_pixels d
 //   g0[P][C] = coef * d d/d f0, masked by (f0 > 0) (the tap is a ReLU output)
-__global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
-                                 const float* __restrict__ w, __nv_bfloat16* __restrict__ g0, long P, int C, float coef,
-                                 float* __restrict__ loss_acc) {
-    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    float local = 0.f;
-    for (long pix = warp; pix < P; pix += ((long)gridDim.x * blockDim.x) >> 5) {
-        float a[16], bq[16];  // C <= 512: 16 values per lane (2 per 64-channel group)
-        float s0 = 0.f, s1 = 0.f;
-        const int nper = C / 32;
+// (one warp per pixel left 4-byte loads and 20 full-warp shuffles per pixel at C = 64: 18 % of the HBM roofline)
+template <int LPP>
+__device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-            if (i < nper) {
-                const int c = (i / 2) * 64 + 2 * lane;
-                const uint32_t u = *reinterpret_cast<const uint32_t*>(f0 + pix * C + c);
-                const uint32_t v = *reinterpret_cast<const uint32_t*>(f1 + pix * C + c);
-                a[i] = bf16_lo(u), a[i + 1] = bf16_hi(u), bq[i] = bf16_lo(v), bq[i + 1] = bf16_hi(v);
-                s0 += a[i] * a[i] + a[i + 1] * a[i + 1], s1 += bq[i] * bq[i] + bq[i + 1] * bq[i + 1];
-            }
+    for (int o = LPP / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+    f[0] = bf16_lo(u.x), f[1] = bf16_hi(u.x), f[2] = bf16_lo(u.y), f[3] = bf16_hi(u.y);
+    f[4] = bf16_lo(u.z), f[5] = bf16_hi(u.z), f[6] = bf16_lo(u.w), f[7] = bf16_hi(u.w);
+}
+template <int LPP, int V>
+__global__ void __launch_bounds__(256) lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
+                                                        const float* __restrict__ w, __nv_bfloat16* __restrict__ g0, long P,
+                                                        float coef, float* __restrict__ loss_acc) {
+    constexpr int C = 8 * LPP * V;
+    constexpr int PPW = 32 / LPP;  // pixels per warp
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const int sub = lane / LPP, li = lane % LPP;
+    float wv[V][8];
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const float4 wa = __ldg(reinterpret_cast<const float4*>(w + (v * LPP + li) * 8));
+        const float4 wb = __ldg(reinterpret_cast<const float4*>(w + (v * LPP + li) * 8 + 4));
+        wv[v][0] = wa.x, wv[v][1] = wa.y, wv[v][2] = wa.z, wv[v][3] = wa.w;
+        wv[v][4] = wb.x, wv[v][5] = wb.y, wv[v][6] = wb.z, wv[v][7] = wb.w;
+    }
+    float local = 0.f;
+    for (long base = warp * PPW; base < P; base += nwarps * PPW) {  // warp-uniform trip count
+        const long pix = base + sub;
+        const bool ok = pix < P;
+        float a[V][8], bq[V][8];
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            const long off = pix * C + (v * LPP + li) * 8;
+            const uint4 u = ok ? *reinterpret_cast<const uint4*>(f0 + off) : make_uint4(0, 0, 0, 0);
+            const uint4 t = ok ? *reinterpret_cast<const uint4*>(f1 + off) : make_uint4(0, 0, 0, 0);
+            unpack8(u, a[v]);
+            unpack8(t, bq[v]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s0 += a[v][k] * a[v][k], s1 += bq[v][k] * bq[v][k];
         }
-        s0 = warp_sum(s0), s1 = warp_sum(s1);
+        s0 = group_sum<LPP>(s0), s1 = group_sum<LPP>(s1);
         const float r0 = sqrtf(s0), r1 = sqrtf(s1);
         const float i0 = 1.f / (r0 + 1e-10f), i1 = 1.f / (r1 + 1e-10f);
         float d = 0.f, dot = 0.f;
-        float gn[16];
+        float gn[V][8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (i < nper) {
-                const int c = (i / 2) * 64 + 2 * lane + (i & 1);
-                const float diff = a[i] * i0 - bq[i] * i1;
-                const float wc = __ldg(w + c);
-                d += wc * diff * diff;
-                gn[i] = 2.f * coef * wc * diff;  // d/d n0
-                dot += gn[i] * a[i];
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const float diff = a[v][k] * i0 - bq[v][k] * i1;
+                d += wv[v][k] * diff * diff;
+                gn[v][k] = 2.f * coef * wv[v][k] * diff;  // d/d n0
+                dot += gn[v][k] * a[v][k];
             }
-        }
-        d = warp_sum(d), dot = warp_sum(dot);
-        local += d;
+        d = group_sum<LPP>(d), dot = group_sum<LPP>(dot);
+        if (li == 0 && ok) local += d;
         // g_f = gn/(r+eps) − f (gn·f) / (r (r+eps)^2)
         const float k2 = dot * i0 * i0 / fmaxf(r0, 1e-20f);
+        if (ok) {
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
-            if (i < nper) {
-                const int c = (i / 2) * 64 + 2 * lane;
-                const float g_lo = a[i] > 0.f ? gn[i] * i0 - a[i] * k2 : 0.f;
-                const float g_hi = a[i + 1] > 0.f ? gn[i + 1] * i0 - a[i + 1] * k2 : 0.f;
-                *reinterpret_cast<uint32_t*>(g0 + pix * C + c) = pack_bf16x2(g_lo, g_hi);
+            for (int v = 0; v < V; ++v) {
+                float g[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) g[k] = a[v][k] > 0.f ? gn[v][k] * i0 - a[v][k] * k2 : 0.f;
+                uint4 o;
+                o.x = pack_bf16x2(g[0], g[1]), o.y = pack_bf16x2(g[2], g[3]);
+                o.z = pack_bf16x2(g[4], g[5]), o.w = pack_bf16x2(g[6], g[7]);
+                *reinterpret_cast<uint4*>(g0 + pix * C + (v * LPP + li) * 8) = o;
             }
         }
     }
+    local = warp_sum(local);
     if (lane == 0 && local != 0.f) atomicAdd(loss_acc, coef * local);
 }
 
@@ -245,8 +273,16 @@ extern "C" int vtp_pool_relu_bwd(const void* y, const void* dpool, const void* g
 extern "C" int vtp_lpips_tap(const void* f0, const void* f1, const float* w, void* g0, long P, int C, float coef,
                              float* loss_acc, vtp_stream_t st) {
     VTP_CHECK_ARG(f0 && f1 && w && g0 && loss_acc && P > 0 && C % 64 == 0 && C <= 512, "lpips_tap: bad args (C %% 64, C <= 512)");
-    lpips_tap_kernel<<<gridn(P * 32, 256), 256, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)f0, (const __nv_bfloat16*)f1, w,
-                                                                      (__nv_bfloat16*)g0, P, C, coef, loss_acc);
+    const __nv_bfloat16 *a0 = (const __nv_bfloat16*)f0, *a1 = (const __nv_bfloat16*)f1;
+    __nv_bfloat16* g = (__nv_bfloat16*)g0;
+    cudaStream_t stream = (cudaStream_t)st;
+    switch (C) {
+        case 64: lpips_tap_kernel<8, 1><<<gridn(P * 8, 256), 256, 0, stream>>>(a0, a1, w, g, P, coef, loss_acc); break;
+        case 128: lpips_tap_kernel<16, 1><<<gridn(P * 16, 256), 256, 0, stream>>>(a0, a1, w, g, P, coef, loss_acc); break;
+        case 256: lpips_tap_kernel<32, 1><<<gridn(P * 32, 256), 256, 0, stream>>>(a0, a1, w, g, P, coef, loss_acc); break;
+        case 512: lpips_tap_kernel<32, 2><<<gridn(P * 32, 256), 256, 0, stream>>>(a0, a1, w, g, P, coef, loss_acc); break;
+        default: VTP_FAIL(VTP_ERR_ARG, "lpips_tap: C = %d not in {64, 128, 256, 512}", C);
+    }
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

@@ -128,11 +128,9 @@ def _tower_views(store: ParamStore, pre: str, tw: TowerW, depth: int, hidden: in
 def wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor, Mtok: int):
     """dW[N_out, K_in] += dYᵀ X  (dY [Mtok, N_out] bf16, X [Mtok, K_in] bf16): TN GEMM, split-K + fp32 atomics."""
     n_out, k_in = dw.shape
-    tiles = ((n_out + 127) // 128) * ((k_in + 127) // 128)
-    nkb = (Mtok + 63) // 64
-    split = max(1, min(nkb // 4 if nkb >= 8 else 1, (2 * 148 + tiles - 1) // tiles))
+    # split_k = -1: the library picks the split that fills its persistent grid most evenly for the tile shape it chose
     lib.gemm(dy, x, dw, M=n_out, N=k_in, K=Mtok, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0), ldo=k_in,
-             accumulate=True, split_k=split, round_bf16=False)
+             accumulate=True, split_k=-1, round_bf16=False)
 
 
 def dgrad(dy: torch.Tensor, w: torch.Tensor, out: torch.Tensor, Mtok: int, **kw):
