@@ -49,3 +49,32 @@ def test_conv_mode_gemm_matches_conv2d():
     ref2 = torch.nn.functional.conv2d(x2.float().permute(0, 3, 1, 2), w.float(), None, padding=1).permute(0, 2, 3, 1)
     ref2 = ref2 * (m2.float() > 0)
     assert rel(y2, ref2) < 5e-3
+
+
+@pytest.mark.parametrize("variant", ["default", "VTP_GEMM_CONV_NO_FAST", "VTP_GEMM_CONV_NO_CLUSTER"])
+@pytest.mark.parametrize("B,H,W,Ci,Co,mask", [(1, 24, 16, 64, 64, False), (3, 8, 8, 128, 256, True), (2, 32, 32, 64, 64, True),
+                                              (5, 16, 16, 256, 512, False), (1, 8, 8, 512, 512, True)])
+def test_conv_mode_variants(monkeypatch, variant, B, H, W, Ci, Co, mask):
+    """Implicit 3x3 conv GEMM through the TMA-store epilogue (4-D NHWC tensor map) on clustered / single-CTA kernels:
+    odd tile counts (padded pair tile), Cout < tile width, bias+ReLU forward form and masked dgrad form."""
+    if variant != "default":
+        monkeypatch.setenv(variant, "1")
+    g = torch.Generator(device="cuda").manual_seed(B * 100 + Ci)
+    x = (torch.randn(B, H, W, Ci, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(Co, Ci, 3, 3, device="cuda", generator=g) * (2.0 / (9 * Ci)) ** 0.5).to(torch.bfloat16)
+    wk = w.permute(0, 2, 3, 1).reshape(Co, 9 * Ci).contiguous()
+    y = torch.full((B, H, W, Co), float("nan"), device="cuda", dtype=torch.bfloat16)
+    conv = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, padding=1).permute(0, 2, 3, 1)
+    if mask:
+        m = torch.randn(B, H, W, Co, device="cuda", generator=g).to(torch.bfloat16)
+        lib.gemm(x, wk, y, M=B * H * W, N=Co, K=9 * Ci, lda=Ci, ldb=9 * Ci, ldo=Co, conv=(Ci, H, W), round_bf16=False,
+                 mask_pos=m)
+        ref = conv * (m.float() > 0)
+    else:
+        b = torch.randn(Co, device="cuda", generator=g) * 0.1
+        lib.gemm(x, wk, y, M=B * H * W, N=Co, K=9 * Ci, lda=Ci, ldb=9 * Ci, bias=b, act=lib.ACT_RELU, ldo=Co,
+                 conv=(Ci, H, W))
+        ref = torch.relu(conv + b)
+    torch.cuda.synchronize()
+    assert torch.isfinite(y.float()).all()
+    assert rel(y, ref) < 5e-3, rel(y, ref)

@@ -33,10 +33,12 @@ def timed(name, fn):
         l0 = lib.LAUNCHES
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        c0 = time.perf_counter()
         fn()
+        cpu_ms = (time.perf_counter() - c0) * 1e3   # host time to enqueue everything (>= GPU time means launch-bound)
         e1.record()
         torch.cuda.synchronize()
-        print(f"{name:10s} rep{i}: {e0.elapsed_time(e1):8.1f} ms  launches {lib.LAUNCHES-l0:5d}  "
+        print(f"{name:10s} rep{i}: {e0.elapsed_time(e1):8.1f} ms  host enqueue {cpu_ms:7.1f} ms  launches {lib.LAUNCHES-l0:5d}  "
               f"peak mem {torch.cuda.max_memory_allocated()/2**30:.1f} GiB", flush=True)
 
 

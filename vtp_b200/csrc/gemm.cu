@@ -42,7 +42,7 @@ struct GemmDev {
     __nv_bfloat16* out2;
     int ldo2;
     // implicit 3x3 / pad-1 convolution over an NHWC activation (A operand loaded by 4-D TMA, zero fill = padding)
-    int conv_C, conv_H, conv_W, conv_TW, conv_TH, conv_tiles_h, conv_tiles_w;
+    int conv_C, conv_H, conv_W, conv_TW, conv_TH, conv_tiles_h, conv_tiles_w, conv_B;
     const __nv_bfloat16* mask_pos;  // optional: out *= (mask_pos[row][col] > 0)   (ReLU backward in the dgrad epilogue)
     int ldm;
     int dbg;  // DIAG bits: 1 no global stores, 2 no tmem ld, 4 no epilogue work, 8 no MMA issue
@@ -69,7 +69,7 @@ __device__ __forceinline__ long out_row(const GemmDev& p, int grow) {
         const int tx = m_blk % p.conv_tiles_w, ty = (m_blk / p.conv_tiles_w) % p.conv_tiles_h;
         const int b = m_blk / (p.conv_tiles_w * p.conv_tiles_h);
         const int h = ty * p.conv_TH + r / p.conv_TW, w = tx * p.conv_TW + r % p.conv_TW;
-        return (h < p.conv_H && w < p.conv_W) ? ((long)b * p.conv_H + h) * p.conv_W + w : -1;
+        return (h < p.conv_H && w < p.conv_W && b < p.conv_B) ? ((long)b * p.conv_H + h) * p.conv_W + w : -1;
     }
     if (grow >= p.M) return -1;
     if (p.rr_group <= 0) return grow;
@@ -357,7 +357,10 @@ __device__ __forceinline__ void epilogue_unit(const GemmDev& p, float* stg, int 
 // 4 KB SWIZZLE_128B staging tile and leaves through ONE TMA store (clipped at the M / N tails by the tensor map);
 // bias comes from a 256-byte per-warp shared tile (broadcast reads), the residual is fetched into registers one chunk
 // ahead, before the accumulator is waited for.
-//   FAST: 1 bf16 out, 2 bf16 out + bf16 residual, 3 fp32 out, 4 fp32 out + fp32 residual.   ACT: NONE | RELU.
+//   FAST: 1 bf16 out, 2 bf16 out + bf16 residual, 3 fp32 out, 4 fp32 out + fp32 residual, 5 bf16 out masked by
+//   (mask_pos > 0) (ReLU backward of the LPIPS dgrads).   ACT: NONE | RELU.
+// Implicit-conv GEMMs (tile = conv_TH x conv_TW pixel patch of one image) store through a 4-D NHWC tensor map: the warp's
+// 32 rows are 32 / conv_TW image rows of conv_TW pixels.
 // hand the accumulator buffer back to the MMA issuer: with cta_group::2 the issuer lives in the leader CTA (rank 0)
 template <bool G2>
 __device__ __forceinline__ void arrive_tempty(uint64_t* bar) {
@@ -367,18 +370,31 @@ __device__ __forceinline__ void arrive_tempty(uint64_t* bar) {
 
 template <int BN, int ACT, int FAST, bool G2>
 __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUtensorMap* tmO, uint8_t* stg, float* bias_s,
-                                                   int lane, int q, int hsel, uint32_t taddr, int m0, int n0,
+                                                   int lane, int q, int hsel, uint32_t taddr, int m_blk, int n0,
                                                    uint64_t* tfull, uint32_t aph, uint64_t* tempty) {
-    constexpr bool OF32 = FAST >= 3;
-    constexpr bool RES = FAST == 2 || FAST == 4;
+    constexpr bool OF32 = FAST == 3 || FAST == 4;
+    constexpr bool MASK = FAST == 5;
+    constexpr bool RES = FAST == 2 || FAST == 4 || MASK;  // a second [M][N]-shaped operand read one chunk ahead
+    const int m0 = m_blk * BM;
     constexpr int CW = OF32 ? 32 : 64;   // accumulator columns per 128-byte output chunk
     constexpr int TCH = BN / CW;         // chunks per tile row
     constexpr int NCH = (TCH + 1) / 2;   // chunks per warp and tile (the two warps of a lane quarter interleave)
     constexpr int PW = OF32 ? 4 : 8;     // columns per 16-byte piece
     const int N = p.N;
-    const long row = (long)m0 + q * 32 + lane;
-    const bool row_ok = row < p.M;
-    const char* rrow = RES ? reinterpret_cast<const char*>(p.resid) + row * (long)p.ldr * (OF32 ? 4 : 2) : nullptr;
+    long row = (long)m0 + q * 32 + lane;
+    bool row_ok = row < p.M;
+    int ctx = 0, cty = 0, cb = 0;  // conv: tile coordinates
+    if (p.conv_C) {
+        ctx = m_blk % p.conv_tiles_w, cty = (m_blk / p.conv_tiles_w) % p.conv_tiles_h;
+        cb = m_blk / (p.conv_tiles_w * p.conv_tiles_h);
+        const int r = q * 32 + lane;
+        const int h = cty * p.conv_TH + r / p.conv_TW, w = ctx * p.conv_TW + r % p.conv_TW;
+        row = ((long)cb * p.conv_H + h) * p.conv_W + w;
+        row_ok = h < p.conv_H && cb < p.conv_B;
+    }
+    const char* rrow = !RES ? nullptr
+                       : MASK ? reinterpret_cast<const char*>(p.mask_pos) + row * (long)p.ldm * 2
+                              : reinterpret_cast<const char*>(p.resid) + row * (long)p.ldr * (OF32 ? 4 : 2);
 
     float b0n = 0.f, b1n = 0.f;
     uint4 rr[8];
@@ -461,9 +477,17 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
                     uint4 w;
                     w.x = pack_bf16x2(v[0], v[1]), w.y = pack_bf16x2(v[2], v[3]);
                     w.z = pack_bf16x2(v[4], v[5]), w.w = pack_bf16x2(v[6], v[7]);
-                    if (RES)
+                    if (MASK) {  // keep x where the forward activation was > 0 (bf16: sign bit clear, non-zero)
+                        auto keep = [](uint32_t x, uint32_t mm) {
+                            const uint32_t lo = ((mm & 0x7FFFu) != 0u && (mm & 0x8000u) == 0u) ? 0x0000FFFFu : 0u;
+                            const uint32_t hi = ((mm & 0x7FFF0000u) != 0u && (mm & 0x80000000u) == 0u) ? 0xFFFF0000u : 0u;
+                            return x & (lo | hi);
+                        };
+                        w.x = keep(w.x, rr[i].x), w.y = keep(w.y, rr[i].y), w.z = keep(w.z, rr[i].z), w.w = keep(w.w, rr[i].w);
+                    } else if (RES) {
                         w.x = add_bf16x2(w.x, rr[i].x), w.y = add_bf16x2(w.y, rr[i].y), w.z = add_bf16x2(w.z, rr[i].z),
                         w.w = add_bf16x2(w.w, rr[i].w);
+                    }
                     *reinterpret_cast<uint4*>(stg + stgb_off(lane, i)) = w;
                 }
             }
@@ -471,7 +495,8 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0 && !(p.dbg & 1)) {
-                tma_store_2d(tmO, stg, col0, m0 + q * 32);
+                if (p.conv_C) tma_store_4d(tmO, stg, col0, ctx * p.conv_TW, cty * p.conv_TH + q * (32 / p.conv_TW), cb);
+                else tma_store_2d(tmO, stg, col0, m0 + q * 32);
                 bulk_commit();
             }
         }
@@ -673,7 +698,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE;
             if constexpr (FAST != 0) {
                 fast_epilogue_tile<BN, ACT, FAST, G2>(p, &tmO, reinterpret_cast<uint8_t*>(stg), bias_base + (warp - 2) * 64, lane,
-                                                  q, hsel, taddr, m0, n0, &tfull_bar[as], aph, &tempty_bar[as]);
+                                                  q, hsel, taddr, m_blk, n0, &tfull_bar[as], aph, &tempty_bar[as]);
                 if (++as == 2) as = 0, aph ^= 1;
                 continue;
             }
@@ -808,21 +833,22 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     int BN = (pad256 * 8 <= pad128 * 9) ? 256 : 128;  // accept <= 12.5 % padding for the higher-intensity tile
     // 2-CTA multicast variant whenever there are at least two m-blocks (odd counts are padded with an all-OOB tile)
     const bool allow_cl2 = getenv("VTP_GEMM_NO_CLUSTER") == nullptr;
-    const bool cl2 = allow_cl2 && !conv && ceil_div(a->M, BM) >= 2;
+    const bool cl2 = allow_cl2 && ceil_div(a->M, BM) >= 2 && !(conv && getenv("VTP_GEMM_CONV_NO_CLUSTER"));
     // cta_group::2 (256 x BN pair tiles) wherever the 2-CTA cluster applies
     // measured (tools/gemm_diag.py): within 3 % of the TMA-multicast variant, slightly behind on every shape (both are
     // bound by L2->SM reads, which the two variants issue identically), so it is opt-in
     const bool g2 = cl2 && getenv("VTP_GEMM_G2") != nullptr;
     // lean TMA-store epilogue for the recurring shapes (see fast_epilogue_tile)
     const bool allow_fast = getenv("VTP_GEMM_NO_FAST") == nullptr;
-    const bool fast = allow_fast && !conv && a->rr_group == 0 && a->ps_r == 0 && !a->out2 && !a->mask_pos && !a->accumulate &&
-                      split_k == 1 && (a->act == VTP_ACT_NONE || a->act == VTP_ACT_RELU) &&
+    const bool fast_conv = conv && a->out_dtype == VTP_BF16 && !a->resid && getenv("VTP_GEMM_CONV_NO_FAST") == nullptr;
+    const bool fast = allow_fast && (!conv || fast_conv) && a->rr_group == 0 && a->ps_r == 0 && !a->out2 &&
+                      (!a->mask_pos || fast_conv) && !a->accumulate && split_k == 1 &&
+                      (a->act == VTP_ACT_NONE || (a->act == VTP_ACT_RELU && !a->mask_pos)) &&
                       (!a->resid || a->resid_dtype == a->out_dtype);
-    // N = 384-type widths: 192-wide tiles halve nothing but re-read A twice instead of three times (112 vs 87 flop per
-    // L2 byte for the pair tile) and leave no padding
     const bool plain_acc = !fast && !g2 && !conv && a->accumulate && a->act == VTP_ACT_NONE && a->ps_r == 0 &&
                            a->rr_group == 0 && !a->out2 && !a->mask_pos && !a->resid;  // wgrad: split-K + fp32 red.add
-    if ((fast || plain_acc) && !g2 && BN == 128 && a->N % 192 == 0 && getenv("VTP_GEMM_NO_BN192") == nullptr) BN = 192;
+    if ((fast || plain_acc) && !g2 && !a->mask_pos && BN == 128 && a->N % 192 == 0 && getenv("VTP_GEMM_NO_BN192") == nullptr)
+        BN = 192;
     if (auto_split) {
         // fill the persistent grid (148 CTAs, or 74 CTA pairs) as evenly as possible: the split with the best wave
         // efficiency among those that keep >= 8 k-blocks per work item
@@ -869,7 +895,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     CUtensorMap tmA, tmB;
     if (conv) {
         const int W = a->conv_W, H = a->conv_H, Cc = a->conv_C, Bimg = a->M / (H * W);
-        p.conv_C = Cc, p.conv_H = H, p.conv_W = W;
+        p.conv_C = Cc, p.conv_H = H, p.conv_W = W, p.conv_B = Bimg;
         p.conv_TW = (W % 16 == 0) ? 16 : (W % 8 == 0 ? 8 : 4);
         p.conv_TH = 128 / p.conv_TW;
         p.conv_tiles_w = W / p.conv_TW, p.conv_tiles_h = ceil_div(H, p.conv_TH);
@@ -905,11 +931,26 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     if (fast) {
         CUtensorMap tmO;
         const int esz = a->out_dtype == VTP_F32 ? 4 : 2;
-        uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldo * esz};
-        uint32_t box[2] = {(uint32_t)(128 / esz), 32};
-        int rc = make_tmap(&tmO, a->out, a->out_dtype, 2, dims, strides, box);
+        int rc;
+        if (conv) {  // NHWC output: the warp's 32 rows are 32 / TW image rows of TW pixels
+            uint64_t dims[4] = {(uint64_t)a->N, (uint64_t)p.conv_W, (uint64_t)p.conv_H, (uint64_t)p.conv_B};
+            uint64_t strides[3] = {(uint64_t)a->ldo * 2, (uint64_t)p.conv_W * a->ldo * 2, (uint64_t)p.conv_H * p.conv_W * a->ldo * 2};
+            uint32_t box[4] = {64, (uint32_t)p.conv_TW, (uint32_t)(32 / p.conv_TW), 1};
+            rc = make_tmap(&tmO, a->out, VTP_BF16, 4, dims, strides, box);
+        } else {
+            uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldo * esz};
+            uint32_t box[2] = {(uint32_t)(128 / esz), 32};
+            rc = make_tmap(&tmO, a->out, a->out_dtype, 2, dims, strides, box);
+        }
         if (rc) return rc;
-        const int mode = (a->out_dtype == VTP_F32 ? 3 : 1) + (a->resid ? 1 : 0);
+        const int mode = a->mask_pos ? 5 : (a->out_dtype == VTP_F32 ? 3 : 1) + (a->resid ? 1 : 0);
+        if (mode == 5) {  // LPIPS dgrad with the ReLU mask: bf16 out, no bias / activation
+            if (cl2)
+                return (BN == 256) ? launch_gemm<256, 4, VTP_ACT_NONE, false, true, 1, 5>(tmA, tmB, p, stream, &tmO)
+                                   : launch_gemm<128, 6, VTP_ACT_NONE, false, true, 1, 5>(tmA, tmB, p, stream, &tmO);
+            return (BN == 256) ? launch_gemm<256, 4, VTP_ACT_NONE, false, false, 1, 5>(tmA, tmB, p, stream, &tmO)
+                               : launch_gemm<128, 6, VTP_ACT_NONE, false, false, 1, 5>(tmA, tmB, p, stream, &tmO);
+        }
 #define VTP_FAST_CFG(ACT_, MODE_)                                                                                     \
     do { /* one CTA per SM with the deep ring: measured faster than 2 x (2-stage) once the epilogue is lean */        \
         if (g2)                                                                                                       \
