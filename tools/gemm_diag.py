@@ -50,8 +50,7 @@ cases = [
     ("fc2+res    N384  K1024 f32", 2 * M * D * Hs, lambda: lib.gemm(xh, W3, stream, M=M, N=D, K=Hs, bias=bd, resid=stream),
      lambda: torch.mm(xh, W3.t(), out=o_d)),
 ]
-variants = [("default (g2)", {}), ("no-g2 (multicast)", {"VTP_GEMM_NO_G2": "1"}),
-            ("g2 dbg4 noepi", {"VTP_GEMM_DBG": "4"}), ("g2 dbg12 neither", {"VTP_GEMM_DBG": "12"})]
+variants = [("default (TMA store)", {}), ("dbg16 LSU store", {"VTP_GEMM_DBG": "16"}), ("dbg1 no store", {"VTP_GEMM_DBG": "1"})]
 KEYS = ["VTP_GEMM_DBG", "VTP_GEMM_NO_CLUSTER", "VTP_GEMM_NO_2PERSM", "VTP_GEMM_NO_FAST", "VTP_GEMM_NO_G2"]
 print(f"M = {M}   (us per launch; TFLOP/s in brackets for the full-work variants)")
 print(f"{'variant':18s}" + "".join(f"{c[0]:>30s}" for c in cases))

@@ -48,3 +48,54 @@ def to_device(batch: Dict[str, torch.Tensor], device, non_blocking: bool = True)
 
 def batch_bytes(batch: Dict[str, torch.Tensor]) -> int:
     return sum(v.numel() * v.element_size() for v in batch.values())
+
+
+class BatchPrefetcher:
+    """Host -> device input pipeline of the training loop: the pinned host batch of step i+1 is copied on a side
+    stream while step i computes (what a pinned-memory DataLoader + `non_blocking` prefetch does around the reference).
+
+        pf = BatchPrefetcher(device); pf.put(host_batch)
+        for ...:
+            batch, slot = pf.get(); pf.put(next_host_batch)
+            loss = trainer.train_step(batch); pf.release(slot)
+
+    `depth` device buffers rotate; a buffer is overwritten only after the step that consumed it (event recorded by
+    `release`) and is handed out only after its copy landed (event recorded by `put`)."""
+
+    def __init__(self, device, depth: int = 2):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.depth = depth
+        self.buffers = [None] * depth
+        self.copied = [None] * depth   # event: H2D copy of this slot finished
+        self.freed = [None] * depth    # event: the step that used this slot finished
+        self.queue = []
+        self.next_slot = 0
+
+    def put(self, host_batch: Dict[str, torch.Tensor]) -> None:
+        slot = self.next_slot
+        self.next_slot = (slot + 1) % self.depth
+        assert slot not in self.queue, "prefetch depth exceeded: get() a batch before putting another"
+        with torch.cuda.stream(self.stream):
+            if self.freed[slot] is not None:
+                self.stream.wait_event(self.freed[slot])
+            buf = self.buffers[slot]
+            if buf is None or any(buf[k].shape != v.shape or buf[k].dtype != v.dtype for k, v in host_batch.items()):
+                buf = {k: torch.empty(v.shape, dtype=v.dtype, device=self.device) for k, v in host_batch.items()}
+                self.buffers[slot] = buf
+            for k, v in host_batch.items():
+                buf[k].copy_(v, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+            self.copied[slot] = ev
+        self.queue.append(slot)
+
+    def get(self):
+        slot = self.queue.pop(0)
+        torch.cuda.current_stream(self.device).wait_event(self.copied[slot])
+        return self.buffers[slot], slot
+
+    def release(self, slot: int) -> None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.freed[slot] = ev
