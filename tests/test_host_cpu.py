@@ -86,3 +86,16 @@ def test_rope_table_matches_oracle():
     s, c = rope_sincos(16, 16, per)
     so, co = vo.rope_table(16, 16, per)
     assert torch.equal(s, so) and torch.equal(c, co) and s.dtype == torch.bfloat16
+
+
+def test_compat_shim_serves_reference_import_path():
+    """`from vtp.models.vtp_hf import VTPModel` (tools/test_reconstruction_hf.py:37) resolves to this implementation when
+    <repo>/compat is first on the path; the rest of the `vtp` namespace is left to the reference checkout."""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r); sys.path.insert(0, %r); "
+            "from vtp.models.vtp_hf import VTPModel, VTPConfig, VTPPreTrainedModel; "
+            "import vtp_b200.model as m; assert VTPModel is m.VTPModel and issubclass(VTPModel, VTPPreTrainedModel); "
+            "c = VTPConfig(); assert c.model_type == 'vtp'; print('ok')") % (ROOT, os.path.join(ROOT, "compat"))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
