@@ -196,6 +196,37 @@ int vtp_lpips_tap(const void* f0, const void* f1, const float* w, void* g0, long
 /* col2im of the conv1_1 input gradient + ScalingLayer backward: bf16 [B*H*W][32] -> fp32 NCHW d(image) */
 int vtp_lpips_img_grad(const void* dcol, float* dimg, int B, int H, int W, vtp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Contrastive exchange over NVLink peer memory (vtp_b200/csrc/clip.cu): collective C2 of SURVEY.md §8e — the feature
+ * all-gather that OpenCLIP's ClipLoss performs before vtp_hf/modeling_vtp.py:329's logits — fused with the logits, the
+ * logit-scale softmax-CE and the gradient matrices.  No backward collective is needed (every rank holds the full
+ * Bg x Bg similarity matrix).
+ * ------------------------------------------------------------------------------------------------------------ */
+/* img_ptrs/txt_ptrs: HOST arrays of `world` device pointers (own + IPC-mapped peers) to L2-normalised bf16 features
+ * [B][E].  One kernel: gather through peer memory + S = I_all·T_allᵀ fp32 [world*B][ld] and St = Sᵀ; fi_all/ft_all bf16
+ * [world*B][E] receive the gathered features. */
+int vtp_clip_gather_logits(const void* const* img_ptrs, const void* const* txt_ptrs, int world, int B, int E, float* S,
+                           float* St, long ld, void* fi_all, void* ft_all, vtp_stream_t stream);
+/* lse[0][r] / lse[1][r] = logsumexp_c exp(*log_scale)·S[r][c] / ·St[r][c] for all Bg rows; rows [row0,row0+B) add
+ * coef·(lse − logit[r][r]) to *loss_acc and Σ_c g·logit to *dscale_acc (g = coef (softmax − onehot)) */
+int vtp_clip_lse(const float* S, const float* St, long ld, int Bg, int row0, int B, const float* log_scale, float coef,
+                 float* lse, float* loss_acc, float* dscale_acc, vtp_stream_t stream);
+/* dMi / dMt bf16 [B][Bgp]: d(Σ_ranks L_local)/dS (resp. /dSt) rows [row0,row0+B): row-direction softmax term +
+ * column-direction softmax term − 2·onehot, times coef·exp(*log_scale); columns [Bg,Bgp) zero.
+ * Then dI_local = dMi·T_all and dT_local = dMt·I_all (vtp_gemm_bf16, b_mn_major). */
+int vtp_clip_grad(const float* S, const float* St, long ld, int Bg, int Bgp, int row0, int B, const float* log_scale,
+                  float coef, const float* lse, void* dMi, void* dMt, vtp_stream_t stream);
+/* Peer-memory plumbing (set-up time only; the ONLY entry points that allocate / synchronise): a zeroed cudaMalloc
+ * buffer, its 64-byte CUDA IPC handle, mapping of a peer's handle, and a flag barrier over the ranks' signal pads
+ * (pad_ptrs: HOST array of `world` device pointers to uint64[world] pads; epoch strictly increasing; *err_flag = 1 if
+ * a peer did not arrive within ~20 s). */
+int vtp_comm_alloc(long bytes, void** ptr);
+int vtp_comm_free(void* ptr);
+int vtp_comm_get_handle(void* ptr, unsigned char* handle64);
+int vtp_comm_open_handle(const unsigned char* handle64, void** peer_ptr);
+int vtp_comm_close_handle(void* peer_ptr);
+int vtp_comm_barrier(const void* const* pad_ptrs, int world, int rank, long epoch, int* err_flag, vtp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,10 +15,12 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, formulation="sharded"):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from oracle.dist_clip import sharded_clip_feature_grads
+    from oracle import dist_clip
+
+    sharded_clip_feature_grads = getattr(dist_clip, f"{formulation}_clip_feature_grads")
 
     torch.manual_seed(0)
     Bg, E = 8, 16
@@ -36,11 +38,17 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_sharded_clip_equals_global_batch():
+import pytest
+
+
+@pytest.mark.parametrize("formulation", ["sharded", "replicated"])
+def test_sharded_clip_equals_global_batch(formulation):
+    """sharded = NCCL path (local-row logits + all-reduced cross terms); replicated = peer-memory path (full logits on
+    every rank, forward gather only — csrc/clip.cu)."""
     world, port = 2, _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, formulation), nprocs=world, join=True)
     from oracle import vtp_oracle as vo
 
     torch.manual_seed(0)

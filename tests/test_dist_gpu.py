@@ -15,7 +15,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, exchange="nccl"):
     import torch.distributed as dist
 
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
@@ -29,7 +29,7 @@ def _worker(rank, world, port, out):
     meta, _ = load_golden("tiny")
     cfg = VTPConfig(**meta["config"])
     sd = seeded_state_dict(meta["spec"], seed=0)
-    tc = TrainConfig(head_out_dim=512, head_hidden=256, head_bottleneck=64, n_local_crops=2)
+    tc = TrainConfig(head_out_dim=512, head_hidden=256, head_bottleneck=64, n_local_crops=2, clip_exchange=exchange)
     Bg = 8
     B = Bg // world
     x = seeded_images(Bg, 64, 64).cuda()
@@ -40,6 +40,8 @@ def _worker(rank, world, port, out):
     tr.clip_fwd_bwd(x[sl].contiguous(), ids[sl].contiguous(), 1.0)
     tr.rec_fwd_bwd(x[sl].contiguous(), 1.0)
     tr.allreduce_grads()
+    if exchange == "p2p":
+        tr.peer.check()                      # the flag barriers did not time out
     g = (tr.store.g / world).cpu()
     loss = tr.loss_acc.clone()
     dist.all_reduce(loss)
@@ -62,13 +64,15 @@ def _worker(rank, world, port, out):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_rank_step_equals_global_batch():
+@pytest.mark.parametrize("exchange", ["nccl", "p2p"])
+def test_two_rank_step_equals_global_batch(exchange):
+    """nccl: all-gather + all-reduced cross terms; p2p: peer-memory gather fused with the logits (csrc/clip.cu)."""
     import torch.multiprocessing as mp
 
     world, port = 2, _free_port()
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, out, exchange), nprocs=world, join=True)
     for r in range(world):
         rel, pdiff, loss, loss_ref = out[r]
         assert rel < 2e-2, rel                 # bf16 noise: different batch tiling of the same math

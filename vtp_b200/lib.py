@@ -99,6 +99,18 @@ SIGNATURES: dict[str, tuple] = {
     "vtp_lpips_img_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vtp_recon_l1_grad": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
                                     C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "vtp_clip_gather_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_long,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vtp_clip_lse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vtp_clip_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vtp_comm_alloc": (C.c_int, [C.c_long, C.POINTER(C.c_void_p)]),
+    "vtp_comm_free": (C.c_int, [C.c_void_p]),
+    "vtp_comm_get_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "vtp_comm_open_handle": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "vtp_comm_close_handle": (C.c_int, [C.c_void_p]),
+    "vtp_comm_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -120,9 +132,9 @@ def load() -> C.CDLL:
 LAUNCHES = 0  # number of C-ABI kernel launches issued by this process (every entry point launches exactly one kernel)
 
 
-def check(status: int, what: str = "") -> None:
+def check(status: int, what: str = "", launch: bool = True) -> None:
     global LAUNCHES
-    if what != "vtp_check_device":
+    if launch and what != "vtp_check_device":
         LAUNCHES += 1
     if status != 0:
         msg = load().vtp_last_error()
@@ -365,3 +377,56 @@ def swiglu_fwd(pre, hid, M: int, Hs: int, stream=None):
 
 def rope_fwd(qkv, sin, cos, rows: int, T: int, prefix: int, D: int, stream=None):
     check(load().vtp_rope_fwd(_ptr(qkv), _ptr(sin), _ptr(cos), rows, T, prefix, D, _st(stream)), "vtp_rope_fwd")
+
+
+# ------------------------------------------------------------------------------------------------ contrastive exchange
+def _ptr_array(ptrs):
+    return (C.c_void_p * len(ptrs))(*[int(p) for p in ptrs])
+
+
+def clip_gather_logits(img_ptrs, txt_ptrs, B: int, E: int, S, St, fi_all, ft_all, stream=None):
+    """img_ptrs / txt_ptrs: per-rank device addresses (ints) of the L2-normalised bf16 features [B, E]."""
+    world = len(img_ptrs)
+    check(load().vtp_clip_gather_logits(_ptr_array(img_ptrs), _ptr_array(txt_ptrs), world, B, E, _ptr(S), _ptr(St),
+                                        S.stride(0), _ptr(fi_all), _ptr(ft_all), _st(stream)), "vtp_clip_gather_logits")
+
+
+def clip_lse(S, St, Bg: int, row0: int, B: int, log_scale, coef: float, lse, loss_acc, dscale_acc=None, stream=None):
+    check(load().vtp_clip_lse(_ptr(S), _ptr(St), S.stride(0), Bg, row0, B, _ptr(log_scale), coef, _ptr(lse), _ptr(loss_acc),
+                              _ptr(dscale_acc), _st(stream)), "vtp_clip_lse")
+
+
+def clip_grad(S, St, Bg: int, row0: int, B: int, log_scale, coef: float, lse, dMi, dMt, stream=None):
+    check(load().vtp_clip_grad(_ptr(S), _ptr(St), S.stride(0), Bg, dMi.stride(0), row0, B, _ptr(log_scale), coef, _ptr(lse),
+                               _ptr(dMi), _ptr(dMt), _st(stream)), "vtp_clip_grad")
+
+
+def comm_alloc(nbytes: int) -> int:
+    p = C.c_void_p()
+    check(load().vtp_comm_alloc(nbytes, C.byref(p)), "vtp_comm_alloc", launch=False)
+    return int(p.value)
+
+
+def comm_free(ptr: int) -> None:
+    check(load().vtp_comm_free(ptr), "vtp_comm_free", launch=False)
+
+
+def comm_get_handle(ptr: int) -> bytes:
+    buf = C.create_string_buffer(64)
+    check(load().vtp_comm_get_handle(ptr, buf), "vtp_comm_get_handle", launch=False)
+    return buf.raw
+
+
+def comm_open_handle(handle: bytes) -> int:
+    p = C.c_void_p()
+    check(load().vtp_comm_open_handle(C.create_string_buffer(handle, 64), C.byref(p)), "vtp_comm_open_handle", launch=False)
+    return int(p.value)
+
+
+def comm_close_handle(ptr: int) -> None:
+    check(load().vtp_comm_close_handle(ptr), "vtp_comm_close_handle", launch=False)
+
+
+def comm_barrier(pad_ptrs, rank: int, epoch: int, err_flag, stream=None):
+    check(load().vtp_comm_barrier(_ptr_array(pad_ptrs), len(pad_ptrs), rank, epoch, _ptr(err_flag), _st(stream)),
+          "vtp_comm_barrier")

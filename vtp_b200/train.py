@@ -201,6 +201,9 @@ class TrainConfig:
     w_ssl: float = 1.0
     w_rec: float = 1.0
     lpips_weight: float = 1.0
+    # contrastive exchange (collective C2): "nccl" = all-gather + local-row logits + all-reduced cross terms;
+    # "p2p" = peer-memory gather fused with the full logits / softmax-CE (csrc/clip.cu), no backward collective
+    clip_exchange: str = "nccl"
 
 
 class VTPTrainer:
@@ -249,6 +252,7 @@ class VTPTrainer:
         self._build_towers()
         self.step_count = 0
         self.lpips = None  # perceptual term of the reconstruction loss, see enable_lpips()
+        self.peer = None   # peer-memory exchange buffers of the contrastive objective (clip_exchange == "p2p")
         self.loss_acc = torch.zeros(8, dtype=F32, device=self.device)  # clip, dino_local, dino_global, ibot, rec
         self.center_dino = torch.zeros(K, dtype=F32, device=self.device)
         self.center_ibot = torch.zeros(K, dtype=F32, device=self.device)
@@ -469,12 +473,16 @@ class VTPTrainer:
         fi_raw = _e((B, Dt), BF, dev)
         lib.gemm(cls, vp.w, fi_raw, M=B, N=Dt, K=D)
         nrm_i = _e((B,), F32, dev)
-        fi = torch.empty_like(fi_raw)
-        lib.l2norm_fwd(fi_raw, fi, B, Dt, 1e-12, norm_out=nrm_i)
         # ---- text tower
         tp_t = {}
         ft_raw = E.text_forward(Wt, text, "bf16", tape=tp_t)
         nrm_t = _e((B,), F32, dev)
+        if self._clip_exchange() == "p2p":
+            dfi, dft = self._clip_loss_p2p(fi_raw, ft_raw, nrm_i, nrm_t, B, weight)
+            self._clip_backward(tp_i, tp_t, x, nt, cls, self.peer.img, self.peer.txt, nrm_i, nrm_t, dfi, dft, text, B, T)
+            return
+        fi = torch.empty_like(fi_raw)
+        lib.l2norm_fwd(fi_raw, fi, B, Dt, 1e-12, norm_out=nrm_i)
         ft = torch.empty_like(ft_raw)
         lib.l2norm_fwd(ft_raw, ft, B, Dt, 1e-12, norm_out=nrm_t)
         # ---- contrastive loss over the global batch (features all-gathered: collective C2)
@@ -517,6 +525,57 @@ class VTPTrainer:
         else:
             lib.gemm(Gt_, ft, dfi, M=B, N=Dt, K=B, a_mn=True, b_mn=True, lda=Bgp, ldb=Dt, accumulate=True, round_bf16=False)
             lib.gemm(Gi, fi, dft, M=B, N=Dt, K=B, a_mn=True, b_mn=True, lda=Bgp, ldb=Dt, accumulate=True, round_bf16=False)
+        self._clip_backward(tp_i, tp_t, x, nt, cls, fi, ft, nrm_i, nrm_t, dfi, dft, text, B, T)
+
+    def _clip_exchange(self) -> str:
+        import os
+        mode = os.environ.get("VTP_CLIP_EXCHANGE", self.tc.clip_exchange)
+        if mode not in ("nccl", "p2p"):
+            raise ValueError(f"clip_exchange must be 'nccl' or 'p2p', got {mode!r}")
+        return mode
+
+    def _clip_loss_p2p(self, fi_raw, ft_raw, nrm_i, nrm_t, B: int, weight: float):
+        """Collective C2 over NVLink peer memory (csrc/clip.cu): the normalised features are written straight into this
+        rank's exchange buffer, one kernel gathers every rank's rows and forms the full Bg x Bg logits, two small kernels
+        do both softmax directions; returns d(Σ_ranks L_local)/d(f_local) for images and captions (fp32 [B, E])."""
+        from .comm import PeerFeatures
+        dev, Dt = self.device, self.Dt
+        if self.peer is None or self.peer.B != B:
+            if self.peer is not None:
+                self.peer.close()
+            self.peer = PeerFeatures(B, Dt, dev, self.pg)
+        pf = self.peer
+        lib.l2norm_fwd(fi_raw, pf.img, B, Dt, 1e-12, norm_out=nrm_i)
+        lib.l2norm_fwd(ft_raw, pf.txt, B, Dt, 1e-12, norm_out=nrm_t)
+        Bg = self.world * B
+        Bgp = (Bg + 7) // 8 * 8
+        S = _e((Bg, Bgp), F32, dev)
+        St = _e((Bg, Bgp), F32, dev)
+        fi_all = torch.zeros((Bgp, Dt), dtype=BF, device=dev)
+        ft_all = torch.zeros((Bgp, Dt), dtype=BF, device=dev)
+        pf.barrier()                       # every rank's features are written
+        lib.clip_gather_logits(pf.img_ptrs, pf.txt_ptrs, B, Dt, S, St, fi_all, ft_all)
+        pf.barrier()                       # every rank has read them: the buffers may be overwritten by the next step
+        ls = self.store.f32("logit_scale")
+        dls = self.store.grad("logit_scale")
+        coef = weight * 0.5 / B
+        lse = _e((2, Bg), F32, dev)
+        lib.clip_lse(S, St, Bg, self.rank * B, B, ls, coef, lse, self.loss_acc[0:1], dls)
+        dMi = _e((B, Bgp), BF, dev)
+        dMt = _e((B, Bgp), BF, dev)
+        lib.clip_grad(S, St, Bg, self.rank * B, B, ls, coef, lse, dMi, dMt)
+        dfi = _e((B, Dt), F32, dev)
+        dft = _e((B, Dt), F32, dev)
+        lib.gemm(dMi, ft_all, dfi, M=B, N=Dt, K=Bgp, b_mn=True, ldb=Dt, round_bf16=False)
+        lib.gemm(dMt, fi_all, dft, M=B, N=Dt, K=Bgp, b_mn=True, ldb=Dt, round_bf16=False)
+        return dfi, dft
+
+    def _clip_backward(self, tp_i, tp_t, x, nt, cls, fi, ft, nrm_i, nrm_t, dfi, dft, text, B: int, T: int):
+        dev = self.device
+        W, G = self.towers[("trunk", "param")], self.towers[("trunk", "grad")]
+        D, Dt = self.D, self.Dt
+        M = B * T
+        vp: Lin = W.extra["visual_proj"]
         # ---- image side backward
         dfi_raw = _e((B, Dt), BF, dev)
         lib.l2norm_bwd(fi, nrm_i, dfi, dfi_raw, B, Dt)
