@@ -168,7 +168,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cfg = preset(args.model)
-    tc = TrainConfig(head_out_dim=args.prototypes)
+    # VTP-Base/Large at 256 images per GPU: size the SSL / reconstruction image groups for the 180 GB of HBM
+    # (vtp_b200/memory.py; (0, 0) = whole batch in one pass, which is what VTP-Small uses)
+    from vtp_b200.memory import suggest_chunks
+    ssl_chunk, rec_chunk = suggest_chunks(cfg, args.batch, head_out_dim=args.prototypes, lpips=not args.no_lpips)
+    tc = TrainConfig(head_out_dim=args.prototypes, ssl_chunk=ssl_chunk, rec_chunk=rec_chunk)
     tr = VTPTrainer(cfg, tc, device=dev)
     if not args.no_lpips:
         tr.enable_lpips(seed=0, chunk=32)
@@ -284,7 +288,8 @@ def main():
                    "prototypes": args.prototypes, "losses": ["clip", "dino_local", "dino_global", "ibot", "rec_l1"] + ([] if args.no_lpips else ["rec_lpips"]),
                    "lpips": (not args.no_lpips) and "VGG16 (frozen, seeded-random weights: pretrained ones need network), weight 1.0", "optimizer": "fused AdamW + EMA teacher, in the timed region",
                    "l2": "inputs (>1 GB/step) and activations far exceed the 126 MB L2; no reuse across steps",
-                   "parallelism": f"dp{world}", "flops_per_image": fl["total"]},
+                   "parallelism": f"dp{world}", "flops_per_image": fl["total"],
+                   "image_groups": {"ssl_chunk": ssl_chunk, "rec_chunk": rec_chunk}},
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
                 "pipeline": "vtp_b200.synthetic.BatchPrefetcher: pinned host batch of step i+1 copied on a side stream "

@@ -204,6 +204,12 @@ class TrainConfig:
     # contrastive exchange (collective C2): "nccl" = all-gather + local-row logits + all-reduced cross terms;
     # "p2p" = peer-memory gather fused with the full logits / softmax-CE (csrc/clip.cu), no backward collective
     clip_exchange: str = "nccl"
+    # activation-memory control (configs 3/4: VTP-Base/Large at 256 images per GPU exceed 180 GB of saved activations
+    # in one piece, see vtp_b200/memory.py): source images per forward+backward pass of the SSL / reconstruction
+    # objectives; gradients accumulate in the flat buffer, losses and centre statistics are those of the whole batch.
+    # 0 = the whole per-GPU batch at once.
+    ssl_chunk: int = 0
+    rec_chunk: int = 0
 
 
 class VTPTrainer:
@@ -611,7 +617,9 @@ class VTPTrainer:
         lib.cast_colsum(g, None, Gt.extra["pos"].view(-1), B, L * Dt, ldx=L * Dt)
 
     # -------------------------------------------------------------- objective 3: reconstruction (vtp.py:487-512)
-    def rec_fwd_bwd(self, image: torch.Tensor, weight: float = 1.0, return_image: bool = False):
+    def rec_fwd_bwd(self, image: torch.Tensor, weight: float = 1.0, return_image: bool = False,
+                    norm_B: Optional[int] = None):
+        """norm_B: batch size the loss is normalised by (the whole per-GPU batch when `image` is one chunk of it)."""
         dev = self.device
         W, G = self.towers[("trunk", "param")], self.towers[("trunk", "grad")]
         Wd, Gd = self.towers[("decoder", "param")], self.towers[("decoder", "grad")]
@@ -620,6 +628,7 @@ class VTPTrainer:
         x, (B, T, gh, gw) = self._trunk_fwd(W, image, tp_e)
         M, HW = B * T, gh * gw
         Md = B * HW
+        nB = norm_B if norm_B is not None else B
         nt = {}
         xn = E.norm(x, M, D, W.norm_w, None, W.eps, "bf16", want="op", tape=nt)
         bneck: Lin = W.extra["bneck"]
@@ -641,9 +650,10 @@ class VTPTrainer:
         # ---- loss: L1 (+ LPIPS gradient if a perceptual module is attached)
         dlp = None
         if getattr(self, "lpips", None) is not None and self.tc.lpips_weight > 0:
-            dlp = self.lpips.loss_and_grad(rec, image, weight * self.tc.lpips_weight / B, self.loss_acc[5:6])
+            dlp = self.lpips.loss_and_grad(rec, image, weight * self.tc.lpips_weight / nB, self.loss_acc[5:6])
         dY = _e((Md, pout.N), BF, dev)
-        lib.recon_l1_grad(rec, image.contiguous(), dlp, dY, self.loss_acc[4:5], B, 3, gh, gw, r, weight / rec.numel())
+        lib.recon_l1_grad(rec, image.contiguous(), dlp, dY, self.loss_acc[4:5], B, 3, gh, gw, r,
+                          weight / (rec.numel() // B * nB))
         # ---- decoder backward
         dxdn = _e((Md, Dd), BF, dev)
         dgrad(dY, pout.w, dxdn, Md)
@@ -729,12 +739,52 @@ class VTPTrainer:
     # -------------------------------------------------------------- objective 2: SSL (vtp.py:365-386,410-484)
     def ssl_fwd_bwd(self, global_crops, local_crops, mask_indices, masks_weight, weight: float = 1.0):
         """global_crops [2B,3,H,W] (view-major), local_crops [n_local*B,3,h,w] (crop-major), mask_indices int64 flat
-        indices into [2B*HW] of masked global patches, masks_weight [n_masked] = 1/(#masked in that image)."""
+        indices into [2B*HW] of masked global patches (ascending), masks_weight [n_masked] = 1/(#masked in that image).
+        With TrainConfig.ssl_chunk = c the B source images are processed c at a time (all their crops together): the
+        teacher targets use last step's centre either way, so chunking only changes floating-point summation order."""
         import torch.distributed as dist
+        dev, tc = self.device, self.tc
+        K = tc.head_out_dim
+        self._head_prepare()
+        B2 = global_crops.shape[0]
+        B = B2 // 2
+        n_m = mask_indices.numel()
+        csum = torch.zeros((2, K), dtype=F32, device=dev)   # Σ raw teacher logits: [cls rows, masked-patch rows]
+        chunk = tc.ssl_chunk if 0 < tc.ssl_chunk < B else B
+        if chunk == B:
+            self._ssl_chunk(global_crops, local_crops, mask_indices, masks_weight, weight, B, csum)
+        else:
+            ps = self.cfg.vision_patch_size
+            HW = (global_crops.shape[-2] // ps) * (global_crops.shape[-1] // ps)
+            n_loc = tc.n_local_crops
+            lc = local_crops.view(n_loc, B, *local_crops.shape[1:])
+            img = mask_indices // HW
+            for b0 in range(0, B, chunk):
+                b1 = min(B, b0 + chunk)
+                bc = b1 - b0
+                g = torch.cat([global_crops[b0:b1], global_crops[B + b0:B + b1]])
+                l = lc[:, b0:b1].reshape(n_loc * bc, *local_crops.shape[1:])
+                s0 = (img >= b0) & (img < b1)
+                s1 = (img >= B + b0) & (img < B + b1)
+                idx = torch.cat([mask_indices[s0] - b0 * HW, mask_indices[s1] - (B + b0 - bc) * HW])
+                mw = torch.cat([masks_weight[s0], masks_weight[s1]])
+                self._ssl_chunk(g, l, idx, mw, weight, B, csum)
+        # teacher centre EMA over the whole (global) batch (DINOv2 softmax_center_teacher / update_center)
+        cnt = torch.tensor([float(B2), float(max(n_m, 1))], device=dev)
+        if self.world > 1:
+            dist.all_reduce(csum, group=self.pg)
+            dist.all_reduce(cnt, group=self.pg)
+        cm = tc.center_momentum
+        mean = csum / cnt[:, None]
+        lib.axpby(self.center_dino, mean[0].contiguous(), cm, 1 - cm, K)
+        lib.axpby(self.center_ibot, mean[1].contiguous(), cm, 1 - cm, K)
+
+    def _ssl_chunk(self, global_crops, local_crops, mask_indices, masks_weight, weight: float, norm_B: int, csum):
+        """Teacher + student forward, DINO/iBOT losses and the full backward for one group of source images; the loss
+        terms are normalised by `norm_B` (the whole per-GPU batch) and the raw teacher-logit sums are added to csum."""
         dev, tc = self.device, self.tc
         W, G, Wt = self.towers[("trunk", "param")], self.towers[("trunk", "grad")], self.towers[("trunk", "teacher")]
         D, K = self.D, tc.head_out_dim
-        self._head_prepare()
         n_loc = tc.n_local_crops
         B2 = global_crops.shape[0]
         B = B2 // 2
@@ -751,18 +801,13 @@ class VTPTrainer:
         tin = _e((Tt, D), BF, dev)
         lib.gather_rows(xnt, tin, torch.cat([swapped, m_rows]), D)
         tlog = self._head_fwd(Wt, self.head_wn_t, tin, None)
-        # centre statistics (batch mean of raw teacher logits), then centred + sharpened softmax in place
-        csum = torch.zeros((2, K), dtype=F32, device=dev)
+        # centre statistics (sums of raw teacher logits), then centred + sharpened softmax in place
         lib.cast_colsum(tlog, None, csum[0], B2, K)
         if n_m:
             lib.cast_colsum(tlog[B2:], None, csum[1], n_m, K)
         lib.dino_teacher_probs(tlog, self.center_dino, B2, K, tc.teacher_temp)
         if n_m:
             lib.dino_teacher_probs(tlog[B2:], self.center_ibot, n_m, K, tc.teacher_temp)
-        cnt = torch.tensor([float(B2), float(max(n_m, 1))], device=dev)
-        if self.world > 1:
-            dist.all_reduce(csum, group=self.pg)
-            dist.all_reduce(cnt, group=self.pg)
         del xt, xnt
         # ---------------- student: get_student_ssl_outputs vtp.py:452-484
         tp_g, tp_l = {}, {}
@@ -784,20 +829,15 @@ class VTPTrainer:
         t0 = torch.cat([bidx.repeat(n_loc), torch.arange(B2, device=dev, dtype=torch.int32),
                         B2 + torch.arange(n_m, device=dev, dtype=torch.int32)])
         t1 = torch.cat([(B + bidx).repeat(n_loc), torch.full((B2 + n_m,), -1, device=dev, dtype=torch.int32)])
-        wl = weight / (B * n_terms)
+        wl = weight / (norm_B * n_terms)
         wrow = torch.cat([torch.full((Bl,), wl, device=dev), torch.full((B2,), wl, device=dev),
-                          masks_weight.to(F32) * (weight / B)])
+                          masks_weight.to(F32) * (weight / norm_B)])
         lib.dino_student_ce(slog[:Bl], tlog, t0[:Bl], t1[:Bl], wrow[:Bl], Bl, K, tc.student_temp, self.loss_acc[1:2])
         lib.dino_student_ce(slog[Bl:Bl + B2], tlog, t0[Bl:Bl + B2], t1[Bl:Bl + B2], wrow[Bl:Bl + B2], B2, K,
                             tc.student_temp, self.loss_acc[2:3])
         if n_m:
             lib.dino_student_ce(slog[Bl + B2:], tlog, t0[Bl + B2:], t1[Bl + B2:], wrow[Bl + B2:], n_m, K,
                                 tc.student_temp, self.loss_acc[3:4])
-        # teacher centre EMA (DINOv2 softmax_center_teacher / update_center)
-        cm = tc.center_momentum
-        mean = csum / cnt[:, None]
-        lib.axpby(self.center_dino, mean[0].contiguous(), cm, 1 - cm, K)
-        lib.axpby(self.center_ibot, mean[1].contiguous(), cm, 1 - cm, K)
         del tlog
         # ---------------- backward: head -> scatter to the two trunk passes
         dsin = self._head_bwd(htape, slog)
@@ -845,7 +885,11 @@ class VTPTrainer:
             self.ssl_fwd_bwd(batch["global_crops"], batch["local_crops"], batch["mask_indices"], batch["masks_weight"],
                              tc.w_ssl)
         if tc.w_rec:
-            self.rec_fwd_bwd(batch["rec_image"], tc.w_rec)
+            img = batch["rec_image"]
+            nB = img.shape[0]
+            rc = tc.rec_chunk if 0 < tc.rec_chunk < nB else nB
+            for b0 in range(0, nB, rc):
+                self.rec_fwd_bwd(img[b0:b0 + rc], tc.w_rec, norm_B=nB)
         self.allreduce_grads()
         self.optimizer_step()
         return self.loss_acc
