@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by running the REAL reference (imported from /root/reference,
 see oracle/ref_harness.py) on seeded weights/inputs (oracle/seeded.py).  Run in the dev container:
 
-    python -m oracle.make_golden
+    python -m oracle.make_golden [name ...]
 
 Each file holds the reference outputs in fp32 and under torch.autocast("cpu", bfloat16), plus the state-dict
 key->shape spec so the GPU box can rebuild the same weights without the reference."""
@@ -32,6 +32,11 @@ CONFIGS = {
     "small": (dict(vision_embed_dim=384, vision_depth=12, vision_num_heads=6, text_embed_dim=384, text_num_heads=6,
                    text_depth=12, decoder_embed_dim=384, decoder_num_heads=6, decoder_depth=12, text_vocab_size=2048),
               2, 256, True),
+    # VTP-Large geometry (BASELINE configs 4/5) at depth 2: D = 1024, 16 heads, SwiGLU hidden 2736 (= 16·171, the ragged
+    # N/K tile case), text tower 768/12 heads
+    "large2": (dict(vision_embed_dim=1024, vision_depth=2, vision_num_heads=16, text_embed_dim=768, text_num_heads=12,
+                    text_depth=2, decoder_embed_dim=1024, decoder_num_heads=16, decoder_depth=2, text_vocab_size=2048),
+               2, 256, True, dict(qkv_std=0.0367)),   # 0.06·sqrt(384/1024): same attention peakiness as "small"
 }
 
 
@@ -41,11 +46,16 @@ def main():
 
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(os.cpu_count())
-    for name, (kw, B, size, with_text) in CONFIGS.items():
+    only = set(sys.argv[1:])
+    for name, entry in CONFIGS.items():
+        kw, B, size, with_text = entry[:4]
+        seed_opts = entry[4] if len(entry) > 4 else {}
+        if only and name not in only:
+            continue
         cfg = VTPConfig(**kw)
         m = VTPModel(cfg).eval()
         spec = {k: list(v.shape) for k, v in m.state_dict().items()}
-        sd = seeded_state_dict(spec, seed=0)
+        sd = seeded_state_dict(spec, seed=0, **seed_opts)
         m.load_state_dict(sd)
         x = seeded_images(B, size, size)
         ids = seeded_captions(B, 77, kw["text_vocab_size"])
@@ -62,7 +72,7 @@ def main():
                     out[f"img_feat_{tag}"] = fi.float().numpy()
                     feats = m.get_last_layer_feature(x)
                     out[f"cls_{tag}"] = feats["cls_token"].float().numpy()
-                    if name != "small":
+                    if name not in ("small", "large2"):
                         out[f"patch_{tag}"] = feats["patch_tokens"].float().numpy()
                     if with_text:
                         ft = m.get_clip_text_feature(ids)
@@ -87,7 +97,7 @@ def main():
         np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **out)
         with open(os.path.join(OUT, f"{name}.json"), "w") as f:
             json.dump({"config": kw, "batch": B, "image_size": size, "spec": spec,
-                       "reference_commit": "5ce1eb6", "torch": torch.__version__,
+                       "reference_commit": "5ce1eb6", "torch": torch.__version__, "seed_opts": seed_opts,
                        "ref_sensitivity_1e-6": sens}, f)
         print(name, "reference sensitivity to 1e-6 input perturbation:", sens)
 

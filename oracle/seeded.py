@@ -16,7 +16,10 @@ def _gen(key: str, seed: int) -> torch.Generator:
     return torch.Generator().manual_seed((zlib.crc32(key.encode()) + 7919 * seed) % (2**31 - 1))
 
 
-def seeded_state_dict(spec: Dict[str, Sequence[int]], seed: int = 0, dtypes: Dict[str, torch.dtype] | None = None):
+def seeded_state_dict(spec: Dict[str, Sequence[int]], seed: int = 0, dtypes: Dict[str, torch.dtype] | None = None,
+                      qkv_std: float = 0.06):
+    """qkv_std: std of the q/k/v projection weights (0.06 gives attention logits of std ~1.4 at D = 384; scale it by
+    sqrt(384 / D) for wider models to keep the same peakiness)."""
     sd = {}
     for k in sorted(spec):
         shape = tuple(spec[k])
@@ -35,7 +38,7 @@ def seeded_state_dict(spec: Dict[str, Sequence[int]], seed: int = 0, dtypes: Dic
         elif leaf in ("bias", "in_proj_bias"):
             sd[k] = 0.02 * r
         elif "qkv.weight" in k or "in_proj_weight" in k:
-            sd[k] = 0.06 * r
+            sd[k] = qkv_std * r
         elif k in ("trunk.cls_token", "trunk.mask_token", "positional_embedding"):
             sd[k] = 0.05 * r
         elif k == "text_projection" or "visual_proj" in k or "proj.weight" in k:

@@ -25,7 +25,7 @@ def _build(name):
     return m.cuda(), g, x.cuda(), ids.cuda(), meta
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny96", "small"])
+@pytest.mark.parametrize("name", ["tiny", "tiny96", "small", "large2"])
 def test_fp32_mode_matches_reference_fp32(name):
     m, g, x, ids, meta = _build(name)
     lat = m.get_reconstruction_latents(x)
@@ -53,7 +53,7 @@ def test_fp32_mode_matches_reference_fp32(name):
         assert v < max(1e-3, 3 * floor[k]), (k, v, floor[k])
 
 
-@pytest.mark.parametrize("name", ["tiny", "tiny96", "small"])
+@pytest.mark.parametrize("name", ["tiny", "tiny96", "small", "large2"])
 def test_bf16_mode_matches_reference_autocast(name):
     m, g, x, ids, meta = _build(name)
     e, dev = {}, {}

@@ -22,7 +22,7 @@ def rel(a, b):
 def golden_inputs(meta):
     from oracle.seeded import seeded_captions, seeded_images, seeded_state_dict
 
-    sd = seeded_state_dict(meta["spec"], seed=0)
+    sd = seeded_state_dict(meta["spec"], seed=0, **meta.get("seed_opts", {}))
     x = seeded_images(meta["batch"], meta["image_size"], meta["image_size"])
     ids = seeded_captions(meta["batch"], 77, meta["config"]["text_vocab_size"])
     return sd, x, ids
