@@ -227,6 +227,18 @@ int vtp_comm_open_handle(const unsigned char* handle64, void** peer_ptr);
 int vtp_comm_close_handle(void* peer_ptr);
 int vtp_comm_barrier(const void* const* pad_ptrs, int world, int rank, long epoch, int* err_flag, vtp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Data formats either side of the encode / decode path (vtp_b200/csrc/latents_io.cu)
+ * ------------------------------------------------------------------------------------------------------------ */
+/* generation/tokenizer/vtp_tokenizer.py:106-119 (decode_to_images) and tools/test_reconstruction_hf.py:371-372,
+ * 401-402: torchvision Normalize(inv_mean, inv_std) = (x - sub3[c]) / div3[c], x255, clamp [0,255], truncation to
+ * uint8, NCHW (fp32|bf16) -> NHWC, in one pass.  Bit-exact with the torch expression. */
+int vtp_image_to_u8(const void* img, int img_dtype, const float* sub3, const float* div3, uint8_t* out_nhwc, int B, int H,
+                    int W, vtp_stream_t stream);
+/* latents_stats.pt of generation/tools/extract_features_vtp.py:128-131: sum[c] += sum x, sumsq[c] += sum x^2 (fp64)
+ * over latents [B][C][HW] (fp32|bf16) */
+int vtp_latent_stats(const void* lat, int dtype, int B, int C, int HW, double* sum, double* sumsq, vtp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -99,3 +99,38 @@ def test_compat_shim_serves_reference_import_path():
             "c = VTPConfig(); assert c.model_type == 'vtp'; print('ok')") % (ROOT, os.path.join(ROOT, "compat"))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_center_crop_matches_adm_definition():
+    """vtp_b200/image_utils.py vs the ADM procedure written out with numpy slicing (vtp/utils/image_utils.py:5-31)."""
+    import numpy as np
+    from PIL import Image
+
+    from vtp_b200.image_utils import center_crop_arr
+
+    rng = np.random.default_rng(0)
+    for (w, h), size in (((700, 520), 256), ((300, 260), 256), ((1030, 2051), 224), ((256, 256), 256)):
+        im = Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8))
+        ref = im
+        while min(*ref.size) >= 2 * size:
+            ref = ref.resize(tuple(x // 2 for x in ref.size), resample=Image.BOX)
+        sc = size / min(*ref.size)
+        ref = ref.resize(tuple(round(x * sc) for x in ref.size), resample=Image.BICUBIC)
+        a = np.array(ref)
+        cy, cx = (a.shape[0] - size) // 2, (a.shape[1] - size) // 2
+        out = np.array(center_crop_arr(im, size))
+        assert out.shape == (size, size, 3) and np.array_equal(out, a[cy:cy + size, cx:cx + size])
+
+
+def test_tokenizer_normalisation_constants():
+    from vtp_b200.generation import VTP_Tokenizer
+
+    t = VTP_Tokenizer.__new__(VTP_Tokenizer)
+    t._setup_normalization("imagenet")
+    assert t.norm_mean == [0.485, 0.456, 0.406] and t.norm_std == [0.229, 0.224, 0.225]
+    assert abs(t.inv_mean[0] + 0.485 / 0.229) < 1e-12 and abs(t.inv_std[2] - 1 / 0.225) < 1e-12
+    t._setup_normalization("half")
+    assert t.inv_mean == [-1.0, -1.0, -1.0] and t.inv_std == [2.0, 2.0, 2.0]
+    import pytest
+    with pytest.raises(ValueError):
+        t._setup_normalization("other")

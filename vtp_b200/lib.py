@@ -105,6 +105,9 @@ SIGNATURES: dict[str, tuple] = {
                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "vtp_clip_grad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_float,
                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "vtp_image_to_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p]),
+    "vtp_latent_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "vtp_comm_alloc": (C.c_int, [C.c_long, C.POINTER(C.c_void_p)]),
     "vtp_comm_free": (C.c_int, [C.c_void_p]),
     "vtp_comm_get_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
@@ -430,3 +433,18 @@ def comm_close_handle(ptr: int) -> None:
 def comm_barrier(pad_ptrs, rank: int, epoch: int, err_flag, stream=None):
     check(load().vtp_comm_barrier(_ptr_array(pad_ptrs), len(pad_ptrs), rank, epoch, _ptr(err_flag), _st(stream)),
           "vtp_comm_barrier")
+
+
+# ------------------------------------------------------------------------------------------------ image / latent formats
+def image_to_u8(img, sub3, div3, out, stream=None):
+    """img NCHW [B,3,H,W] fp32|bf16 -> out uint8 NHWC [B,H,W,3] = clamp(((img - sub3[c]) / div3[c]) * 255, 0, 255)."""
+    B, _, H, W = img.shape
+    check(load().vtp_image_to_u8(_ptr(img), _dt(img), _ptr(sub3), _ptr(div3), _ptr(out), B, H, W, _st(stream)),
+          "vtp_image_to_u8")
+
+
+def latent_stats(lat, sum64, sumsq64, stream=None):
+    B, Cc = lat.shape[0], lat.shape[1]
+    HW = lat.numel() // (B * Cc)
+    check(load().vtp_latent_stats(_ptr(lat), _dt(lat), B, Cc, HW, _ptr(sum64), _ptr(sumsq64), _st(stream)),
+          "vtp_latent_stats")
