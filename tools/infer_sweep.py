@@ -1,6 +1,7 @@
 """Config 5 of BASELINE.json: encode+decode inference throughput sweep (bf16 autocast mode) + optional parity check of
 the fp32 mode against the CPU oracle at batch 1.  GPU only.
-  python tools/infer_sweep.py --model large --batches 1,8,64,256 [--check]"""
+  python tools/infer_sweep.py --model large --batches 1,8,64,256 [--check] [--graphs]
+--graphs also times CUDA-graph replays (VTPModel.enable_cuda_graphs) — the small-batch serving path."""
 import argparse
 import json
 import os
@@ -17,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--model", default="large")
 ap.add_argument("--batches", default="1,8,64,256")
 ap.add_argument("--check", action="store_true")
+ap.add_argument("--graphs", action="store_true")
 a = ap.parse_args()
 cfg = preset(a.model)
 torch.manual_seed(0)
@@ -37,8 +39,24 @@ for B in [int(b) for b in a.batches.split(",")]:
         e1.record()
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    out["rows"].append({"batch": B, "ms": ms, "img_per_s": B / ms * 1e3, "tflops": fl * B / ms / 1e9})
-    print(f"{a.model} B={B:4d}: {ms:8.2f} ms  {B / ms * 1e3:9.1f} img/s  {fl * B / ms / 1e9:7.1f} TFLOP/s", flush=True)
+    row = {"batch": B, "ms": ms, "img_per_s": B / ms * 1e3, "tflops": fl * B / ms / 1e9}
+    if a.graphs:
+        m.enable_cuda_graphs()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            for _ in range(2):
+                rec_g = m.get_latents_decoded_images(m.get_reconstruction_latents(x))
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps):
+                rec_g = m.get_latents_decoded_images(m.get_reconstruction_latents(x))
+            e1.record()
+            torch.cuda.synchronize()
+        m.enable_cuda_graphs(False)
+        row["ms_graphs"] = e0.elapsed_time(e1) / reps
+        row["graphs_equal_eager"] = bool(torch.equal(rec_g, rec))
+    out["rows"].append(row)
+    print(f"{a.model} B={B:4d}: {ms:8.2f} ms  {B / ms * 1e3:9.1f} img/s  {fl * B / ms / 1e9:7.1f} TFLOP/s"
+          + (f"   graphs: {row['ms_graphs']:8.2f} ms" if a.graphs else ""), flush=True)
 if a.check:
     from oracle import vtp_oracle as vo
     sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}

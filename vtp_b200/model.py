@@ -8,6 +8,10 @@ Precision follows the caller's autocast context exactly like the reference does:
                                              tools/test_reconstruction_hf.py:369-372 uses for the decoder)
 `model.compute_mode = "bf16" | "fp32"` overrides the detection.
 
+Small-batch serving (BASELINE config 5, batch 1..512): `model.enable_cuda_graphs()` captures each inference entry point
+once per (input shape, dtype, precision mode) in a CUDA graph and replays it afterwards — a VTP-Large encode+decode is
+~1 000 kernel launches, which at batch 1 costs more host time than device time.
+
 Checkpoints: `from_pretrained(dir)` / `save_pretrained(dir)` read/write the reference's HF layout (config.json +
 model.safetensors, keys unchanged).  The text tower needs no `attn_mask` buffer (causality is applied in-kernel), which
 also removes the reference's uninitialised-buffer NaN after from_pretrained under transformers 5.x.
@@ -99,6 +103,50 @@ class VTPModel(VTPPreTrainedModel):
             self._init_text_components()
         self.reset_parameters()
         self._packs: Dict[Tuple[str, str], Tuple[int, E.TowerW]] = {}
+        self._graphs_on = False          # see enable_cuda_graphs()
+        self._graph_busy = False         # True while a graph is being warmed up / captured (the eager path runs)
+        self._graphs: Dict[tuple, tuple] = {}
+
+    # ------------------------------------------------------------------ CUDA graphs for the inference entry points
+    def enable_cuda_graphs(self, on: bool = True):
+        """Replay captured CUDA graphs for get_reconstruction_latents / get_latents_decoded_images /
+        get_clip_image_feature / get_clip_text_feature (one graph per input shape, dtype and precision mode; dropped
+        when the parameters change).  Results are identical to the eager launches: the same kernels in the same order."""
+        self._graphs_on = bool(on)
+        if not on:
+            self._graphs = {}
+        return self
+
+    def _graphed(self, name: str, fn, x: torch.Tensor, *extra):
+        """Run fn(x) through a captured graph: static input buffer <- x, replay, fresh copy of the static output."""
+        if not x.is_cuda:
+            raise lib.VtpError("VTPModel inputs must live on the CUDA device (no CPU path)")
+        key = (name, tuple(x.shape), x.dtype, self._mode(), extra)
+        ver = self._version()
+        hit = self._graphs.get(key)
+        if hit is None or hit[0] != ver:
+            static_in = x.detach().clone()
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            self._graph_busy = True
+            try:
+                with torch.cuda.stream(side):    # warm-up: packs the weights, builds RoPE tables, sizes the allocator
+                    for _ in range(2):
+                        fn(static_in)
+                cur.wait_stream(side)
+                torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    static_out = fn(static_in)
+            finally:
+                self._graph_busy = False
+            hit = (ver, graph, static_in, static_out)
+            self._graphs[key] = hit
+        _, graph, static_in, static_out = hit
+        static_in.copy_(x)
+        graph.replay()
+        return static_out.clone()
 
     # ------------------------------------------------------------------ parameters (reference names)
     def _init_vision_components(self):
@@ -341,6 +389,9 @@ class VTPModel(VTPPreTrainedModel):
     def get_clip_image_feature(self, image: torch.Tensor, normalize: bool = True) -> torch.Tensor:
         if self.visual_proj is None:
             raise RuntimeError("CLIP not enabled. Set train_clip=True in config.")
+        if self._graphs_on and image.is_cuda and not self._graph_busy:
+            self._check_image(image)
+            return self._graphed("clip_image", lambda t: self.get_clip_image_feature(t, normalize), image, normalize)
         mode = self._mode()
         out, meta, W = self._trunk(image, not self.config.vision_bottleneck_ae_only, mode)
         if self.config.vision_clip_feat == "cls":
@@ -363,6 +414,8 @@ class VTPModel(VTPPreTrainedModel):
             raise RuntimeError("CLIP not enabled. Set train_clip=True in config.")
         if text.dtype != torch.int64 or text.dim() != 2 or text.shape[1] != self.config.text_context_length:
             raise ValueError(f"expected int64 token ids of shape (B, {self.config.text_context_length})")
+        if self._graphs_on and text.is_cuda and not self._graph_busy:
+            return self._graphed("clip_text", lambda t: self.get_clip_text_feature(t, normalize), text, normalize)
         mode = self._mode()
         W = self._pack("text", mode)
         f = E.text_forward(W, text, mode)
@@ -394,6 +447,9 @@ class VTPModel(VTPPreTrainedModel):
         return logits, logits.T
 
     def get_reconstruction_latents(self, image: torch.Tensor) -> torch.Tensor:
+        if self._graphs_on and image.is_cuda and not self._graph_busy:
+            self._check_image(image)
+            return self._graphed("latents", self.get_reconstruction_latents, image)
         out, meta, _ = self._trunk(image, True, self._mode())
         _, _, gh, gw = meta
         pt = out["x_norm_patchtokens"]
@@ -407,6 +463,8 @@ class VTPModel(VTPPreTrainedModel):
             raise RuntimeError("Reconstruction not enabled. Set train_reconstruction=True in config.")
         if not latents.is_cuda:
             raise lib.VtpError("VTPModel inputs must live on the CUDA device (no CPU path)")
+        if self._graphs_on and latents.is_cuda and not self._graph_busy:
+            return self._graphed("decode", self.get_latents_decoded_images, latents)
         mode = self._mode()
         return E.decoder_forward(self._pack("decoder", mode), latents, mode)
 
