@@ -105,7 +105,10 @@ def _sdpa_ref(qkv, B, T, H, causal):
                                                   (4, 77, 6, 0, True), (2, 197, 12, 1, False), (2, 130, 2, 2, False),
                                                   (64, 257, 6, 1, False), (7, 50, 2, 0, False), (3, 64, 2, 1, False),
                                                   (100, 37, 6, 1, False)])
-def test_attention_fwd(B, T, H, prefix, causal):
+@pytest.mark.parametrize("variant", ["rows4", "rows8"])
+def test_attention_fwd(B, T, H, prefix, causal, variant, monkeypatch):
+    """rows4: one thread per query row (default); rows8: two threads per row, opt-in VTP_ATTN_FWD8=1 (attn_fwd8_kernel)."""
+    monkeypatch.setenv("VTP_ATTN_FWD8", "1" if variant == "rows8" else "0")
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T)
     qkv = (torch.randn(B * T, 3 * H * 64, device="cuda", generator=g) * 1.5).to(BF)
     out = torch.full((B * T, H * 64), float("nan"), device="cuda", dtype=BF)

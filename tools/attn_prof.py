@@ -29,5 +29,10 @@ def t(fn, reps=10):
 HW = T - prefix
 fl = 4.0 * T * T * 64 * B * H
 uf, ub = t(fwd), t(bwd)
+os.environ["VTP_ATTN_FWD8"] = "1"     # opt-in variant: two row threads per query row (attn_fwd8_kernel)
+o_ref = o.clone()
+uf8 = t(fwd)
+os.environ["VTP_ATTN_FWD8"] = "0"
+print(f"fwd rows8 variant: {uf8:.1f} us (x{uf / uf8:.2f} vs rows4), max |diff| vs rows4 = {(o.float() - o_ref.float()).abs().max().item():.3e}")
 print(f"B={B} T={T} H={H}: fwd {uf:.1f} us ({fl / uf / 1e6:.0f} TFLOP/s, {(M * 4 * D * 2) / uf / 1e3:.0f} GB/s)   "
       f"bwd {ub:.1f} us ({2.5 * fl / ub / 1e6:.0f} TFLOP/s, {(M * 8 * D * 2) / ub / 1e3:.0f} GB/s)")

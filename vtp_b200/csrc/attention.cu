@@ -362,6 +362,338 @@ __global__ void __launch_bounds__(ATT_THREADS, 2) attn_fwd_kernel(const __grid_c
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Variant with TWO row threads per query row (opt-in: VTP_ATTN_FWD8=1).  The one-thread-per-row kernel above is
+// latency-bound (profiles/ncu_attn_r1b_before_cls_fix.md: 16 % warps active, 24 % issue slots, 5 % tensor pipe): its 4
+// row warps per CTA walk 256 score columns serially.  Here 8 row warps share the 128 TMEM lanes pairwise (warps w and
+// w+4 own the same lane quarter, as in attn_bwd_kernel): both compute the full-row max (the cheap pass), then each
+// exponentiates HALF of the columns, writes its half of P and later normalises half of the 64 output dims.  With two
+// 128-key halves the second P half goes into the Q|K0 region, which is dead once S is complete and the cls warp has
+// finished its score pass (bar_kfree) — so both halves are produced concurrently and smem stays at 2 CTAs/SM.  The row
+// sums are exchanged once, after the last MMA, through the then-dead P buffer.
+static constexpr int ATT8_THREADS = 320;  // warp 0: TMA + MMA; warps 1-8: row warps; warp 9: prefix (cls) query rows
+
+__global__ void __launch_bounds__(ATT8_THREADS, 2) attn_fwd8_kernel(const __grid_constant__ CUtensorMap tm, const AttnDev p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if (smem_u32(smem) & 1023) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SBAR);
+    uint64_t* bar_qk = bars + 0;     // Q,K landed
+    uint64_t* bar_v = bars + 1;      // V landed
+    uint64_t* bar_s = bars + 2;      // S complete in TMEM
+    uint64_t* bar_p0 = bars + 3;     // P half 0 written
+    uint64_t* bar_p1 = bars + 4;     // P half 1 written (nkt == 2)
+    uint64_t* bar_o = bars + 5;      // O complete
+    uint64_t* bar_kfree = bars + 6;  // cls warp has finished reading the K tiles
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, b = p.pack ? blockIdx.z * p.pack : blockIdx.z;
+    const int D = p.D, T = p.T, prefix = p.prefix, HW = p.HW, nkt = p.nkt;
+    const long seq_row0 = (long)b * T;
+    const int kvrows = 128 * nkt;
+
+    if (threadIdx.x == 0) {
+        tma_prefetch_desc(&tm);
+        mbar_init(bar_qk, 1), mbar_init(bar_v, 1), mbar_init(bar_s, 1), mbar_init(bar_p0, nkt == 2 ? 128 : 256);
+        mbar_init(bar_p1, 128), mbar_init(bar_o, 1), mbar_init(bar_kfree, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) {
+        tmem_alloc(tmem_slot, 256);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int row_q = (int)seq_row0 + prefix + 128 * qt;
+            const int row_k = (int)seq_row0 + prefix;
+            mbar_expect_tx(bar_qk, 16384 + 16384 * nkt);
+            tma_load_2d(smem + SQ, &tm, bar_qk, h * 64, row_q);
+            for (int i = 0; i < nkt; ++i) tma_load_2d(smem + SK + i * 16384, &tm, bar_qk, D + h * 64, row_k + 128 * i);
+            mbar_expect_tx(bar_v, 16384 * nkt);
+            for (int i = 0; i < nkt; ++i) tma_load_2d(smem + SV + i * 16384, &tm, bar_v, 2 * D + h * 64, row_k + 128 * i);
+            mbar_wait(bar_qk, 0);
+            tc_fence_after();
+            const uint32_t idesc_s = umma_idesc_bf16(128, kvrows, 0, 0);
+            const uint32_t qa = smem_u32(smem + SQ), ka = smem_u32(smem + SK);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                umma_bf16_ss(tmem, umma_desc_sw128(qa + j * 32, 0, 1024), umma_desc_sw128(ka + j * 32, 0, 1024), idesc_s,
+                             j > 0);
+            umma_commit(bar_s);
+            const uint32_t idesc_o = umma_idesc_bf16(128, 64, 0, 1);  // B (= V) is MN-major
+            const uint32_t va = smem_u32(smem + SV);
+            mbar_wait(bar_v, 0);
+            for (int half = 0; half < nkt; ++half) {
+                mbar_wait(half == 0 ? bar_p0 : bar_p1, 0);
+                tc_fence_after();
+                const uint32_t pa = smem_u32(smem + (half == 0 ? SP : SQ));  // half 1 lives in the dead Q|K0 region
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint64_t ad = umma_desc_sw128(pa + (j >> 2) * 16384 + (j & 3) * 32, 0, 1024);
+                    const uint64_t bd = umma_desc_sw128(va + half * 16384 + j * 2048, 8192, 1024);
+                    umma_bf16_ss(tmem, ad, bd, idesc_o, (half > 0 || j > 0) ? 1u : 0u);
+                }
+            }
+            umma_commit(bar_o);
+        }
+    } else if (warp <= 8) {
+        const int set = (warp - 1) >> 2;  // 0: first half of the columns / output dims, 1: second half
+        const int q4 = warp & 3;          // TMEM lane quarter this warp may access (== warp id % 4)
+        const int r = q4 * 32 + lane;
+        const int qpos = 128 * qt + r;
+        const int qtok = prefix + qpos;
+        const int pseq = p.pack ? r / T : 0;
+        const bool row_valid = p.pack ? (pseq < p.pack && b + pseq < p.B) : (qpos < HW);
+        const uint32_t trow = tmem + (uint32_t(q4 * 32) << 16);
+
+        float s_pre[MAX_PREFIX];
+        mbar_wait(bar_qk, 0);
+        if (prefix > 0) {
+            float qf[64];
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint4 w = *reinterpret_cast<const uint4*>(smem + SQ + sw128_off(r, c * 8));
+                qf[c * 8 + 0] = bf16_lo(w.x), qf[c * 8 + 1] = bf16_hi(w.x), qf[c * 8 + 2] = bf16_lo(w.y);
+                qf[c * 8 + 3] = bf16_hi(w.y), qf[c * 8 + 4] = bf16_lo(w.z), qf[c * 8 + 5] = bf16_hi(w.z);
+                qf[c * 8 + 6] = bf16_lo(w.w), qf[c * 8 + 7] = bf16_hi(w.w);
+            }
+#pragma unroll
+            for (int j = 0; j < MAX_PREFIX; ++j) {
+                s_pre[j] = -INFINITY;
+                if (j < prefix) {
+                    const uint4* kp = reinterpret_cast<const uint4*>(p.qkv + (seq_row0 + j) * 3 * D + D + h * 64);
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 w = __ldg(kp + c);
+                        acc += qf[c * 8 + 0] * bf16_lo(w.x) + qf[c * 8 + 1] * bf16_hi(w.x) + qf[c * 8 + 2] * bf16_lo(w.y) +
+                               qf[c * 8 + 3] * bf16_hi(w.y) + qf[c * 8 + 4] * bf16_lo(w.z) + qf[c * 8 + 5] * bf16_hi(w.z) +
+                               qf[c * 8 + 6] * bf16_lo(w.w) + qf[c * 8 + 7] * bf16_hi(w.w);
+                    }
+                    if (!p.causal || j <= qtok) s_pre[j] = acc;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < MAX_PREFIX; ++j) s_pre[j] = -INFINITY;
+        }
+
+        mbar_wait(bar_s, 0);
+        tc_fence_after();
+        // pass 1 (both threads of a row, redundantly): row max over all visible keys
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < MAX_PREFIX; ++j) m = fmaxf(m, s_pre[j]);
+        const int kmin = p.pack ? (row_valid ? pseq * T : 0) : 0;
+        const int kmax = p.pack ? (row_valid ? kmin + T : 0) : (p.causal ? min(HW, qpos + 1) : HW);
+        for (int c = 0; c < kvrows; c += 32) {
+            if (__all_sync(0xffffffffu, c + 32 <= kmin || c >= kmax)) continue;
+            uint32_t rr[32];
+            tmem_ld_32x32(trow + c, rr);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (c + i >= kmin && c + i < kmax) m = fmaxf(m, __uint_as_float(rr[i]));
+        }
+        // Every row thread has now (a) read its Q row for the prefix scores and (b) finished reading ALL score columns.
+        // Both matter before anyone moves on: the second P half overwrites the Q tile, and the first P·V MMA overwrites
+        // score columns [0,64) with O while a slower partner thread could still be scanning them for its maximum.
+        tc_fence_before();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        tc_fence_after();
+        const float msc = (m == -INFINITY) ? 0.f : m * p.scale_log2;
+        float l = 0.f;
+        float p_pre[MAX_PREFIX];
+#pragma unroll
+        for (int j = 0; j < MAX_PREFIX; ++j) {
+            p_pre[j] = (s_pre[j] == -INFINITY) ? 0.f : ex2f(s_pre[j] * p.scale_log2 - msc);
+            if (set == 0) l += p_pre[j];        // the prefix key columns are counted once per row
+            p_pre[j] = bf16_round(p_pre[j]);
+        }
+        // pass 2: my half of the columns.  nkt == 2: key half `set` (its own P buffer); nkt == 1: 64 of the 128 keys
+        const bool second_buf = (nkt == 2 && set == 1);
+        if (second_buf && qt == 0 && prefix > 0) mbar_wait(bar_kfree, 0);  // K0 tile is about to be overwritten
+        uint8_t* pbase = smem + (second_buf ? SQ : SP);
+        const int nchunk = (nkt == 2) ? 4 : 2;
+#pragma unroll 1
+        for (int i = 0; i < nchunk; ++i) {
+            const int c32 = (nkt == 2) ? i : 2 * set + i;          // 32-key chunk within the 128-key P tile
+            const int c = ((nkt == 2) ? set * 128 : 0) + c32 * 32;  // score column
+            uint32_t pk[16];
+            if (__all_sync(0xffffffffu, c + 32 <= kmin || c >= kmax)) {
+#pragma unroll
+                for (int k = 0; k < 16; ++k) pk[k] = 0u;
+            } else {
+                uint32_t rr[32];
+                tmem_ld_32x32(trow + c, rr);
+                tmem_ld_wait();
+#pragma unroll
+                for (int k = 0; k < 32; k += 2) {
+                    const bool v0 = c + k >= kmin && c + k < kmax, v1 = c + k + 1 >= kmin && c + k + 1 < kmax;
+                    const float e0 = v0 ? ex2f(__uint_as_float(rr[k]) * p.scale_log2 - msc) : 0.f;
+                    const float e1 = v1 ? ex2f(__uint_as_float(rr[k + 1]) * p.scale_log2 - msc) : 0.f;
+                    l += e0 + e1;
+                    pk[k >> 1] = pack_bf16x2(e0, e1);
+                }
+            }
+            uint8_t* pb = pbase + (c32 >> 1) * 16384;
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+                const int col = (c32 & 1) * 32 + v4 * 8;
+                *reinterpret_cast<uint4*>(pb + sw128_off(r, col)) =
+                    make_uint4(pk[v4 * 4], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
+            }
+        }
+        tc_fence_before();
+        fence_proxy_async_smem();
+        mbar_arrive(second_buf ? bar_p1 : bar_p0);
+
+        // epilogue: wait for O, exchange the partial row sums through the (now dead) P buffer, normalise 32 dims each
+        mbar_wait(bar_o, 0);
+        tc_fence_after();
+        float* xs = reinterpret_cast<float*>(smem + SP);
+        xs[set * 128 + r] = l;
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        l = xs[r] + xs[128 + r];
+        uint32_t o0[32];
+        tmem_ld_32x32(trow + 32 * set, o0);
+        tmem_ld_wait();
+        float o[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __uint_as_float(o0[i]);
+#pragma unroll
+        for (int j = 0; j < MAX_PREFIX; ++j) {
+            if (j < prefix && p_pre[j] != 0.f) {
+                const uint4* vp = reinterpret_cast<const uint4*>(p.qkv + (seq_row0 + j) * 3 * D + 2 * D + h * 64 + 32 * set);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 w = __ldg(vp + c);
+                    o[c * 8 + 0] += p_pre[j] * bf16_lo(w.x), o[c * 8 + 1] += p_pre[j] * bf16_hi(w.x);
+                    o[c * 8 + 2] += p_pre[j] * bf16_lo(w.y), o[c * 8 + 3] += p_pre[j] * bf16_hi(w.y);
+                    o[c * 8 + 4] += p_pre[j] * bf16_lo(w.z), o[c * 8 + 5] += p_pre[j] * bf16_hi(w.z);
+                    o[c * 8 + 6] += p_pre[j] * bf16_lo(w.w), o[c * 8 + 7] += p_pre[j] * bf16_hi(w.w);
+                }
+            }
+        }
+        if (row_valid) {
+            const float inv = 1.f / l;
+            __nv_bfloat16* op = p.out + (seq_row0 + qtok) * D + h * 64 + 32 * set;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 w;
+                w.x = pack_bf16x2(o[c * 8] * inv, o[c * 8 + 1] * inv), w.y = pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+                w.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv), w.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+                *reinterpret_cast<uint4*>(op + c * 8) = w;
+            }
+            if (p.lse && set == 0) {
+                if (p.pack) p.lse[((long)(b + pseq) * p.H + h) * T + (r - pseq * T)] = m * p.scale + logf(l);
+                else p.lse[((long)b * p.H + h) * T + qtok] = m * p.scale + logf(l);
+            }
+        }
+        tc_fence_before();
+    } else {
+        // ---------------- warp 9: prefix query rows (only the qt == 0 CTA), CUDA cores over the smem K/V tiles
+        if (qt == 0 && prefix > 0) {
+            mbar_wait(bar_qk, 0);
+            mbar_wait(bar_v, 0);
+            for (int j = 0; j < prefix; ++j) {
+                float qf[64];
+                {
+                    const uint4* qp = reinterpret_cast<const uint4*>(p.qkv + (seq_row0 + j) * 3 * D + h * 64);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 w = __ldg(qp + c);
+                        qf[c * 8 + 0] = bf16_lo(w.x), qf[c * 8 + 1] = bf16_hi(w.x), qf[c * 8 + 2] = bf16_lo(w.y);
+                        qf[c * 8 + 3] = bf16_hi(w.y), qf[c * 8 + 4] = bf16_lo(w.z), qf[c * 8 + 5] = bf16_hi(w.z);
+                        qf[c * 8 + 6] = bf16_lo(w.w), qf[c * 8 + 7] = bf16_hi(w.w);
+                    }
+                }
+                auto dot_row = [&](const uint4* kp, bool from_smem, int row) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const uint4 w = from_smem ? *reinterpret_cast<const uint4*>(smem + SK + sw128_off(row, c * 8))
+                                                  : __ldg(kp + c);
+                        acc += qf[c * 8 + 0] * bf16_lo(w.x) + qf[c * 8 + 1] * bf16_hi(w.x) + qf[c * 8 + 2] * bf16_lo(w.y) +
+                               qf[c * 8 + 3] * bf16_hi(w.y) + qf[c * 8 + 4] * bf16_lo(w.z) + qf[c * 8 + 5] * bf16_hi(w.z) +
+                               qf[c * 8 + 6] * bf16_lo(w.w) + qf[c * 8 + 7] * bf16_hi(w.w);
+                    }
+                    return acc;
+                };
+                float sp[MAX_PREFIX], s[8];
+                float m = -INFINITY;
+#pragma unroll
+                for (int t = 0; t < MAX_PREFIX; ++t) {
+                    sp[t] = -INFINITY;
+                    if (t < prefix && (!p.causal || t <= j))
+                        sp[t] = dot_row(reinterpret_cast<const uint4*>(p.qkv + (seq_row0 + t) * 3 * D + D + h * 64), false, 0);
+                    m = fmaxf(m, sp[t]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int kk = lane + 32 * i;
+                    s[i] = -INFINITY;
+                    if (kk < HW && kk < kvrows && (!p.causal || prefix + kk <= j)) s[i] = dot_row(nullptr, true, kk);
+                    m = fmaxf(m, s[i]);
+                }
+                __syncwarp();
+                if (j == prefix - 1 && lane == 0) mbar_arrive(bar_kfree);  // last read of the K tiles is behind us
+                m = warp_max(m);
+                const float msc = m * p.scale_log2;
+                float l = 0.f;
+                __nv_bfloat16* pcls = reinterpret_cast<__nv_bfloat16*>(smem + SPCLS);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float e = (s[i] == -INFINITY) ? 0.f : ex2f(s[i] * p.scale_log2 - msc);
+                    l += e;
+                    pcls[lane + 32 * i] = __float2bfloat16_rn(e);
+                }
+                l = warp_sum(l);
+                __syncwarp();
+                float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll
+                for (int t = 0; t < MAX_PREFIX; ++t) {
+                    if (t < prefix && sp[t] != -INFINITY) {
+                        const float pe = ex2f(sp[t] * p.scale_log2 - msc);
+                        l += pe;
+                        const uint32_t w = __ldg(reinterpret_cast<const uint32_t*>(p.qkv + (seq_row0 + t) * 3 * D + 2 * D + h * 64) + lane);
+                        a0 += bf16_round(pe) * bf16_lo(w), a1 += bf16_round(pe) * bf16_hi(w);
+                    }
+                }
+                const int kend = min(HW, kvrows);
+                for (int k8 = 0; k8 < kend; k8 += 8) {
+                    const uint4 pw = *reinterpret_cast<const uint4*>(pcls + k8);
+                    const uint32_t pr[4] = {pw.x, pw.y, pw.z, pw.w};
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const float pk = (u & 1) ? bf16_hi(pr[u >> 1]) : bf16_lo(pr[u >> 1]);
+                        const uint32_t w = *reinterpret_cast<const uint32_t*>(smem + SV + sw128_off(k8 + u, 2 * lane));
+                        if (u & 1) c0 += pk * bf16_lo(w), c1 += pk * bf16_hi(w);
+                        else a0 += pk * bf16_lo(w), a1 += pk * bf16_hi(w);
+                    }
+                }
+                a0 += c0, a1 += c1;
+                const float inv = 1.f / l;
+                *reinterpret_cast<uint32_t*>(p.out + (seq_row0 + j) * D + h * 64 + 2 * lane) = pack_bf16x2(a0 * inv, a1 * inv);
+                if (p.lse && lane == 0) p.lse[((long)b * p.H + h) * T + j] = m * p.scale + logf(l);
+            }
+        }
+    }
+
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem, 256);
+    }
+}
+
 }  // namespace vtp
 
 namespace vtp {
@@ -452,10 +784,15 @@ extern "C" int vtp_attention_fwd(const void* qkv, void* out, float* lse, int B, 
     static bool configured = false;
     if (!configured) {
         VTP_CUDA(cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
+        VTP_CUDA(cudaFuncSetAttribute(attn_fwd8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ATT_SMEM));
         configured = true;
     }
     dim3 grid(p.pack ? 1 : ceil_div(HW, 128), H, p.pack ? ceil_div(B, p.pack) : B);
-    attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tm, p);
+    const char* v8 = getenv("VTP_ATTN_FWD8");  // opt-in: two row threads per query row (see attn_fwd8_kernel)
+    if (v8 && v8[0] == '1')
+        attn_fwd8_kernel<<<grid, ATT8_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tm, p);
+    else
+        attn_fwd_kernel<<<grid, ATT_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tm, p);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }
