@@ -34,7 +34,7 @@ def parse():
     ap.add_argument("--model", default="small")
     ap.add_argument("--batch", type=int, default=256, help="source images per GPU per step")
     ap.add_argument("--prototypes", type=int, default=65536)
-    ap.add_argument("--cpu-batch", type=int, default=2, help="source images per step of the CPU baseline sample")
+    ap.add_argument("--cpu-batch", type=int, default=4, help="source images per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lpips", action="store_true", help="reconstruction loss = L1 only")
     return ap.parse_args()
@@ -129,6 +129,23 @@ def cpu_baseline(args, steps: int, warmup: int):
                       f"{cores} threads), {dt:.2f} s/step"}, dt
 
 
+def workload_config(args, world: int, flops_per_image: float, image_groups=None) -> dict:
+    """The `config` object of the JSON line — identical for both arms (the reference arm adds its bounded sample)."""
+    B = args.batch
+    cfg = {"workload": f"VTP-{args.model} f16d64 full 3-loss training step (contrastive+SSL+recon), batch={B}/GPU",
+           "model": "VTP-Small 384/12/6 x3 towers (ASSUMED, SURVEY.md §8d)" if args.model == "small" else args.model,
+           "global_batch": B * world, "image": 256, "crops": "2 global 256 + 8 local 96 per image",
+           "prototypes": args.prototypes,
+           "losses": ["clip", "dino_local", "dino_global", "ibot", "rec_l1"] + ([] if args.no_lpips else ["rec_lpips"]),
+           "lpips": (not args.no_lpips) and "VGG16 (frozen, seeded-random weights: pretrained ones need network), weight 1.0",
+           "optimizer": "fused AdamW + EMA teacher, in the timed region",
+           "l2": "inputs (>1 GB/step) and activations far exceed the 126 MB L2; no reuse across steps",
+           "parallelism": f"dp{world}", "flops_per_image": flops_per_image}
+    if image_groups is not None:
+        cfg["image_groups"] = image_groups
+    return cfg
+
+
 def log(msg):
     if os.environ.get("RANK", "0") == "0":
         print(f"[bench {time.strftime('%H:%M:%S')}] {msg}", file=sys.stderr, flush=True)
@@ -144,11 +161,17 @@ def main():
         if rank != 0:
             return
         cb, dt = cpu_baseline(args, steps=max(1, min(args.steps, 2)), warmup=min(args.warmup, 1))
+        from vtp_b200.config import preset
+        from vtp_b200.flops import train_step_flops_per_image
+        fl = train_step_flops_per_image(preset(args.model), K=args.prototypes, lpips=not args.no_lpips)
+        conf = workload_config(args, args.gpus, fl["total"])
+        conf["sample"] = (f"CPU restatement of the reference's step (oracle port, torch CPU, {cb['cores']} threads): each timed "
+                          f"step is a bounded sample of {args.cpu_batch} source images of this workload (same crops, "
+                          f"prototypes, losses, optimiser)")
         out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-               "config": {"workload": f"VTP-{args.model} full 3-loss training step, CPU restatement of the reference "
-                                      f"(oracle port), bounded sample of {args.cpu_batch} images/step"},
+               "config": conf,
                "cpu_baseline": cb,
                "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out))
@@ -282,14 +305,7 @@ def main():
         "metric": METRIC, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": f"VTP-{args.model} f16d64 full 3-loss training step (contrastive+SSL+recon), batch={B}/GPU",
-                   "model": "VTP-Small 384/12/6 x3 towers (ASSUMED, SURVEY.md §8d)" if args.model == "small" else args.model,
-                   "global_batch": B * world, "image": 256, "crops": "2 global 256 + 8 local 96 per image",
-                   "prototypes": args.prototypes, "losses": ["clip", "dino_local", "dino_global", "ibot", "rec_l1"] + ([] if args.no_lpips else ["rec_lpips"]),
-                   "lpips": (not args.no_lpips) and "VGG16 (frozen, seeded-random weights: pretrained ones need network), weight 1.0", "optimizer": "fused AdamW + EMA teacher, in the timed region",
-                   "l2": "inputs (>1 GB/step) and activations far exceed the 126 MB L2; no reuse across steps",
-                   "parallelism": f"dp{world}", "flops_per_image": fl["total"],
-                   "image_groups": {"ssl_chunk": ssl_chunk, "rec_chunk": rec_chunk}},
+        "config": workload_config(args, world, fl["total"], {"ssl_chunk": ssl_chunk, "rec_chunk": rec_chunk}),
         "e2e": {"value": imgs / (ms_e2e * 1e-3), "unit": "images/sec", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": int(loss_host.numel() * 4), "ms_per_step": ms_e2e / args.steps,
                 "pipeline": "vtp_b200.synthetic.BatchPrefetcher: pinned host batch of step i+1 copied on a side stream "
@@ -307,7 +323,7 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         log("cpu baseline ...")
-        cb, _ = cpu_baseline(args, steps=1, warmup=0)
+        cb, _ = cpu_baseline(args, steps=2, warmup=1)   # ~15 s of CPU work on the box's 32 threads
         out["cpu_baseline"] = cb
     print(json.dumps(out))
     if world > 1:
