@@ -1,0 +1,36 @@
+#!/bin/bash
+# One gpurun call = one pass over this list (each stage under its own timeout, outputs under gpurun_out/).
+#   tools/gpu_checklist.sh new        the GPU tests added since the last hardware run (+ the opt-in kernel variants)
+#   tools/gpu_checklist.sh perf       attention variants, HBM-bound kernels, inference sweep with CUDA graphs
+#   tools/gpu_checklist.sh bench      python bench.py (N = 1)
+#   tools/gpu_checklist.sh dist2      2-GPU tests (needs gpurun --gpus 2): NCCL and peer-memory contrastive exchange
+#   tools/gpu_checklist.sh all        everything above except dist2
+#   tools/gpu_checklist.sh first      new + the two short perf probes (fits a ~5 minute call)
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+what="${1:-new}"
+run() {  # run <name> <timeout-s> <cmd...>
+    local name="$1" t="$2"; shift 2
+    echo "=== $name (timeout ${t}s)"; local t0=$SECONDS
+    timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1; local rc=$?
+    echo "=== $name rc=$rc $((SECONDS - t0))s"; tail -n 15 "gpurun_out/$name.log"
+}
+if [[ "$what" == new || "$what" == all || "$what" == first ]]; then
+    # validated cases (tiny / small goldens, rows4 attention) are left to the full suite; the hang-prone opt-in kernel last
+    VTP_TEST_UNVALIDATED=1 run tests_new 200 python -u -m pytest -v -m gpu -p no:cacheprovider --timeout 90 \
+        -k "not tiny and not small and not rows4" \
+        tests/test_generation_gpu.py tests/test_clip_gpu.py tests/test_chunk_gpu.py tests/test_graphs_gpu.py \
+        tests/test_model_gpu.py "tests/test_kernels_gpu.py::test_attention_fwd"
+fi
+if [[ "$what" == perf || "$what" == all || "$what" == first ]]; then
+    run hbm_kernels 90 python tools/hbm_kernels_bench.py --out gpurun_out/hbm_kernels.json
+    run attn_prof 60 python tools/attn_prof.py
+    [[ "$what" == first ]] || run infer_sweep_small 180 python tools/infer_sweep.py --model small --batches 1,8,64 --graphs
+fi
+if [[ "$what" == bench || "$what" == all ]]; then
+    run bench 400 python bench.py
+fi
+if [[ "$what" == dist2 ]]; then
+    run tests_dist2 400 python -m pytest -q -m gpu -p no:cacheprovider tests/test_dist_gpu.py
+fi
