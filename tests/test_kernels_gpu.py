@@ -109,10 +109,8 @@ def _sdpa_ref(qkv, B, T, H, causal):
 @pytest.mark.parametrize("variant", ["rows4", "rows8"])
 def test_attention_fwd(B, T, H, prefix, causal, variant, monkeypatch):
     """rows4: one thread per query row (default); rows8: two threads per row, opt-in VTP_ATTN_FWD8=1 (attn_fwd8_kernel).
-    The rows8 kernel has not completed a hardware run yet: its cases run only with VTP_TEST_UNVALIDATED=1 (a kernel
-    that spins on an mbarrier must not be able to hang an unattended test run)."""
-    if variant == "rows8" and os.environ.get("VTP_TEST_UNVALIDATED") != "1":
-        pytest.skip("opt-in kernel variant, not yet validated on hardware (set VTP_TEST_UNVALIDATED=1)")
+    Both pass all shapes on hardware; rows8 measured x0.94 of rows4 at B=512, T=257 (profiles/hbm_kernels_r1.md), so it
+    stays opt-in."""
     monkeypatch.setenv("VTP_ATTN_FWD8", "1" if variant == "rows8" else "0")
     g = torch.Generator(device="cuda").manual_seed(B * 1000 + T)
     qkv = (torch.randn(B * T, 3 * H * 64, device="cuda", generator=g) * 1.5).to(BF)

@@ -34,3 +34,10 @@ fi
 if [[ "$what" == dist2 ]]; then
     run tests_dist2 400 python -m pytest -q -m gpu -p no:cacheprovider tests/test_dist_gpu.py
 fi
+if [[ "$what" == final ]]; then   # round-end rehearsal in ~2 minutes: smoke, bench (N = 1), the re-toleranced golden case, graphs sweep
+    run smoke 40 python -c "import __graft_entry__ as g; g.smoke()"
+    run bench 110 python bench.py
+    grep -E '^\{' gpurun_out/bench.log | tail -n 1 > gpurun_out/bench_line.json
+    run tests_large2 60 python -m pytest -q -m gpu -p no:cacheprovider tests/test_model_gpu.py -k large2
+    run infer_sweep_small 60 python tools/infer_sweep.py --model small --batches 1,8 --graphs
+fi
