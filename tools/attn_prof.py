@@ -33,6 +33,11 @@ os.environ["VTP_ATTN_FWD8"] = "1"     # opt-in variant: two row threads per quer
 o_ref = o.clone()
 uf8 = t(fwd)
 os.environ["VTP_ATTN_FWD8"] = "0"
+if os.environ.get("VTP_TEST_UNVALIDATED") == "1" and 128 < T - prefix <= 256:
+    os.environ["VTP_ATTN_FWD_PIPE"] = "1"   # persistent ping-pong kernel (attention_pipe.cu)
+    ufp = t(fwd)
+    os.environ["VTP_ATTN_FWD_PIPE"] = "0"
+    print(f"fwd pipe variant: {ufp:.1f} us (x{uf / ufp:.2f} vs rows4), max |diff| vs rows4 = {(o.float() - o_ref.float()).abs().max().item():.3e}")
 print(f"fwd rows8 variant: {uf8:.1f} us (x{uf / uf8:.2f} vs rows4), max |diff| vs rows4 = {(o.float() - o_ref.float()).abs().max().item():.3e}")
 print(f"B={B} T={T} H={H}: fwd {uf:.1f} us ({fl / uf / 1e6:.0f} TFLOP/s, {(M * 4 * D * 2) / uf / 1e3:.0f} GB/s)   "
       f"bwd {ub:.1f} us ({2.5 * fl / ub / 1e6:.0f} TFLOP/s, {(M * 8 * D * 2) / ub / 1e3:.0f} GB/s)")

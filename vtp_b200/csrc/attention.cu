@@ -13,27 +13,18 @@
 // threads, and their query rows are computed by a spare warp from the K/V tiles already in smem.
 #include <stdlib.h>
 
+#include "attention.h"
 #include "host.h"
 #include "ptx.cuh"
 
 namespace vtp {
 
 static constexpr int ATT_THREADS = 192;
-static constexpr int MAX_PREFIX = 4;
+static constexpr int MAX_PREFIX = ATT_MAX_PREFIX;
 // smem: Q 16K | K 32K | V 32K | P 32K | barriers
 static constexpr int SQ = 0, SK = 16384, SV = SK + 32768, SP = SV + 32768, SBAR = SP + 32768;
 static constexpr int SPCLS = SBAR + 128;      // bf16 [256]: softmax numerators of the cls query row (warp 5)
 static constexpr int ATT_SMEM = SPCLS + 512;  // 115328 B -> 2 CTAs/SM
-
-struct AttnDev {
-    const __nv_bfloat16* qkv;  // [B*T][3D]
-    __nv_bfloat16* out;        // [B*T][D]
-    float* lse;                // [B][H][T] or null
-    int B, T, H, D, prefix, HW, causal, nkt;  // nkt = number of 128-key tiles (1|2)
-    int pack;  // > 0: `pack` whole sequences (T <= 64 tokens, prefix tokens included as ordinary rows) share one 128-row tile
-    float scale_log2;                         // scale * log2(e)
-    float scale;
-};
 
 __device__ __forceinline__ float ex2f(float x) {  // ex2.approx.ftz (ex2f() carries a 4-instruction denormal slow path)
     float y;
@@ -788,6 +779,8 @@ extern "C" int vtp_attention_fwd(const void* qkv, void* out, float* lse, int B, 
         configured = true;
     }
     dim3 grid(p.pack ? 1 : ceil_div(HW, 128), H, p.pack ? ceil_div(B, p.pack) : B);
+    const char* vp = getenv("VTP_ATTN_FWD_PIPE");  // opt-in: persistent ping-pong kernel (attention_pipe.cu), 128 < HW <= 256
+    if (vp && vp[0] == '1' && !p.pack && !causal && p.nkt == 2 && HW % 8 == 0) return attn_fwd_pipe_launch(tm, p, (cudaStream_t)st);
     const char* v8 = getenv("VTP_ATTN_FWD8");  // opt-in: two row threads per query row (see attn_fwd8_kernel)
     if (v8 && v8[0] == '1')
         attn_fwd8_kernel<<<grid, ATT8_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tm, p);
