@@ -367,7 +367,10 @@ class VTPModel(VTPPreTrainedModel):
         mode = self._mode()
         W = self._pack("trunk", mode)
         depth = len(W.blocks)
-        take = list(range(depth - n, depth)) if isinstance(n, int) else list(n)
+        # the reference collects outputs while walking the blocks (vision_transformer.py:266-279): ascending block order
+        # whatever the order of `n`, and every requested index must exist exactly once
+        take = list(range(depth - n, depth)) if isinstance(n, int) else sorted(n)
+        assert len(set(take)) == len(take) and all(0 <= i < depth for i in take), f"only {len(set(take))} / {len(take)} blocks found"
         taps = {i: None for i in take}
         _, meta = E.trunk_forward(W, image, mode, taps=taps)
         B, T, gh, gw = meta
