@@ -28,3 +28,29 @@ def test_tape_bytes_formula():
     assert m.block_tape_bytes(D, Hs, "swiglu", False, H) == 20 * D + 6 * Hs + 4 * H + 8
     assert m.block_tape_bytes(D, Hs, "swiglu", True, H) == 16 * D + 6 * Hs + 4 * H + 8
     assert m.block_tape_bytes(D, 4 * D, "gelu", False, H) == 20 * D + 4 * 4 * D + 4 * H + 8
+
+
+def test_suggest_chunks_rejects_what_cannot_fit():
+    import pytest
+
+    with pytest.raises(ValueError):
+        m.suggest_chunks(preset("large"), 256, budget_bytes=40 * m.GIB)     # the contrastive pass alone is larger
+    # a tighter but feasible budget only makes the groups smaller
+    a = m.suggest_chunks(preset("large"), 256, budget_bytes=150 * m.GIB)
+    b = m.suggest_chunks(preset("large"), 256, budget_bytes=110 * m.GIB)
+    assert 0 < b[0] <= a[0]
+
+
+def test_latent_statistics_formula():
+    """LatentShardWriter.stats(): mean / unbiased std from fp64 sums (host arithmetic only)."""
+    import torch
+
+    from vtp_b200.generation import LatentShardWriter
+
+    z = torch.randn(5, 4, 3, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(0)) * 2 + 1
+    w = LatentShardWriter.__new__(LatentShardWriter)
+    w._sum, w._sumsq, w._n = z.sum(dim=(0, 2, 3)), (z * z).sum(dim=(0, 2, 3)), z.numel() // z.shape[1]
+    st = w.stats()
+    assert st["mean"].shape == (1, 4, 1, 1) and st["std"].dtype == torch.float32
+    assert torch.allclose(st["mean"].double(), z.mean(dim=(0, 2, 3), keepdim=True), atol=1e-6)
+    assert torch.allclose(st["std"].double(), z.std(dim=(0, 2, 3), keepdim=True), atol=1e-6)
