@@ -69,6 +69,8 @@ def test_two_rank_step_equals_global_batch(exchange):
     """nccl: all-gather + all-reduced cross terms; p2p: peer-memory gather fused with the logits (csrc/clip.cu)."""
     import torch.multiprocessing as mp
 
+    if exchange == "p2p" and os.environ.get("VTP_TEST_UNVALIDATED") != "1":
+        pytest.skip("the peer-memory exchange has only run on one GPU so far (set VTP_TEST_UNVALIDATED=1 on a 2-GPU box)")
     world, port = 2, _free_port()
     mgr = mp.Manager()
     out = mgr.dict()

@@ -32,7 +32,7 @@ if [[ "$what" == bench || "$what" == all ]]; then
     run bench 400 python bench.py
 fi
 if [[ "$what" == dist2 ]]; then
-    run tests_dist2 400 python -m pytest -q -m gpu -p no:cacheprovider tests/test_dist_gpu.py
+    VTP_TEST_UNVALIDATED=1 run tests_dist2 400 python -m pytest -v -m gpu -p no:cacheprovider tests/test_dist_gpu.py
 fi
 if [[ "$what" == final ]]; then   # round-end rehearsal in ~2 minutes: smoke, bench (N = 1), the re-toleranced golden case, graphs sweep
     run smoke 40 python -c "import __graft_entry__ as g; g.smoke()"
