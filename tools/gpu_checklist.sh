@@ -21,11 +21,15 @@ if [[ "$what" == new || "$what" == all || "$what" == first ]]; then
     VTP_TEST_UNVALIDATED=1 run tests_new 200 python -u -m pytest -v -m gpu -p no:cacheprovider --timeout 90 \
         -k "not tiny and not small and not rows4" \
         tests/test_generation_gpu.py tests/test_clip_gpu.py tests/test_chunk_gpu.py tests/test_graphs_gpu.py \
-        tests/test_model_gpu.py "tests/test_kernels_gpu.py::test_attention_fwd"
+        tests/test_model_gpu.py "tests/test_gemm_gpu.py::test_gemm_wide_cluster_multicast" \
+        "tests/test_kernels_gpu.py::test_attention_fwd"
 fi
 if [[ "$what" == perf || "$what" == all || "$what" == first ]]; then
     run hbm_kernels 90 python tools/hbm_kernels_bench.py --out gpurun_out/hbm_kernels.json
     VTP_TEST_UNVALIDATED=1 run attn_prof 60 python tools/attn_prof.py
+    if [[ "$what" != first ]]; then   # B-tile multicast across 2 (default) / 4 / 8 CTAs: the L2->SM feed experiment
+        for clm in 2 4 8; do VTP_GEMM_CLM=$clm run gemm_bench_clm$clm 90 python tools/gemm_bench.py; done
+    fi
     [[ "$what" == first ]] || run infer_sweep_small 180 python tools/infer_sweep.py --model small --batches 1,8,64 --graphs
 fi
 if [[ "$what" == bench || "$what" == all ]]; then

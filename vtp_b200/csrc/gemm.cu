@@ -517,13 +517,18 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
 // and only HALF of B (the MMA reads both halves across the pair), so the shared-memory fill per flop drops by a third
 // against the multicast variant — the L2->SM feed is what caps the 128 x BN kernel at ~1.3 PFLOP/s.  The leader CTA's
 // MMA thread issues for both; full barriers (both CTAs' TMA bytes) and accumulator-empty barriers live in the leader.
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST, bool G2>
+// CLM (with CL2, not G2): number of CTAs in the cluster along M that share one B tile.  Each loads its own A tile and
+// 1/CLM of B, multicast to all CLM.  2 is the validated default; 4 / 8 exist because the L2->SM delivery only drops with
+// multicast at cluster sizes above 4 and are opt-in (VTP_GEMM_CLM) until they have run on hardware.
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST, bool G2, int CLM>
 // 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168 (MINB = 1).
 // MINB = 2 (short-K shapes): two CTAs per SM with a 2-stage ring double the epilogue warps per SM at ~100 registers.
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const GemmDev p) {
     static_assert(!G2 || CL2, "cta_group::2 needs the 2-CTA cluster");
+    static_assert(CLM == 2 || (CL2 && !G2 && (CLM == 4 || CLM == 8)), "CLM in {2,4,8}; > 2 only for the multicast variant");
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CLM) - 1u);  // every CTA of the cluster
     constexpr int B_BYTES = (G2 ? BN / 2 : BN) * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr int ACC_STRIDE = BN == 192 ? 256 : BN;  // column distance of the two accumulator buffers
@@ -547,14 +552,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const uint32_t crank = CL2 ? cluster_ctarank() : 0u;
-    const int work_id = CL2 ? (blockIdx.x >> 1) : blockIdx.x;      // CTA pairs share a work item (tile pair)
-    const int work_stride = CL2 ? (gridDim.x >> 1) : gridDim.x;
+    const int work_id = CL2 ? (blockIdx.x / CLM) : blockIdx.x;      // the CTAs of a cluster share a work item (CLM tiles)
+    const int work_stride = CL2 ? (gridDim.x / CLM) : gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (FAST) tma_prefetch_desc(&tmO);
-        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], (CL2 && !G2) ? 2 : 1);
+        for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], (CL2 && !G2) ? CLM : 1);
         for (int s = 0; s < 2; ++s)
             mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], G2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
         fence_barrier_init();
@@ -580,7 +585,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t ph = 0;
             for (int t = work_id; t < num_tiles; t += work_stride) {
                 const int n_blk = t % p.num_n_blocks;
-                const int m_blk = ((t / p.num_n_blocks) % p.num_m_blocks) * (CL2 ? 2 : 1) + (int)crank;
+                const int m_blk = ((t / p.num_n_blocks) % p.num_m_blocks) * (CL2 ? CLM : 1) + (int)crank;
                 const int ks = t / tiles_mn;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -620,14 +625,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             for (int i = 0; i < BN / 128; ++i)
                                 tma_load_2d_g2(sb + i * 8192, &tmB, lbar, n0 + ((int)crank * (BN / 128) + i) * 64, k0);
                         }
-                    } else if (CL2) {  // my half of B, delivered to both CTAs of the pair
+                    } else if (CL2) {  // my 1/CLM of B, delivered to every CTA of the cluster
                         if (!p.b_mn) {
-                            tma_load_2d_mc(sb + crank * (BN / 2) * 128, &tmB, &full_bar[s], k0, n0 + (int)crank * (BN / 2), 3);
+                            tma_load_2d_mc(sb + crank * (BN / CLM) * 128, &tmB, &full_bar[s], k0, n0 + (int)crank * (BN / CLM),
+                                           MC_MASK);
                         } else {
+                            static_assert(CLM <= 2 || (BN / 64) % CLM == 0 || CLM == 8, "MN-major B: 64-column chunks per CTA");
 #pragma unroll
                             for (int i = 0; i < BN / 64; ++i)
-                                if ((i & 1) == (int)crank)
-                                    tma_load_2d_mc(sb + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, k0, 3);
+                                if ((i % CLM) == (int)crank)
+                                    tma_load_2d_mc(sb + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, k0, MC_MASK);
                         }
                     } else if (!p.b_mn) {
                         tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
@@ -672,7 +679,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     }
                     // frees the smem slot once these MMAs have read it (in both CTAs: the peer multicasts into mine)
                     if (G2) umma_commit_mc_g2(&empty_bar[s], 3);
-                    else if (CL2) umma_commit_mc(&empty_bar[s], 3);
+                    else if (CL2) umma_commit_mc(&empty_bar[s], MC_MASK);
                     else umma_commit(&empty_bar[s]);
                     if (++s == STAGES) s = 0, ph ^= 1;
                 }
@@ -692,7 +699,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         uint32_t aph = 0;
         for (int t = work_id; t < num_tiles; t += work_stride) {
             const int n_blk = t % p.num_n_blocks;
-            const int m_blk = ((t / p.num_n_blocks) % p.num_m_blocks) * (CL2 ? 2 : 1) + (int)crank;
+            const int m_blk = ((t / p.num_n_blocks) % p.num_m_blocks) * (CL2 ? CLM : 1) + (int)crank;
             const int m0 = m_blk * BM, n0 = n_blk * BN;
             const int grow0 = m0 + q * 32;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE;
@@ -760,14 +767,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0, bool G2 = false>
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0, bool G2 = false, int CLM = 2>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream,
                        const CUtensorMap* tmO = nullptr) {
     constexpr int smem_bytes = STAGES * (A_BYTES + (G2 ? BN / 2 : BN) * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 +
                                (FAST ? NUM_EPI_WARPS * 256 + 256 : 1024 + 256);
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>,
+        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2, CLM>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
@@ -776,18 +783,30 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];
     if (CL2) {
-        const int pairs = MINB * num_sms() / 2;
-        cfg.gridDim = dim3(2 * (work < pairs ? work : pairs));
+        int groups = MINB * num_sms() / CLM;  // co-resident clusters of the persistent grid
+        cfg.blockDim = dim3(NUM_THREADS);
+        cfg.dynamicSmemBytes = smem_bytes;
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = CLM, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
+        if (CLM > 2) {  // clusters of 4 / 8 SMs must fit inside a GPC: ask the driver how many can be resident at once
+            static int max_clusters = 0;
+            if (max_clusters == 0) {
+                cfg.gridDim = dim3(CLM * groups);
+                int n = 0;
+                VTP_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2, CLM>, &cfg));
+                max_clusters = n > 0 ? n : 1;
+            }
+            if (groups > max_clusters) groups = max_clusters;
+        }
+        cfg.gridDim = dim3(CLM * (work < groups ? work : groups));
     } else {
         cfg.gridDim = dim3(work < MINB * num_sms() ? work : MINB * num_sms());
     }
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>, tmA, tmB, tmO ? *tmO : tmA, p));
+    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2, CLM>, tmA, tmB, tmO ? *tmO : tmA, p));
     return VTP_OK;
 }
 
@@ -869,6 +888,18 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     const bool short_bn128 = getenv("VTP_GEMM_SHORTK_BN128") != nullptr;
     if (short_bn128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1 && a->conv_C == 0) BN = 128;
 
+    // cluster size along M of the B-tile multicast: 2 (validated) unless VTP_GEMM_CLM = 4 | 8 asks for the wider sharing,
+    // which exists for the lean-epilogue 256-wide forward/dgrad tiles only (8: K-major B only — the MN-major B tile is
+    // loaded in four 64-column chunks) and has not run on hardware yet
+    int clm = 2;
+    if (cl2 && !g2 && fast && !conv && !a->mask_pos && BN == 256) {
+        const char* e = getenv("VTP_GEMM_CLM");
+        const int v = e ? atoi(e) : 2;
+        if (v == 4 || v == 8) clm = v;
+        if (clm == 8 && a->b_mn_major) clm = 4;
+        while (clm > 2 && ceil_div(a->M, BM) < clm) clm >>= 1;
+    }
+
     GemmDev p;
     memset(&p, 0, sizeof(p));
     p.M = a->M, p.N = a->N, p.K = a->K;
@@ -917,12 +948,12 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     {
         uint64_t dims[2], strides[1] = {(uint64_t)a->ldb * 2};
         uint32_t box[2];
-        if (!p.b_mn) dims[0] = a->K, dims[1] = a->N, box[0] = 64, box[1] = (uint32_t)(cl2 ? BN / 2 : BN);
+        if (!p.b_mn) dims[0] = a->K, dims[1] = a->N, box[0] = 64, box[1] = (uint32_t)(cl2 ? BN / clm : BN);
         else dims[0] = a->N, dims[1] = a->K, box[0] = 64, box[1] = 64;
         int rc = make_tmap_bf16(&tmB, a->B, 2, dims, strides, box);
         if (rc) return rc;
     }
-    if (cl2) p.num_m_blocks = ceil_div(p.num_m_blocks, 2);  // tile pairs
+    if (cl2) p.num_m_blocks = ceil_div(p.num_m_blocks, clm);  // groups of clm vertically adjacent tiles (pairs by default)
     // one instantiation per epilogue family keeps each kernel's code (and register pressure) small
     // short reductions (<= 16 k-blocks) with 128-wide tiles are epilogue/latency bound: run two CTAs per SM
     // (measured: proj+resid 237 -> 178 us, fc2+resid 244 -> 198 us at M = 131 584)
@@ -960,6 +991,8 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
             if (cl2) return launch_gemm<192, 4, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO);              \
             return launch_gemm<192, 4, ACT_, false, false, 1, MODE_>(tmA, tmB, p, stream, &tmO);                      \
         }                                                                                                             \
+        if (clm == 4) return launch_gemm<256, 4, ACT_, false, true, 1, MODE_, false, 4>(tmA, tmB, p, stream, &tmO);   \
+        if (clm == 8) return launch_gemm<256, 4, ACT_, false, true, 1, MODE_, false, 8>(tmA, tmB, p, stream, &tmO);   \
         if (cl2)                                                                                                      \
             return (BN == 256) ? launch_gemm<256, 4, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO)          \
                                : launch_gemm<128, 6, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO);         \
