@@ -186,10 +186,12 @@ def test_gemm_fast_epilogue_modes(monkeypatch, variant, out_f32, resid, relu, M,
 @pytest.mark.parametrize("clm", [4, 8])
 @pytest.mark.parametrize("out_f32,resid", [(False, False), (True, True)])
 @pytest.mark.parametrize("M,N,K,b_mn", [(2048, 512, 384, False), (1000, 1160, 200, False), (4100, 2048, 384, False),
-                                        (1536, 512, 256, True)])
+                                        (1536, 512, 256, True), (2048, 384, 512, False), (1100, 128, 384, False),
+                                        (1300, 384, 1024, True)])
 def test_gemm_wide_cluster_multicast(monkeypatch, clm, out_f32, resid, M, N, K, b_mn):
-    """VTP_GEMM_CLM = 4 | 8: the B tile multicast across 4 / 8 CTAs along M (256-wide lean-epilogue tiles), incl. M tails
-    that leave all-OOB tiles in the last cluster and the MN-major-B (dgrad) form (8 falls back to 4 there).  These
+    """VTP_GEMM_CLM = 4 | 8: the B tile multicast across 4 / 8 CTAs along M (256-, 192- and 128-wide lean-epilogue tiles),
+    incl. M tails that leave all-OOB tiles in the last cluster and the MN-major-B (dgrad) form, where the cluster size falls
+    back to what divides the BN/64 column chunks (256: 4; 192, 128: 2).  These
     instantiations were written after the round's GPU budget was spent: gated until their first hardware run."""
     import os
 

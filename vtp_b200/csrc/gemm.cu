@@ -630,7 +630,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             tma_load_2d_mc(sb + crank * (BN / CLM) * 128, &tmB, &full_bar[s], k0, n0 + (int)crank * (BN / CLM),
                                            MC_MASK);
                         } else {
-                            static_assert(CLM <= 2 || (BN / 64) % CLM == 0 || CLM == 8, "MN-major B: 64-column chunks per CTA");
+                            // MN-major B arrives in BN/64 chunks of 64 columns: the host only picks a CLM that divides them
+                            if (CLM > 2 && (BN / 64) % CLM != 0) __trap();
 #pragma unroll
                             for (int i = 0; i < BN / 64; ++i)
                                 if ((i % CLM) == (int)crank)
@@ -892,11 +893,12 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     // which exists for the lean-epilogue 256-wide forward/dgrad tiles only (8: K-major B only — the MN-major B tile is
     // loaded in four 64-column chunks) and has not run on hardware yet
     int clm = 2;
-    if (cl2 && !g2 && fast && !conv && !a->mask_pos && BN == 256) {
+    if (cl2 && !g2 && fast && !conv && !a->mask_pos) {
         const char* e = getenv("VTP_GEMM_CLM");
         const int v = e ? atoi(e) : 2;
         if (v == 4 || v == 8) clm = v;
-        if (clm == 8 && a->b_mn_major) clm = 4;
+        if (a->b_mn_major)   // the MN-major B tile is loaded in BN/64 chunks of 64 columns: one or more whole chunks per CTA
+            while (clm > 2 && (BN / 64) % clm != 0) clm >>= 1;
         while (clm > 2 && ceil_div(a->M, BM) < clm) clm >>= 1;
     }
 
@@ -987,12 +989,20 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         if (g2)                                                                                                       \
             return (BN == 256) ? launch_gemm<256, 6, ACT_, false, true, 1, MODE_, true>(tmA, tmB, p, stream, &tmO)    \
                                : launch_gemm<128, 8, ACT_, false, true, 1, MODE_, true>(tmA, tmB, p, stream, &tmO);   \
+        if (clm == 4) {                                                                                               \
+            if (BN == 192) return launch_gemm<192, 4, ACT_, false, true, 1, MODE_, false, 4>(tmA, tmB, p, stream, &tmO); \
+            return (BN == 256) ? launch_gemm<256, 4, ACT_, false, true, 1, MODE_, false, 4>(tmA, tmB, p, stream, &tmO) \
+                               : launch_gemm<128, 6, ACT_, false, true, 1, MODE_, false, 4>(tmA, tmB, p, stream, &tmO); \
+        }                                                                                                             \
+        if (clm == 8) {                                                                                               \
+            if (BN == 192) return launch_gemm<192, 4, ACT_, false, true, 1, MODE_, false, 8>(tmA, tmB, p, stream, &tmO); \
+            return (BN == 256) ? launch_gemm<256, 4, ACT_, false, true, 1, MODE_, false, 8>(tmA, tmB, p, stream, &tmO) \
+                               : launch_gemm<128, 6, ACT_, false, true, 1, MODE_, false, 8>(tmA, tmB, p, stream, &tmO); \
+        }                                                                                                             \
         if (BN == 192) {                                                                                              \
             if (cl2) return launch_gemm<192, 4, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO);              \
             return launch_gemm<192, 4, ACT_, false, false, 1, MODE_>(tmA, tmB, p, stream, &tmO);                      \
         }                                                                                                             \
-        if (clm == 4) return launch_gemm<256, 4, ACT_, false, true, 1, MODE_, false, 4>(tmA, tmB, p, stream, &tmO);   \
-        if (clm == 8) return launch_gemm<256, 4, ACT_, false, true, 1, MODE_, false, 8>(tmA, tmB, p, stream, &tmO);   \
         if (cl2)                                                                                                      \
             return (BN == 256) ? launch_gemm<256, 4, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO)          \
                                : launch_gemm<128, 6, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO);         \
