@@ -48,7 +48,7 @@ def _worker(rank, world, port, out, exchange="nccl"):
     loss = (loss / world).cpu()
     # single-process global-batch reference on the same device
     ref = VTPTrainer(cfg, tc, device=f"cuda:{rank}")
-    ref.world, ref.rank = 1, 0
+    ref.world, ref.rank = 1, 0              # (its contrastive exchange, if peer-memory, is built for world = 1 too)
     ref.import_state_dict(sd)
     ref.clip_fwd_bwd(x, ids, 1.0)
     ref.rec_fwd_bwd(x, 1.0)

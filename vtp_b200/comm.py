@@ -37,15 +37,17 @@ def alias_bf16(ptr: int, shape, device) -> torch.Tensor:
 class PeerFeatures:
     """Feature exchange buffers of one rank + the mapped addresses of every peer's."""
 
-    def __init__(self, B: int, E: int, device, process_group=None):
+    def __init__(self, B: int, E: int, device, process_group=None, world: Optional[int] = None, rank: Optional[int] = None):
+        """world / rank default to the process group's; a trainer that runs single-rank inside an initialised job (the
+        global-batch reference of the 2-GPU test) passes world = 1 and takes no part in any collective."""
         import torch.distributed as dist
 
         self.B, self.E = B, E
         self.device = torch.device(device)
         self.pg = process_group
         live = dist.is_available() and dist.is_initialized()
-        self.world = dist.get_world_size(process_group) if live else 1
-        self.rank = dist.get_rank(process_group) if live else 0
+        self.world = world if world is not None else (dist.get_world_size(process_group) if live else 1)
+        self.rank = rank if rank is not None else (dist.get_rank(process_group) if live and self.world > 1 else 0)
         if self.world > 16:
             raise lib.VtpError("the peer-memory contrastive exchange supports at most 16 ranks (one NVSwitch domain)")
         self.feat_bytes = B * E * 2

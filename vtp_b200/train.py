@@ -549,7 +549,7 @@ class VTPTrainer:
         if self.peer is None or self.peer.B != B:
             if self.peer is not None:
                 self.peer.close()
-            self.peer = PeerFeatures(B, Dt, dev, self.pg)
+            self.peer = PeerFeatures(B, Dt, dev, self.pg, world=self.world, rank=self.rank)
         pf = self.peer
         lib.l2norm_fwd(fi_raw, pf.img, B, Dt, 1e-12, norm_out=nrm_i)
         lib.l2norm_fwd(ft_raw, pf.txt, B, Dt, 1e-12, norm_out=nrm_t)
