@@ -893,7 +893,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     // which exists for the lean-epilogue 256-wide forward/dgrad tiles only (8: K-major B only — the MN-major B tile is
     // loaded in four 64-column chunks) and has not run on hardware yet
     int clm = 2;
-    if (cl2 && !g2 && fast && !conv && !a->mask_pos) {
+    if (cl2 && !g2 && fast && !a->mask_pos) {   // incl. the implicit-conv form (LPIPS): B = the K-major weights
         const char* e = getenv("VTP_GEMM_CLM");
         const int v = e ? atoi(e) : 2;
         if (v == 4 || v == 8) clm = v;
