@@ -190,8 +190,8 @@ def test_gemm_fast_epilogue_modes(monkeypatch, variant, out_f32, resid, relu, M,
                                         (1300, 384, 1024, True)])
 def test_gemm_wide_cluster_multicast(monkeypatch, clm, out_f32, resid, M, N, K, b_mn):
     """VTP_GEMM_CLM = 4 | 8: the B tile multicast across 4 / 8 CTAs along M (256-, 192- and 128-wide lean-epilogue tiles),
-    incl. M tails that leave all-OOB tiles in the last cluster and the MN-major-B (dgrad) form, where the cluster size falls
-    back to what divides the BN/64 column chunks (256: 4; 192, 128: 2).  These
+    incl. M tails that leave all-OOB tiles in the last cluster and the MN-major-B (dgrad) form, where the B tile is dealt out in
+    whole 64-column chunks when they divide evenly (256-wide, 4 CTAs) and sliced by k-rows otherwise.  These
     instantiations were written after the round's GPU budget was spent: gated until their first hardware run."""
     import os
 
@@ -219,3 +219,22 @@ def test_gemm_wide_cluster_multicast(monkeypatch, clm, out_f32, resid, M, N, K, 
     assert torch.isfinite(out.float()).all()
     assert (out.float() - ref.float()).abs().max().item() <= 2.0 ** -7 * ref.float().abs().max().item() + 1e-6
     assert _relerr(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("clm", [4, 8])
+@pytest.mark.parametrize("M,N,K,split", [(2048, 384, 20000, -1), (1024, 1024, 9000, -1), (1152, 128, 9000, 4), (600, 768, 4100, -1)])
+def test_gemm_wide_cluster_wgrad_form(monkeypatch, clm, M, N, K, split):
+    """VTP_GEMM_CLM on the wgrad form (TN, split-K + fp32 red.add): the MN-major B tile is sliced by k-rows across the
+    cluster when its 64-column chunks do not divide evenly (192-wide: 3 chunks; 256-wide with 8 CTAs).  Gated: not yet run
+    on hardware."""
+    import os
+
+    if os.environ.get("VTP_TEST_UNVALIDATED") != "1":
+        pytest.skip("not yet run on hardware (set VTP_TEST_UNVALIDATED=1)")
+    monkeypatch.setenv("VTP_GEMM_CLM", str(clm))
+    A, B = _mk((K, M), 31), _mk((K, N), 32)
+    out = torch.ones((M, N), device="cuda")
+    lib.gemm(A, B, out, M=M, N=N, K=K, a_mn=True, b_mn=True, accumulate=True, split_k=split, round_bf16=False)
+    torch.cuda.synchronize()
+    ref = _ref(A, B, True, True) + 1.0
+    assert _relerr(out, ref) < 2e-5

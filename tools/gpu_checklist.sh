@@ -21,7 +21,7 @@ if [[ "$what" == new || "$what" == all || "$what" == first ]]; then
     VTP_TEST_UNVALIDATED=1 run tests_new 200 python -u -m pytest -v -m gpu -p no:cacheprovider --timeout 90 \
         -k "not tiny and not small and not rows4" \
         tests/test_generation_gpu.py tests/test_clip_gpu.py tests/test_chunk_gpu.py tests/test_graphs_gpu.py \
-        tests/test_model_gpu.py "tests/test_gemm_gpu.py::test_gemm_wide_cluster_multicast" \
+        tests/test_model_gpu.py "tests/test_gemm_gpu.py::test_gemm_wide_cluster_multicast" "tests/test_gemm_gpu.py::test_gemm_wide_cluster_wgrad_form" \
         "tests/test_lpips_gpu.py::test_conv_mode_wide_cluster_multicast" \
         "tests/test_kernels_gpu.py::test_attention_fwd"
 fi

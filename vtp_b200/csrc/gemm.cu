@@ -630,12 +630,20 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             tma_load_2d_mc(sb + crank * (BN / CLM) * 128, &tmB, &full_bar[s], k0, n0 + (int)crank * (BN / CLM),
                                            MC_MASK);
                         } else {
-                            // MN-major B arrives in BN/64 chunks of 64 columns: the host only picks a CLM that divides them
-                            if (CLM > 2 && (BN / 64) % CLM != 0) __trap();
+                            // MN-major B arrives in BN/64 chunks of 64 columns x 64 k-rows.  If the chunks divide evenly they are
+                            // dealt out whole; otherwise (wide clusters) every CTA loads its 64/CLM k-rows of EVERY chunk
+                            // (tensor-map box {64, 64/CLM}; 8 rows = one 1 KB swizzle atom, so the slices stay atom-aligned)
+                            if constexpr (CLM > 2 && (BN / 64) % CLM != 0) {
 #pragma unroll
-                            for (int i = 0; i < BN / 64; ++i)
-                                if ((i % CLM) == (int)crank)
-                                    tma_load_2d_mc(sb + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, k0, MC_MASK);
+                                for (int i = 0; i < BN / 64; ++i)
+                                    tma_load_2d_mc(sb + i * 8192 + crank * (64 / CLM) * 128, &tmB, &full_bar[s], n0 + 64 * i,
+                                                   k0 + (int)crank * (64 / CLM), MC_MASK);
+                            } else {
+#pragma unroll
+                                for (int i = 0; i < BN / 64; ++i)
+                                    if ((i % CLM) == (int)crank)
+                                        tma_load_2d_mc(sb + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, k0, MC_MASK);
+                            }
                         }
                     } else if (!p.b_mn) {
                         tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
@@ -892,15 +900,17 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     // cluster size along M of the B-tile multicast: 2 (validated) unless VTP_GEMM_CLM = 4 | 8 asks for the wider sharing,
     // which exists for the lean-epilogue 256-wide forward/dgrad tiles only (8: K-major B only — the MN-major B tile is
     // loaded in four 64-column chunks) and has not run on hardware yet
+    // (short-K 128-wide accumulate shapes keep the two-CTAs-per-SM kernel)
+    const bool two_plain = plain_acc && BN == 128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1;
     int clm = 2;
-    if (cl2 && !g2 && fast && !a->mask_pos) {   // incl. the implicit-conv form (LPIPS): B = the K-major weights
+    if (cl2 && !g2 && (fast || plain_acc) && !a->mask_pos && !two_plain) {   // incl. the implicit-conv form (LPIPS convs)
         const char* e = getenv("VTP_GEMM_CLM");
         const int v = e ? atoi(e) : 2;
         if (v == 4 || v == 8) clm = v;
-        if (a->b_mn_major)   // the MN-major B tile is loaded in BN/64 chunks of 64 columns: one or more whole chunks per CTA
-            while (clm > 2 && (BN / 64) % clm != 0) clm >>= 1;
         while (clm > 2 && ceil_div(a->M, BM) < clm) clm >>= 1;
     }
+    // MN-major B (dgrad, wgrad): whole 64-column chunks per CTA when they divide evenly, else 64/clm k-rows of every chunk
+    const bool b_kslice = a->b_mn_major && clm > 2 && (BN / 64) % clm != 0;
 
     GemmDev p;
     memset(&p, 0, sizeof(p));
@@ -951,7 +961,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         uint64_t dims[2], strides[1] = {(uint64_t)a->ldb * 2};
         uint32_t box[2];
         if (!p.b_mn) dims[0] = a->K, dims[1] = a->N, box[0] = 64, box[1] = (uint32_t)(cl2 ? BN / clm : BN);
-        else dims[0] = a->N, dims[1] = a->K, box[0] = 64, box[1] = 64;
+        else dims[0] = a->N, dims[1] = a->K, box[0] = 64, box[1] = (uint32_t)(b_kslice ? 64 / clm : 64);
         int rc = make_tmap_bf16(&tmB, a->B, 2, dims, strides, box);
         if (rc) return rc;
     }
@@ -1042,6 +1052,15 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     if (g2 && a->act == VTP_ACT_NONE && !(two && getenv("VTP_GEMM_G2_NOT_SHORT")))  // wgrad (split-K), logits, ...
         return (BN == 256) ? launch_gemm<256, 6, VTP_ACT_NONE, false, true, 1, 0, true>(tmA, tmB, p, stream)
                            : launch_gemm<128, 8, VTP_ACT_NONE, false, true, 1, 0, true>(tmA, tmB, p, stream);
+    if (plain_acc && clm > 2) {  // wgrad / accumulate form with the wide B-tile multicast (opt-in, VTP_GEMM_CLM)
+        if (clm == 4)
+            return BN == 192   ? launch_gemm<192, 4, VTP_ACT_NONE, false, true, 1, 0, false, 4>(tmA, tmB, p, stream)
+                   : BN == 256 ? launch_gemm<256, 4, VTP_ACT_NONE, false, true, 1, 0, false, 4>(tmA, tmB, p, stream)
+                               : launch_gemm<128, 6, VTP_ACT_NONE, false, true, 1, 0, false, 4>(tmA, tmB, p, stream);
+        return BN == 192   ? launch_gemm<192, 4, VTP_ACT_NONE, false, true, 1, 0, false, 8>(tmA, tmB, p, stream)
+               : BN == 256 ? launch_gemm<256, 4, VTP_ACT_NONE, false, true, 1, 0, false, 8>(tmA, tmB, p, stream)
+                           : launch_gemm<128, 6, VTP_ACT_NONE, false, true, 1, 0, false, 8>(tmA, tmB, p, stream);
+    }
     if (BN == 192) {  // only chosen for the fast path (returned above) and the plain split-K accumulate path
         if (cl2) return launch_gemm<192, 4, VTP_ACT_NONE, false, true, 1>(tmA, tmB, p, stream);
         return launch_gemm<192, 4, VTP_ACT_NONE, false, false, 1>(tmA, tmB, p, stream);
