@@ -9,10 +9,12 @@ Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl refere
 The product path (vtp_b200/) never does.
 
 PINNING: the model-side functions are pinned against the real reference imported in the dev container
-(tests/test_oracle_vs_reference.py, runs where /root/reference exists) and against committed golden vectors generated
-from the real reference (tests/golden/, script oracle/make_golden.py).  The three LOSSES do not exist in the
-reference — they are restated from OpenCLIP ClipLoss and DINOv2 DINOLoss/iBOTPatchLoss definitions:
-**loss parity is unpinned** (checked only against an independent fp64 restatement in tests).
+(tests/test_oracle_golden.py::test_oracle_matches_live_reference, runs where /root/reference exists) and against
+committed golden vectors generated from the real reference (tests/golden/, scripts oracle/make_golden.py for the HF
+inference API and oracle/make_golden_legacy.py for the legacy training meta-arch: `VTP.forward_ssl_learning`,
+`update_teacher`, `DINOHead`, `LPIPS`).  The three LOSS FUNCTIONS do not exist in the reference — they
+are restated from OpenCLIP ClipLoss and DINOv2 DINOLoss/iBOTPatchLoss definitions: **loss parity is unpinned**
+(checked only against an independent fp64 restatement in tests).
 
 `mode`:
   "fp32"  — the reference run in fp32 (what `tools/test_reconstruction_hf.py` does for the decoder / on CPU).
@@ -368,3 +370,67 @@ def recon_loss(rec: Tensor, target: Tensor, lpips_val: Optional[Tensor], lpips_w
     if lpips_val is not None:
         l = l + lpips_weight * lpips_val.mean()
     return l
+
+
+# ----------------------------------------------------------------------------------------------- legacy meta-arch
+def legacy_to_hf_keys(sd: Dict[str, Tensor]) -> Dict[str, Tensor]:
+    """Legacy `VTP.state_dict()` (vtp/models/vtp.py: `proj`, `transformer.resblocks.*`, `teacher_*`, `dino_head.*`)
+    -> the HF `VTPModel` key names the rest of this file reads (`visual_proj`, `text_transformer.resblocks.*`); teacher
+    and head keys pass through unchanged."""
+    out = {}
+    for k, v in sd.items():
+        if k == "proj.weight":
+            out["visual_proj.weight"] = v
+        elif k.startswith("transformer.resblocks."):
+            out["text_" + k] = v
+        else:
+            out[k] = v
+    return out
+
+
+def ssl_forward(sd, global_crops: Tensor, local_crops: Tensor, masks: Tensor, mask_indices: Tensor, *, depth: int,
+                heads: int, mode: str = "fp32", upperbound: Optional[int] = None) -> Dict[str, Tensor]:
+    """`VTP.forward_ssl_learning` (vtp/models/vtp.py:365-386): teacher side `get_teacher_forward_outputs` :410-450
+    (no-grad teacher trunk on the global crops, the two views' cls tokens swapped :425-426, masked patch tokens
+    index_select'ed behind them into an `upperbound`-row buffer :432-439, teacher head on the buffer) and student side
+    `get_student_ssl_outputs` :452-484 (list forward [global with masks, local], three head calls; the masked patches
+    go through the head inside a zero-padded `upperbound` buffer :470-477).  sd uses legacy keys (`teacher_trunk.*`,
+    `dino_head.*`, `teacher_dino_head.*`)."""
+    n_m = int(mask_indices.numel())
+    ub = n_m if upperbound is None else upperbound
+    with torch.no_grad():
+        t = trunk_forward([global_crops], [None], sd, pre="teacher_trunk.", depth=depth, heads=heads, mode=mode,
+                          use_bottleneck=False)[0]
+        tcls = t["x_norm_clstoken"]
+        half = tcls.shape[0] // 2
+        tcls = torch.cat([tcls[half:], tcls[:half]])
+        tpatch = t["x_norm_patchtokens"].flatten(0, 1)
+        buf = tpatch.new_zeros(ub + tcls.shape[0], tpatch.shape[-1])
+        buf[:tcls.shape[0]] = tcls
+        buf[tcls.shape[0]:tcls.shape[0] + n_m] = tpatch[mask_indices]
+        t_after = dino_head(buf, sd, "teacher_dino_head.", mode=mode)
+    sg, sl = trunk_forward([global_crops, local_crops], [masks, None], sd, depth=depth, heads=heads, mode=mode,
+                           use_bottleneck=False)
+    sp = sg["x_norm_patchtokens"].flatten(0, 1)
+    sbuf = sp.new_zeros(ub, sp.shape[-1])
+    sbuf[:n_m] = sp[mask_indices]
+    return {"teacher_cls": t_after[:tcls.shape[0]], "teacher_masked": t_after[tcls.shape[0]:tcls.shape[0] + n_m],
+            "student_local": dino_head(sl["x_norm_clstoken"], sd, "dino_head.", mode=mode),
+            "student_global": dino_head(sg["x_norm_clstoken"], sd, "dino_head.", mode=mode),
+            "student_masked": dino_head(sbuf, sd, "dino_head.", mode=mode)[:n_m]}
+
+
+TEACHER_PAIRS = (("trunk.", "teacher_trunk."), ("proj.", "teacher_proj."), ("visual_proj.", "teacher_proj."),
+                 ("dino_head.", "teacher_dino_head."))
+
+
+def update_teacher(sd: Dict[str, Tensor], momentum: float) -> None:
+    """`VTP.update_teacher` (vtp/models/vtp.py:388-401), in place on a legacy-keyed dict: every PARAMETER of the trunk,
+    the clip projection and the DINO head (buffers such as rope_embed.periods are not parameters and are skipped)."""
+    with torch.no_grad():
+        for k in list(sd.keys()):
+            for s_pre, t_pre in TEACHER_PAIRS:
+                if k.startswith(s_pre) and not k.endswith("rope_embed.periods"):
+                    tk = t_pre + k[len(s_pre):]
+                    if tk in sd:
+                        sd[tk] = momentum * sd[tk] + (1 - momentum) * sd[k]
