@@ -5,9 +5,13 @@
   python bench.py --impl reference --gpus N --steps K ...  reference arm: the CPU restatement of the reference's step
                                                            (oracle/train_step.py) on the box's host cores, rank 0 only
 
-Workload (BASELINE.json configs[1]): VTP-Small f16d64, full 3-loss training step (contrastive + DINO/iBOT + recon),
-batch 256 per GPU, 256x256 synthetic RGB, 2 global + 8 local(96) crops, K=65536 prototypes, AdamW + EMA teacher.
-Prints ONE JSON line.
+Workload (BASELINE.json configs[1]): VTP-Small f16d64, full 3-loss training step (contrastive + DINO/iBOT + recon incl.
+LPIPS), batch 256 per GPU, 256x256 synthetic RGB, 2 global + 8 local(96) crops, K=65536 prototypes, AdamW + EMA teacher.
+The step runs as ONE captured CUDA graph by default (--graph off = eager launches).  Prints ONE JSON line.
+
+Both arms time the same workload definition; the reference arm's timed steps are a bounded sample of it (--cpu-batch
+source images per step, stated in its line).  `cpu_config1` in our line is BASELINE configs[0] (the reference's own
+CPU-runnable case: VTP-Small, batch 4, encode->decode, fp32, no_grad) timed on the CPU oracle.
 """
 from __future__ import annotations
 
@@ -37,6 +41,8 @@ def parse():
     ap.add_argument("--cpu-batch", type=int, default=4, help="source images per step of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lpips", action="store_true", help="reconstruction loss = L1 only")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="run the step as one captured CUDA graph (auto = on)")
     return ap.parse_args()
 
 
@@ -88,20 +94,24 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def _cpu_threads() -> int:
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # the GPU boxes expose 128 logical CPUs; intra-op threading of these small CPU GEMMs stops scaling (and, under a
+    # cgroup CPU quota, collapses) long before that — use at most 32 threads and report the number actually used
+    return int(os.environ.get("VTP_CPU_THREADS", min(avail, 32)))
+
+
 def cpu_baseline(args, steps: int, warmup: int):
-    """The reference's step restated on the CPU oracle (towers + restated losses + AdamW + EMA), bounded sample."""
+    """The reference's step restated on the CPU oracle (towers + restated losses incl. LPIPS + autograd + AdamW + EMA),
+    bounded sample: `steps` timed steps of `--cpu-batch` source images each.  Returns (cpu_baseline object, s/step)."""
     import torch
 
-    from oracle.seeded import seeded_state_dict
     from oracle.train_step import OracleTrainer
     from vtp_b200.config import preset
     from vtp_b200.model import VTPModel
     from vtp_b200.synthetic import make_batch
 
-    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    # the GPU boxes expose 128 logical CPUs; intra-op threading of these small CPU GEMMs stops scaling (and, under a
-    # cgroup CPU quota, collapses) long before that — use at most 32 threads and report the number actually used
-    cores = int(os.environ.get("VTP_CPU_THREADS", min(avail, 32)))
+    cores = _cpu_threads()
     torch.set_num_threads(cores)
     cfg = preset(args.model)
     m = VTPModel(cfg)
@@ -115,7 +125,11 @@ def cpu_baseline(args, steps: int, warmup: int):
            "last_layer.weight_g": torch.ones(K, 1), "last_layer.weight_v": torch.randn(K, 256, generator=g) * 0.02}
     dims = dict(vision_depth=cfg.vision_depth, vision_num_heads=cfg.vision_num_heads, text_depth=cfg.text_depth,
                 text_num_heads=cfg.text_num_heads, decoder_depth=cfg.decoder_depth, decoder_num_heads=cfg.decoder_num_heads)
-    tr = OracleTrainer(sd, hsd, dims, n_local=8, mode="bf16")
+    lp = None
+    if not args.no_lpips:
+        from vtp_b200.lpips import random_weights
+        lp = random_weights(0)                      # the same frozen seeded-random VGG16 / lin weights as the GPU arm
+    tr = OracleTrainer(sd, hsd, dims, n_local=8, mode="bf16", lpips=lp)
     Bc = args.cpu_batch
     batch = make_batch(Bc, vocab=cfg.text_vocab_size)
     for _ in range(warmup):
@@ -124,9 +138,41 @@ def cpu_baseline(args, steps: int, warmup: int):
     for _ in range(steps):
         tr.step(batch)
     dt = (time.perf_counter() - t0) / steps
-    return {"value": Bc / dt, "unit": "images/sec", "cores": cores, "kind": "port",
-            "sample": f"{steps} step(s) of the same 3-loss step at batch {Bc} (bf16-autocast emulation, torch CPU, "
-                      f"{cores} threads), {dt:.2f} s/step"}, dt
+    return {"value": Bc / dt, "unit": "images/sec", "cores": cores, "kind": "port", "steps_timed": steps, "warmup": warmup,
+            "batch": Bc,
+            "sample": f"{steps} timed step(s) (+{warmup} warm-up) of the same 3-loss step ({'with' if lp else 'without'} LPIPS) at batch "
+                      f"{Bc} instead of {args.batch} (bf16-autocast emulation, torch CPU, {cores} threads), {dt:.2f} s/step"}, dt
+
+
+def cpu_config1(reps: int = 3):
+    """BASELINE.json configs[0] / SURVEY.md §8(d) "CPU baseline timing": VTP-Small, batch 4, encode -> decode, fp32,
+    no_grad, exactly the call pattern of tools/test_reconstruction_hf.py:360-372 — on the CPU oracle (kind "port": the
+    reference itself cannot travel to the GPU box; the oracle is pinned to it, tests/test_oracle_golden.py)."""
+    import torch
+
+    from oracle import vtp_oracle as vo
+    from vtp_b200.config import preset
+    from vtp_b200.flops import encode_decode_flops
+    from vtp_b200.model import VTPModel
+
+    cores = _cpu_threads()
+    torch.set_num_threads(cores)
+    cfg = preset("small")
+    sd = {k: v.detach().clone() for k, v in VTPModel(cfg).state_dict().items()}
+    x = torch.randn(4, 3, 256, 256, generator=torch.Generator().manual_seed(1234))
+    ts = []
+    with torch.no_grad():
+        for i in range(reps + 1):
+            t0 = time.perf_counter()
+            lat = vo.reconstruction_latents(x, sd, depth=cfg.vision_depth, heads=cfg.vision_num_heads)
+            vo.decode_latents(lat, sd, depth=cfg.decoder_depth, heads=cfg.decoder_num_heads)
+            if i:
+                ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"workload": "VTP-Small f16d64, batch=4 256x256, encode->decode reconstruction only, fp32, no_grad, CPU",
+            "value": 4 / med, "unit": "images/sec", "ms_per_call": med * 1e3, "cores": cores, "kind": "port", "reps": reps,
+            "gflop_per_image": encode_decode_flops(cfg) / 1e9}
 
 
 def workload_config(args, world: int, flops_per_image: float, image_groups=None) -> dict:
@@ -160,16 +206,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        cb, dt = cpu_baseline(args, steps=max(1, min(args.steps, 2)), warmup=min(args.warmup, 1))
+        # bounded: at most 2 timed steps (+1 warm-up) of --cpu-batch images — about 10-30 s of CPU work
+        n_steps, n_warm = max(1, min(args.steps, 2)), min(args.warmup, 1)
+        cb, dt = cpu_baseline(args, steps=n_steps, warmup=n_warm)
         from vtp_b200.config import preset
         from vtp_b200.flops import train_step_flops_per_image
         fl = train_step_flops_per_image(preset(args.model), K=args.prototypes, lpips=not args.no_lpips)
         conf = workload_config(args, args.gpus, fl["total"])
         conf["sample"] = (f"CPU restatement of the reference's step (oracle port, torch CPU, {cb['cores']} threads): each timed "
-                          f"step is a bounded sample of {args.cpu_batch} source images of this workload (same crops, "
-                          f"prototypes, losses, optimiser)")
+                          f"step is a bounded sample of {args.cpu_batch} source images of this workload (same crops, prototypes, "
+                          f"losses incl. LPIPS, optimiser); {n_steps} step(s) timed after {n_warm} warm-up, whatever --steps/--warmup ask")
         out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "images/sec", "n_gpus": args.gpus,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+               "steps": n_steps, "warmup": n_warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+               "ms_per_step": dt * 1e3, "ms_per_step_is_for_batch": args.cpu_batch, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                "config": conf,
                "cpu_baseline": cb,
@@ -217,21 +266,32 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    for i in range(args.warmup):
-        tr.train_step(resident)
+    use_graph = args.graph != "off"
+    step_fn = tr.train_step
+    if use_graph:
+        # warm-up steps run inside capture_step (they are real, eager steps), then one step is captured without executing
+        tr.capture_step(resident, warmup=max(args.warmup, 1))
         torch.cuda.synchronize()
-        log(f"warmup {i} done, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+        log(f"step captured: {tr.graph_launches} kernels per replay, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+        step_fn = tr.replay_step
+        tr.replay_step()           # one replay before timing (graph upload)
+        torch.cuda.synchronize()
+    else:
+        for i in range(args.warmup):
+            tr.train_step(resident)
+            torch.cuda.synchronize()
+            log(f"warmup {i} done, peak mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    # ---- device-resident timing ("value")
+    # ---- device-resident timing ("value"): inputs already in HBM (the graph's static buffers / the resident batch)
     l0 = lib.LAUNCHES
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
     for _ in range(args.steps):
-        loss = tr.train_step(resident)
+        loss = tr.replay_step() if use_graph else tr.train_step(resident)
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
@@ -248,7 +308,7 @@ def main():
         dev_batch, slot = pf.get()
         if i + 1 < args.steps:
             pf.put(host)              # the next step's 1 GB H2D copy runs on the side stream under this step
-        loss = tr.train_step(dev_batch)
+        loss = step_fn(dev_batch)     # graph: device-to-device copy into the static inputs (0.3 ms), then one replay
         pf.release(slot)
         loss_host = loss.cpu()        # D2H read of the step's result, every step (synchronises)
     e3.record()
@@ -275,12 +335,13 @@ def main():
     torch.cuda.synchronize()
     gemm_ms = g0.elapsed_time(g1) / reps
     gemm_tflops = 2.0 * Mg * Ng * Kg / (gemm_ms * 1e-3) / 1e12
-    traffic = None
-    try:  # DRAM bytes of this very launch from the committed ncu --set full capture (profiles/)
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes of this very launch (same M, N, K) from the committed ncu --set full capture under profiles/ — ncu
+        # cannot run inside the timed bench, so the number is stamped with the capture it came from
         with open(os.path.join(ROOT, "profiles", "gemm_fc1_traffic.json")) as f:
             tj = json.load(f)
         if tj.get("M") == Mg and tj.get("N") == Ng and tj.get("K") == Kg:
-            traffic = tj["dram_bytes"]
+            traffic, traffic_src = tj["dram_bytes"], tj.get("source", "profiles/gemm_fc1_traffic.json")
     except Exception:
         pass
 
@@ -311,10 +372,13 @@ def main():
                 "pipeline": "vtp_b200.synthetic.BatchPrefetcher: pinned host batch of step i+1 copied on a side stream "
                             "(2 device buffers) while step i runs; step 0's copy exposed; loss vector read back every step"},
         "gpu_launches": launches,
+        "launch_mode": (f"one CUDA graph replay per step ({tr.graph_launches} kernels of libvtp_b200.so inside)" if use_graph
+                        else "eager: one host launch per kernel"),
         "clocks": clocks,
-        "roofline": {"bound": "tensor", "kernel": f"vtp::gemm_kernel<256,4,NONE,cluster2,TMA-store epilogue> FFN fc1 GEMM M={Mg} N={Ng} K={Kg} (+bias, bf16 out)",
+        "roofline": {"bound": "tensor", "kernel": f"vtp::gemm_kernel<256,4,NONE,cluster2,TMA-store epilogue> FFN fc1 GEMM M={Mg} N={Ng} K={Kg} (+bias, bf16 out), "
+                               f"timed ISOLATED on synthetic operands after the step loop ({reps} launches, CUDA events)",
                      "achieved": gemm_tflops, "peak": peak_burst, "unit": "TFLOP/s", "frac": gemm_tflops / peak_burst,
-                     "peak_source": src + " burst (kernel timed alone)", "traffic": traffic,
+                     "peak_source": src + " burst (kernel timed alone)", "traffic": traffic, "traffic_source": traffic_src,
                      "algorithmic_flops_per_launch": 2.0 * Mg * Ng * Kg,
                      "algorithmic_bytes_per_launch": 2.0 * (Mg * Kg + Ng * Kg + Mg * Ng),
                      "step": {"achieved": step_tflops, "peak": peak_sust, "frac": step_tflops / peak_sust,
@@ -323,8 +387,16 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         log("cpu baseline ...")
-        cb, _ = cpu_baseline(args, steps=2, warmup=1)   # ~15 s of CPU work on the box's 32 threads
+        cb, _ = cpu_baseline(args, steps=2, warmup=1)   # ~20 s of CPU work on the box's 32 threads
         out["cpu_baseline"] = cb
+        out["cpu_config1"] = cpu_config1()              # BASELINE configs[0]: the reference's own CPU-runnable case
+    extra = os.path.join(ROOT, "profiles", "extra_configs_r2.json")
+    if os.path.exists(extra):                           # BASELINE configs[2..4]: committed hardware runs of this round
+        try:
+            with open(extra) as f:
+                out["extra_configs"] = json.load(f)
+        except Exception:
+            pass
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

@@ -158,7 +158,13 @@ int vtp_strip_prefix(const float* g, void* out_bf16, float* dcls, int B, int T, 
  * teacher (vtp.py:388-401: teacher = m*teacher + (1-m)*student) in the same pass */
 int vtp_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, float* teacher, void* teacher_bf16, long n,
                    float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                   float ema_momentum, vtp_stream_t stream);
+                   float ema_momentum, const float* hyper, vtp_stream_t stream);
+/* device-resident step state `hyper` float[8] = {step, 1-b1^step, 1-b2^step, lr, weight decay, EMA momentum, -, -}: advances
+ * the step and looks the scheduled lr / wd / teacher momentum up in device tables (restating the reference's
+ * CosineScheduler, models/utils/text_utils.py:160-207, which is a precomputed table as well; null table = keep the value).
+ * vtp_adamw_step reads it when `hyper` is non-null, so a CUDA graph of the whole training step carries no host scalars. */
+int vtp_hyper_tick(float* hyper, float beta1, float beta2, const float* lr_table, const float* wd_table,
+                   const float* momentum_table, int table_len, vtp_stream_t stream);
 int vtp_cast_f32_to_bf16(const float* x, void* y, long n, vtp_stream_t stream);
 int vtp_axpby(float* y, const float* x, float a, float b, long n, vtp_stream_t stream);
 /* OpenCLIP ClipLoss row-wise softmax-CE on a similarity block sim = I·Tᵀ with logits = exp(*log_scale)·sim
@@ -225,7 +231,10 @@ int vtp_comm_free(void* ptr);
 int vtp_comm_get_handle(void* ptr, unsigned char* handle64);
 int vtp_comm_open_handle(const unsigned char* handle64, void** peer_ptr);
 int vtp_comm_close_handle(void* peer_ptr);
-int vtp_comm_barrier(const void* const* pad_ptrs, int world, int rank, long epoch, int* err_flag, vtp_stream_t stream);
+/* flag barrier; on time-out (~20 s) *err_flag = 1 and, if given, *poison = NaN (the caller's loss slot: the failure
+ * then travels with the step's result instead of needing its own host read) */
+int vtp_comm_barrier(const void* const* pad_ptrs, int world, int rank, long epoch, int* err_flag, float* poison,
+                     vtp_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Data formats either side of the encode / decode path (vtp_b200/csrc/latents_io.cu)

@@ -15,8 +15,10 @@ from . import vtp_oracle as vo
 
 class OracleTrainer:
     def __init__(self, sd: Dict[str, torch.Tensor], head_sd: Dict[str, torch.Tensor], dims: dict, *, n_local: int,
-                 lr=1e-4, betas=(0.9, 0.95), wd=0.05, teacher_momentum=0.994, mode="bf16"):
+                 lr=1e-4, betas=(0.9, 0.95), wd=0.05, teacher_momentum=0.994, mode="bf16", lpips=None, lpips_weight=1.0):
+        """lpips: (vgg_w, vgg_b, lin_w) of the frozen perceptual network (utils/lpips.py) or None = L1 only."""
         self.dims, self.n_local, self.mode, self.mom = dims, n_local, mode, teacher_momentum
+        self.lpips, self.lpips_weight = lpips, lpips_weight
         self.p = {k: (v.clone().float().requires_grad_(True) if v.is_floating_point() and "periods" not in k else v.clone())
                   for k, v in sd.items()}
         self.h = {"h." + k: v.clone().float().requires_grad_(True) for k, v in head_sd.items()}
@@ -65,7 +67,10 @@ class OracleTrainer:
         # REC
         lat = vo.reconstruction_latents(batch["rec_image"], p, depth=dv, heads=hv, mode=m)
         rec = vo.decode_latents(lat, p, depth=d["decoder_depth"], heads=d["decoder_num_heads"], mode=m)
-        losses["rec"] = vo.recon_loss(rec, batch["rec_image"], None)
+        lp = None
+        if self.lpips is not None:
+            lp = vo.lpips(rec, batch["rec_image"], *self.lpips, mode=m)
+        losses["rec"] = vo.recon_loss(rec, batch["rec_image"], lp, self.lpips_weight)
         total = sum(losses.values())
         self.opt.zero_grad(set_to_none=True)
         total.backward()

@@ -70,3 +70,21 @@ def test_rec_chunks_and_full_step_equal_whole_batch():
     torch.cuda.synchronize()
     p0, p1 = ref2.store.p, tr2.store.p
     assert ((p0 - p1).norm() / p0.norm()).item() < 1e-4
+
+
+def test_chunked_step_is_graph_capturable():
+    """ssl_chunk / rec_chunk inside capture_step: the per-group mask lists are split once per batch outside the graph
+    (VTPTrainer.split_masks), so the captured step has no data-dependent shape; replay == eager steps."""
+    te, cfg = _trainer(ssl_chunk=2, rec_chunk=3)
+    tg, _ = _trainer(ssl_chunk=2, rec_chunk=3)
+    b = _batch(4, cfg.text_vocab_size)
+    b2 = _batch(4, cfg.text_vocab_size)
+    b2["mask_indices"], b2["masks_weight"] = b["mask_indices"], b["masks_weight"]      # same number of masked patches
+    b2["global_crops"] = b["global_crops"].flip(0).contiguous()
+    seq = [b, b2, b]
+    le = [te.train_step(x).cpu().clone() for x in seq]
+    tg.capture_step(b, warmup=1)
+    lg = [tg.replay_step(x).cpu().clone() for x in seq[1:]]
+    for a, c in zip(le[1:], lg):
+        assert torch.isfinite(c).all() and torch.allclose(a, c, rtol=2e-3, atol=1e-5), (a, c)
+    assert ((tg.store.p - te.store.p).norm() / te.store.p.norm()).item() < 1e-4

@@ -134,3 +134,36 @@ def test_tokenizer_normalisation_constants():
     import pytest
     with pytest.raises(ValueError):
         t._setup_normalization("other")
+
+
+def test_cosine_schedule_matches_reference_table():
+    """vtp_b200.schedules.CosineSchedule restates the reference's CosineScheduler (models/utils/text_utils.py:160-207):
+    against the live reference where it exists, and against values recorded from it (fixture below) everywhere."""
+    import os
+
+    import numpy as np
+
+    from vtp_b200.schedules import CosineSchedule
+
+    cases = [dict(base_value=1e-3, final_value=1e-6, total_iters=50, warmup_iters=5, start_warmup_value=1e-7, freeze_iters=0),
+             dict(base_value=0.994, final_value=1.0, total_iters=20),
+             dict(base_value=0.04, final_value=0.2, total_iters=12, warmup_iters=3, start_warmup_value=0.0, freeze_iters=2)]
+    # recorded from the reference's CosineScheduler (commit 5ce1eb6): [it 0, 1, 4, 7, total-1, total, total+5] per case
+    recorded = [[1e-07, 0.000250075, 0.001, 0.0009951389003364144, 2.2167568952178134e-06, 1e-06, 1e-06],
+                [0.994, 0.9940369349782145, 0.9945729490168752, 0.9956380285007813, 0.9999630650217854, 1.0, 1.0],
+                [0.0, 0.0, 0.04, 0.07012081585130131, 0.19207750943219354, 0.2, 0.2]]
+    for kw, rec in zip(cases, recorded):
+        s = CosineSchedule(**kw)
+        T = kw["total_iters"]
+        got = [s[i] for i in (0, 1, 4, 7, T - 1, T, T + 5)]
+        assert np.allclose(got, rec, rtol=1e-12, atol=0), (kw, got, rec)
+        assert s.table().dtype == np.float32 and s.table().size == T + 1 and s.table()[-1] == np.float32(kw["final_value"])
+    if os.path.isdir("/root/reference/vtp"):
+        from oracle import ref_harness as rh
+
+        rh.import_reference()
+        from vtp.models.utils.text_utils import CosineScheduler
+
+        for kw in cases:
+            ref, s = CosineScheduler(**kw), CosineSchedule(**kw)
+            assert all(ref[i] == s[i] for i in range(kw["total_iters"] + 3))

@@ -108,14 +108,11 @@ def _sdpa_ref(qkv, B, T, H, causal):
                                                   (100, 37, 6, 1, False), (300, 257, 6, 1, False)])
 @pytest.mark.parametrize("variant", ["rows4", "rows8", "pipe"])
 def test_attention_fwd(B, T, H, prefix, causal, variant, monkeypatch):
-    """rows4: one thread per query row (default); rows8: two threads per row, opt-in VTP_ATTN_FWD8=1 (attn_fwd8_kernel).
-    Both pass all shapes on hardware; rows8 measured x0.94 of rows4 at B=512, T=257 (profiles/hbm_kernels_r1.md), so it
-    stays opt-in.  pipe: persistent ping-pong kernel (attention_pipe.cu, VTP_ATTN_FWD_PIPE=1, shapes with 128 < HW <= 256);
-    it has NOT completed a hardware run yet, so its cases need VTP_TEST_UNVALIDATED=1 (a kernel that spins on mbarriers
-    must not be able to hang an unattended run)."""
+    """rows4: one thread per query row; rows8: two threads per row, opt-in VTP_ATTN_FWD8=1 (attn_fwd8_kernel), measured
+    x0.94 of rows4 at B=512, T=257 (profiles/hbm_kernels_r1.md).  pipe: persistent ping-pong kernel (attention_pipe.cu) for
+    128 < HW <= 256 — first hardware run in round 2: bit-identical to rows4 and x1.11 faster (profiles/r2_first_hardware_pass.md),
+    the default for those shapes since (VTP_ATTN_FWD_PIPE=0 selects rows4)."""
     if variant == "pipe":
-        if os.environ.get("VTP_TEST_UNVALIDATED") != "1":
-            pytest.skip("opt-in kernel, not yet validated on hardware (set VTP_TEST_UNVALIDATED=1)")
         if causal or not (128 < T - prefix <= 256) or (T - prefix) % 8:
             pytest.skip("shape not handled by the persistent kernel (falls back to rows4)")
     monkeypatch.setenv("VTP_ATTN_FWD_PIPE", "1" if variant == "pipe" else "0")

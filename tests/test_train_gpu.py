@@ -233,3 +233,80 @@ def test_rec_objective_with_lpips_gradients():
     errs["proj_out.w"] = _check(tr, "decoder.proj_out.w", p["pixel_decoder.proj_out.weight"].grad.flatten(1))
     errs["bneck"] = _check(tr, "trunk.bneck.w", p["trunk.feature_bottleneck.weight"].grad)
     print("rec+lpips grad rel errors: max", max(errs.values()))
+
+
+def _tiny_batch(B=4, n_loc=2, HW=16):
+    masks = torch.zeros(2 * B, HW, dtype=torch.bool)
+    masks[::2, :5] = True
+    return dict(image=seeded_images(B, 64, 64).cuda(), text=seeded_captions(B, 77, 1000).cuda(),
+                global_crops=seeded_images(2 * B, 64, 64, seed=21).cuda(), local_crops=seeded_images(n_loc * B, 32, 32, seed=22).cuda(),
+                mask_indices=masks.flatten().nonzero().flatten().cuda(),
+                masks_weight=(1.0 / masks.sum(-1).clamp(min=1).float())[:, None].expand_as(masks)[masks].cuda(),
+                rec_image=seeded_images(B, 64, 64).cuda())
+
+
+def test_graph_step_equals_eager_steps():
+    """VTPTrainer.capture_step / replay_step: the CUDA graph of the whole step (3 objectives + LPIPS + optimiser + EMA,
+    device-side step counter and bias corrections) must train exactly like the eager launches — same kernels, same order;
+    only the split-K fp32 atomics of the weight gradients may reorder, hence a tolerance instead of bit equality."""
+    from vtp_b200 import lib
+
+    batch = _tiny_batch()
+    b2 = dict(batch)
+    b2["rec_image"] = seeded_images(4, 64, 64, seed=77).cuda()     # a second batch of the same shapes
+    seq = [batch, batch, b2, batch, b2]                             # the capture's two warm-up steps train on `batch`
+
+    def trainer():
+        _, _, _, t = _setup()
+        t.hyper[3] = 2e-4
+        t.enable_lpips(seed=0, chunk=2)
+        return t
+
+    te = trainer()
+    le = [te.train_step(b).cpu().clone() for b in seq]
+    tg = trainer()
+    tg.capture_step(batch, warmup=2)
+    lg = [tg.replay_step(b).cpu().clone() for b in seq[2:]]
+    assert tg.step_count == te.step_count == 5
+    assert int(tg.hyper[0].item()) == 5 and int(te.hyper[0].item()) == 5
+    for a, b in zip(le[2:], lg):
+        assert torch.isfinite(b).all()
+        assert torch.allclose(a, b, rtol=2e-3, atol=1e-5), (a, b)
+    assert rel(tg.store.p, te.store.p) < 1e-4
+    assert rel(tg.store.tp, te.store.tp) < 1e-5
+    assert float(tg.store.g.abs().max()) == 0.0
+    assert tg.graph_launches > 100
+    with pytest.raises(ValueError):
+        bad = dict(batch)
+        bad["rec_image"] = seeded_images(2, 64, 64).cuda()
+        tg.replay_step(bad)
+
+
+def test_device_schedules_drive_the_optimizer():
+    """set_schedules(): lr / weight decay / teacher momentum follow the device tables by the optimiser's own step counter
+    (eagerly and inside the captured graph), holding the last value past the end."""
+    from vtp_b200.schedules import CosineSchedule
+
+    _, _, _, tr = _setup()
+    lr = CosineSchedule(1e-3, 1e-5, total_iters=6, warmup_iters=2, start_warmup_value=1e-6)
+    mom = CosineSchedule(0.99, 1.0, total_iters=4)
+    tr.set_schedules(lr=lr, teacher_momentum=mom)
+    batch = _tiny_batch()
+    seen = []
+    for _ in range(3):
+        tr.train_step(batch)
+        seen.append(tr.scheduled_values())
+    tr.capture_step(batch, warmup=1)                 # step 4 eagerly
+    seen.append(tr.scheduled_values())
+    for _ in range(4):                               # steps 5..8 by replay: beyond both tables
+        tr.replay_step()
+        seen.append(tr.scheduled_values())
+    for i, sv in enumerate(seen):
+        assert sv["step"] == i + 1
+        assert abs(sv["lr"] - lr[i]) <= 1e-6 * abs(lr[i]) + 1e-12, (i, sv, lr[i])
+        assert abs(sv["teacher_momentum"] - mom[i]) < 1e-6, (i, sv, mom[i])
+        assert abs(sv["weight_decay"] - tr.tc.weight_decay) < 1e-9
+    # momentum 1.0 from step 5 on: the teacher stops moving
+    t0 = tr.store.tp.clone()
+    tr.replay_step()
+    assert torch.equal(t0, tr.store.tp)

@@ -18,6 +18,9 @@ bwd = lambda: lib.attention_bwd(qkv, o, do, lse, dqkv, B, T, H, prefix=prefix)
 if "--once" in sys.argv:
     for _ in range(2):
         fwd(); bwd()
+    os.environ["VTP_ATTN_FWD_PIPE"] = "1"   # persistent ping-pong forward (attention_pipe.cu)
+    fwd(); fwd()
+    os.environ["VTP_ATTN_FWD_PIPE"] = "0"
     torch.cuda.synchronize(); print("done"); sys.exit(0)
 def t(fn, reps=10):
     for _ in range(3): fn()

@@ -78,10 +78,12 @@ class PeerFeatures:
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.epoch = 0
 
-    def barrier(self):
-        """All ranks' preceding stream work (their feature writes / reads) is complete and visible after this."""
+    def barrier(self, poison: Optional[torch.Tensor] = None):
+        """All ranks' preceding stream work (their feature writes / reads) is complete and visible after this.
+        `poison`: fp32 device scalar (the step's loss slot) set to NaN if the bounded wait times out, so the failure is
+        seen by whoever reads the step's result — no extra synchronisation on the hot path."""
         self.epoch += 1
-        lib.comm_barrier(self.bases, self.rank, self.epoch, self.err)
+        lib.comm_barrier(self.bases, self.rank, self.epoch, self.err, poison)
 
     def check(self):
         """Host-side check of the barrier time-out flag (synchronises; call it off the hot path)."""

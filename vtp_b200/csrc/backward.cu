@@ -294,10 +294,16 @@ __global__ void scatter_add_rows_kernel(const TS* __restrict__ src, long ld_src,
 // p -= lr * (m̂ / (sqrt(v̂)+eps) + wd * p) on the fp32 master, refresh the bf16 compute copy in the same pass, and
 // (optionally) the EMA teacher  t = mom*t + (1-mom)*p  (vtp.py:388-401) with its bf16 copy.  grad is scaled by
 // gscale (1/world or loss scaling) and zeroed for the next step.
+// `hyper` (optional, device): [0] step, [1] 1-b1^step, [2] 1-b2^step, [3] lr, [4] weight decay, [5] EMA momentum — written by
+// hyper_tick_kernel so that a captured CUDA graph of the step needs no host-side scalars; it overrides the arguments.
 __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                              __nv_bfloat16* __restrict__ pb, float* __restrict__ tp, __nv_bfloat16* __restrict__ tpb,
                              long n4, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2, float gscale,
-                             float ema_mom) {
+                             float ema_mom, const float* __restrict__ hyper) {
+    if (hyper) {
+        bc1 = hyper[1], bc2 = hyper[2], lr = hyper[3], ema_mom = hyper[5];
+        if (wd != 0.f) wd = hyper[4];     // regions without decay (norms, biases) keep 0
+    }
     // 4 parameters per thread per iteration (all buffers are 128-byte aligned and n % 4 == 0 by construction)
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 gi = reinterpret_cast<float4*>(g)[i];
@@ -331,6 +337,24 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
                 reinterpret_cast<uint2*>(tpb)[i] = w;
             }
         }
+    }
+}
+
+// one thread: step += 1, Adam bias corrections, and the scheduled lr / weight decay / teacher momentum of this step taken
+// from device tables (the reference's CosineScheduler is a precomputed table too: models/utils/text_utils.py:160-207;
+// past the end of a table its last entry = final_value holds)
+__global__ void hyper_tick_kernel(float* __restrict__ hyper, float b1, float b2, const float* __restrict__ lr_tab,
+                                  const float* __restrict__ wd_tab, const float* __restrict__ mom_tab, int n_tab) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float step = hyper[0] + 1.f;     // exact in fp32 up to 2^24 steps
+    hyper[0] = step;
+    hyper[1] = 1.f - powf(b1, step);
+    hyper[2] = 1.f - powf(b2, step);
+    if (n_tab > 0) {
+        const int it = min((int)step - 1, n_tab - 1);   // schedule[it] for the it-th (0-based) optimiser step
+        if (lr_tab) hyper[3] = lr_tab[it];
+        if (wd_tab) hyper[4] = wd_tab[it];
+        if (mom_tab) hyper[5] = mom_tab[it];
     }
 }
 
@@ -466,16 +490,24 @@ extern "C" int vtp_scatter_add_rows(const void* src, int src_dtype, long ld_src,
     return VTP_OK;
 }
 
+extern "C" int vtp_hyper_tick(float* hyper, float beta1, float beta2, const float* lr_tab, const float* wd_tab,
+                              const float* mom_tab, int n_tab, vtp_stream_t st) {
+    VTP_CHECK_ARG(hyper && n_tab >= 0 && (n_tab > 0 || (!lr_tab && !wd_tab && !mom_tab)), "hyper_tick: bad args");
+    hyper_tick_kernel<<<1, 32, 0, (cudaStream_t)st>>>(hyper, beta1, beta2, lr_tab, wd_tab, mom_tab, n_tab);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
 extern "C" int vtp_adamw_step(float* p, float* g, float* m, float* v, void* p_bf16, float* teacher, void* teacher_bf16,
                               long n, float lr, float beta1, float beta2, float eps, float weight_decay, int step,
-                              float grad_scale, float ema_momentum, vtp_stream_t st) {
-    VTP_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "adamw_step: bad args");
+                              float grad_scale, float ema_momentum, const float* hyper, vtp_stream_t st) {
+    VTP_CHECK_ARG(p && g && m && v && n > 0 && (step >= 1 || hyper), "adamw_step: bad args");
     VTP_CHECK_ARG(n % 4 == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0,
                   "adamw_step: n %% 4 == 0 and 16B-aligned buffers required");
-    const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
+    const float bc1 = 1.f - powf(beta1, (float)(step < 1 ? 1 : step)), bc2 = 1.f - powf(beta2, (float)(step < 1 ? 1 : step));
     adamw_kernel<<<grid_cap(n / 4, 256), 256, 0, (cudaStream_t)st>>>(p, g, m, v, (__nv_bfloat16*)p_bf16, teacher,
                                                                      (__nv_bfloat16*)teacher_bf16, n / 4, lr, beta1, beta2, eps,
-                                                                 weight_decay, bc1, bc2, grad_scale, ema_momentum);
+                                                                     weight_decay, bc1, bc2, grad_scale, ema_momentum, hyper);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

@@ -204,8 +204,11 @@ __global__ void __launch_bounds__(256) clip_grad_kernel(const float* __restrict_
 
 // ------------------------------------------------------------------------------------------------ flag barrier
 // pads[p] = signal pad of rank p (uint64 [world]); thread p tells rank p "rank `rank` reached `epoch`" and waits
-// until rank p has told us the same.  Bounded wait: *err = 1 after ~20 s instead of hanging the GPU.
-__global__ void comm_barrier_kernel(PeerTable pads, int world, int rank, unsigned long long epoch, int* __restrict__ err) {
+// until rank p has told us the same.  Bounded wait: after ~20 s *err = 1 instead of hanging the GPU, and *poison (the
+// caller's loss slot, read back with the step's result) becomes NaN so that the time-out reaches the host on the hot
+// path without an extra synchronisation: whatever consumed stale peer features afterwards is flagged with it.
+__global__ void comm_barrier_kernel(PeerTable pads, int world, int rank, unsigned long long epoch, int* __restrict__ err,
+                                    float* __restrict__ poison) {
     const int p = threadIdx.x;
     if (p >= world) return;
     __threadfence_system();
@@ -220,6 +223,7 @@ __global__ void comm_barrier_kernel(PeerTable pads, int world, int rank, unsigne
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
         if (t1 - t0 > 20000000000ull) {
             *err = 1;
+            if (poison) *poison = __int_as_float(0x7fc00000);
             break;
         }
         __nanosleep(200);
@@ -306,12 +310,12 @@ extern "C" int vtp_comm_close_handle(void* peer_ptr) {
     return VTP_OK;
 }
 extern "C" int vtp_comm_barrier(const void* const* pad_ptrs, int world, int rank, long epoch, int* err_flag,
-                                vtp_stream_t st) {
+                                float* poison, vtp_stream_t st) {
     VTP_CHECK_ARG(pad_ptrs && err_flag && world >= 1 && world <= CLIP_MAX_WORLD && rank >= 0 && rank < world && epoch > 0,
                   "comm_barrier: bad args");
     PeerTable tbl;
     VTP_CHECK_ARG(fill_table(tbl, pad_ptrs, nullptr, world) == 0, "comm_barrier: null pad pointer");
-    comm_barrier_kernel<<<1, 32, 0, (cudaStream_t)st>>>(tbl, world, rank, (unsigned long long)epoch, err_flag);
+    comm_barrier_kernel<<<1, 32, 0, (cudaStream_t)st>>>(tbl, world, rank, (unsigned long long)epoch, err_flag, poison);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

@@ -517,17 +517,16 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
 // and only HALF of B (the MMA reads both halves across the pair), so the shared-memory fill per flop drops by a third
 // against the multicast variant — the L2->SM feed is what caps the 128 x BN kernel at ~1.3 PFLOP/s.  The leader CTA's
 // MMA thread issues for both; full barriers (both CTAs' TMA bytes) and accumulator-empty barriers live in the leader.
-// CLM (with CL2, not G2): number of CTAs in the cluster along M that share one B tile.  Each loads its own A tile and
-// 1/CLM of B, multicast to all CLM.  2 is the validated default; 4 / 8 exist because the L2->SM delivery only drops with
-// multicast at cluster sizes above 4 and are opt-in (VTP_GEMM_CLM) until they have run on hardware.
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST, bool G2, int CLM>
+// Wider clusters (4 / 8 CTAs sharing one B tile) were built and measured in round 2 (profiles/r2_gemm_cluster_width.md):
+// slower than the pair on every shape of the step (fc1 197 -> 203 -> 216 us), so only the pair remains.
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST, bool G2>
 // 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168 (MINB = 1).
 // MINB = 2 (short-K shapes): two CTAs per SM with a 2-stage ring double the epilogue warps per SM at ~100 registers.
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmO, const GemmDev p) {
     static_assert(!G2 || CL2, "cta_group::2 needs the 2-CTA cluster");
-    static_assert(CLM == 2 || (CL2 && !G2 && (CLM == 4 || CLM == 8)), "CLM in {2,4,8}; > 2 only for the multicast variant");
+    constexpr int CLM = 2;                                      // CTAs per cluster (along M) sharing one B tile
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CLM) - 1u);  // every CTA of the cluster
     constexpr int B_BYTES = (G2 ? BN / 2 : BN) * BK * 2;
     constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
@@ -630,20 +629,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                             tma_load_2d_mc(sb + crank * (BN / CLM) * 128, &tmB, &full_bar[s], k0, n0 + (int)crank * (BN / CLM),
                                            MC_MASK);
                         } else {
-                            // MN-major B arrives in BN/64 chunks of 64 columns x 64 k-rows.  If the chunks divide evenly they are
-                            // dealt out whole; otherwise (wide clusters) every CTA loads its 64/CLM k-rows of EVERY chunk
-                            // (tensor-map box {64, 64/CLM}; 8 rows = one 1 KB swizzle atom, so the slices stay atom-aligned)
-                            if constexpr (CLM > 2 && (BN / 64) % CLM != 0) {
 #pragma unroll
-                                for (int i = 0; i < BN / 64; ++i)
-                                    tma_load_2d_mc(sb + i * 8192 + crank * (64 / CLM) * 128, &tmB, &full_bar[s], n0 + 64 * i,
-                                                   k0 + (int)crank * (64 / CLM), MC_MASK);
-                            } else {
-#pragma unroll
-                                for (int i = 0; i < BN / 64; ++i)
-                                    if ((i % CLM) == (int)crank)
-                                        tma_load_2d_mc(sb + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, k0, MC_MASK);
-                            }
+                            for (int i = 0; i < BN / 64; ++i)   // MN-major B: whole 64-column chunks, dealt out alternately
+                                if ((i % CLM) == (int)crank)
+                                    tma_load_2d_mc(sb + i * 8192, &tmB, &full_bar[s], n0 + 64 * i, k0, MC_MASK);
                         }
                     } else if (!p.b_mn) {
                         tma_load_2d(sb, &tmB, &full_bar[s], k0, n0);
@@ -776,14 +765,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0, bool G2 = false, int CLM = 2>
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0, bool G2 = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream,
                        const CUtensorMap* tmO = nullptr) {
     constexpr int smem_bytes = STAGES * (A_BYTES + (G2 ? BN / 2 : BN) * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 +
                                (FAST ? NUM_EPI_WARPS * 256 + 256 : 1024 + 256);
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2, CLM>,
+        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
@@ -791,23 +780,14 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cudaLaunchAttribute attr[1];
+    constexpr int CLM = 2;
     if (CL2) {
-        int groups = MINB * num_sms() / CLM;  // co-resident clusters of the persistent grid
+        const int groups = MINB * num_sms() / CLM;  // co-resident clusters of the persistent grid
         cfg.blockDim = dim3(NUM_THREADS);
         cfg.dynamicSmemBytes = smem_bytes;
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = CLM, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr, cfg.numAttrs = 1;
-        if (CLM > 2) {  // clusters of 4 / 8 SMs must fit inside a GPC: ask the driver how many can be resident at once
-            static int max_clusters = 0;
-            if (max_clusters == 0) {
-                cfg.gridDim = dim3(CLM * groups);
-                int n = 0;
-                VTP_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2, CLM>, &cfg));
-                max_clusters = n > 0 ? n : 1;
-            }
-            if (groups > max_clusters) groups = max_clusters;
-        }
         cfg.gridDim = dim3(CLM * (work < groups ? work : groups));
     } else {
         cfg.gridDim = dim3(work < MINB * num_sms() ? work : MINB * num_sms());
@@ -815,7 +795,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2, CLM>, tmA, tmB, tmO ? *tmO : tmA, p));
+    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>, tmA, tmB, tmO ? *tmO : tmA, p));
     return VTP_OK;
 }
 
@@ -897,20 +877,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     const bool short_bn128 = getenv("VTP_GEMM_SHORTK_BN128") != nullptr;
     if (short_bn128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1 && a->conv_C == 0) BN = 128;
 
-    // cluster size along M of the B-tile multicast: 2 (validated) unless VTP_GEMM_CLM = 4 | 8 asks for the wider sharing,
-    // which exists for the lean-epilogue 256-wide forward/dgrad tiles only (8: K-major B only — the MN-major B tile is
-    // loaded in four 64-column chunks) and has not run on hardware yet
-    // (short-K 128-wide accumulate shapes keep the two-CTAs-per-SM kernel)
-    const bool two_plain = plain_acc && BN == 128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1;
-    int clm = 2;
-    if (cl2 && !g2 && (fast || plain_acc) && !a->mask_pos && !two_plain) {   // incl. the implicit-conv form (LPIPS convs)
-        const char* e = getenv("VTP_GEMM_CLM");
-        const int v = e ? atoi(e) : 2;
-        if (v == 4 || v == 8) clm = v;
-        while (clm > 2 && ceil_div(a->M, BM) < clm) clm >>= 1;
-    }
-    // MN-major B (dgrad, wgrad): whole 64-column chunks per CTA when they divide evenly, else 64/clm k-rows of every chunk
-    const bool b_kslice = a->b_mn_major && clm > 2 && (BN / 64) % clm != 0;
+    const int clm = 2;  // CTAs per cluster sharing one B tile (see gemm_kernel)
 
     GemmDev p;
     memset(&p, 0, sizeof(p));
@@ -961,7 +928,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         uint64_t dims[2], strides[1] = {(uint64_t)a->ldb * 2};
         uint32_t box[2];
         if (!p.b_mn) dims[0] = a->K, dims[1] = a->N, box[0] = 64, box[1] = (uint32_t)(cl2 ? BN / clm : BN);
-        else dims[0] = a->N, dims[1] = a->K, box[0] = 64, box[1] = (uint32_t)(b_kslice ? 64 / clm : 64);
+        else dims[0] = a->N, dims[1] = a->K, box[0] = 64, box[1] = 64;
         int rc = make_tmap_bf16(&tmB, a->B, 2, dims, strides, box);
         if (rc) return rc;
     }
@@ -999,16 +966,6 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         if (g2)                                                                                                       \
             return (BN == 256) ? launch_gemm<256, 6, ACT_, false, true, 1, MODE_, true>(tmA, tmB, p, stream, &tmO)    \
                                : launch_gemm<128, 8, ACT_, false, true, 1, MODE_, true>(tmA, tmB, p, stream, &tmO);   \
-        if (clm == 4) {                                                                                               \
-            if (BN == 192) return launch_gemm<192, 4, ACT_, false, true, 1, MODE_, false, 4>(tmA, tmB, p, stream, &tmO); \
-            return (BN == 256) ? launch_gemm<256, 4, ACT_, false, true, 1, MODE_, false, 4>(tmA, tmB, p, stream, &tmO) \
-                               : launch_gemm<128, 6, ACT_, false, true, 1, MODE_, false, 4>(tmA, tmB, p, stream, &tmO); \
-        }                                                                                                             \
-        if (clm == 8) {                                                                                               \
-            if (BN == 192) return launch_gemm<192, 4, ACT_, false, true, 1, MODE_, false, 8>(tmA, tmB, p, stream, &tmO); \
-            return (BN == 256) ? launch_gemm<256, 4, ACT_, false, true, 1, MODE_, false, 8>(tmA, tmB, p, stream, &tmO) \
-                               : launch_gemm<128, 6, ACT_, false, true, 1, MODE_, false, 8>(tmA, tmB, p, stream, &tmO); \
-        }                                                                                                             \
         if (BN == 192) {                                                                                              \
             if (cl2) return launch_gemm<192, 4, ACT_, false, true, 1, MODE_>(tmA, tmB, p, stream, &tmO);              \
             return launch_gemm<192, 4, ACT_, false, false, 1, MODE_>(tmA, tmB, p, stream, &tmO);                      \
@@ -1052,15 +1009,6 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     if (g2 && a->act == VTP_ACT_NONE && !(two && getenv("VTP_GEMM_G2_NOT_SHORT")))  // wgrad (split-K), logits, ...
         return (BN == 256) ? launch_gemm<256, 6, VTP_ACT_NONE, false, true, 1, 0, true>(tmA, tmB, p, stream)
                            : launch_gemm<128, 8, VTP_ACT_NONE, false, true, 1, 0, true>(tmA, tmB, p, stream);
-    if (plain_acc && clm > 2) {  // wgrad / accumulate form with the wide B-tile multicast (opt-in, VTP_GEMM_CLM)
-        if (clm == 4)
-            return BN == 192   ? launch_gemm<192, 4, VTP_ACT_NONE, false, true, 1, 0, false, 4>(tmA, tmB, p, stream)
-                   : BN == 256 ? launch_gemm<256, 4, VTP_ACT_NONE, false, true, 1, 0, false, 4>(tmA, tmB, p, stream)
-                               : launch_gemm<128, 6, VTP_ACT_NONE, false, true, 1, 0, false, 4>(tmA, tmB, p, stream);
-        return BN == 192   ? launch_gemm<192, 4, VTP_ACT_NONE, false, true, 1, 0, false, 8>(tmA, tmB, p, stream)
-               : BN == 256 ? launch_gemm<256, 4, VTP_ACT_NONE, false, true, 1, 0, false, 8>(tmA, tmB, p, stream)
-                           : launch_gemm<128, 6, VTP_ACT_NONE, false, true, 1, 0, false, 8>(tmA, tmB, p, stream);
-    }
     if (BN == 192) {  // only chosen for the fast path (returned above) and the plain split-K accumulate path
         if (cl2) return launch_gemm<192, 4, VTP_ACT_NONE, false, true, 1>(tmA, tmB, p, stream);
         return launch_gemm<192, 4, VTP_ACT_NONE, false, false, 1>(tmA, tmB, p, stream);

@@ -195,8 +195,23 @@ class LatentShardWriter:
         var = (ss - n * mean * mean) / max(n - 1.0, 1.0)
         return {"mean": mean.float().view(1, -1, 1, 1), "std": var.clamp_min(0).sqrt().float().view(1, -1, 1, 1)}
 
-    def close(self, write_stats: bool = True):
+    def close(self, write_stats: Optional[bool] = None, process_group=None):
+        """Flush the last shard and write `latents_stats.pt`.  Multi-rank extraction (one writer per rank into a shared
+        directory, like extract_features_vtp.py): the fp64 partial sums Σx, Σx², n are all-reduced over the process group
+        (when torch.distributed is initialised) so the statistics cover every rank's latents, and ONLY rank 0 writes the
+        file — the default `write_stats=None` means "rank 0 only"."""
         self._drain(block=True)
         self._save()
+        import torch.distributed as dist
+        multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(process_group) > 1
+        if self._sum is None and multi:          # a rank without data still has to join the reduction
+            raise RuntimeError("LatentShardWriter.close(): this rank added no latents; every rank must add at least one batch")
+        if multi:
+            n = torch.tensor([float(self._n)], dtype=torch.float64, device=self.device)
+            for t in (self._sum, self._sumsq, n):
+                dist.all_reduce(t, group=process_group)
+            self._n = int(n.item())
+        if write_stats is None:
+            write_stats = self.rank == 0
         if write_stats and self._sum is not None:
             torch.save(self.stats(), os.path.join(self.dir, "latents_stats.pt"))

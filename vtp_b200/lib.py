@@ -80,7 +80,8 @@ SIGNATURES: dict[str, tuple] = {
                                        C.c_void_p]),
     "vtp_strip_prefix": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vtp_adamw_step": (C.c_int, [C.c_void_p] * 7 + [C.c_long] + [C.c_float] * 5 + [C.c_int, C.c_float, C.c_float,
-                                                                                  C.c_void_p]),
+                                                                                  C.c_void_p, C.c_void_p]),
+    "vtp_hyper_tick": (C.c_int, [C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "vtp_cast_f32_to_bf16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_void_p]),
     "vtp_axpby": (C.c_int, [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_long, C.c_void_p]),
     "vtp_softmax_ce": (C.c_int, [C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_long,
@@ -113,7 +114,7 @@ SIGNATURES: dict[str, tuple] = {
     "vtp_comm_get_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vtp_comm_open_handle": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "vtp_comm_close_handle": (C.c_int, [C.c_void_p]),
-    "vtp_comm_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p]),
+    "vtp_comm_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
 
@@ -246,12 +247,20 @@ def gather_rows(inp, out, idx, D: int, *, ld_in: int | None = None, ld_out: int 
           "vtp_gather_rows")
 
 
+def _check_qkv(qkv, B: int, T: int, H: int):
+    if qkv.shape[-1] != 3 * 64 * H or qkv.numel() != B * T * 3 * 64 * H:
+        raise VtpError(f"attention: qkv of shape {tuple(qkv.shape)} is not [B*T={B * T}, 3*64*H={3 * 64 * H}] "
+                       "(the kernels are specialised for head_dim 64)")
+
+
 def attention_fwd(qkv, out, B: int, T: int, H: int, *, prefix: int, causal: bool = False, lse=None, stream=None):
+    _check_qkv(qkv, B, T, H)
     check(load().vtp_attention_fwd(_ptr(qkv), _ptr(out), _ptr(lse), B, T, H, prefix, int(causal), _st(stream)),
           "vtp_attention_fwd")
 
 
 def attention_fwd_f32(qkv, out, B: int, T: int, H: int, *, causal: bool = False, stream=None):
+    _check_qkv(qkv, B, T, H)
     check(load().vtp_attention_fwd_f32(_ptr(qkv), _ptr(out), B, T, H, int(causal), _st(stream)),
           "vtp_attention_fwd_f32")
 
@@ -270,6 +279,7 @@ def l2norm_fwd(x, y, M: int, D: int, eps: float = 1e-12, norm_out=None, stream=N
 # ------------------------------------------------------------------------------------------------ training step
 def attention_bwd(qkv, o, dout, lse, dqkv, B: int, T: int, H: int, *, prefix: int, causal: bool = False, rope=None,
                   stream=None):
+    _check_qkv(qkv, B, T, H)
     sin, cos = (rope[0], rope[1]) if rope is not None else (None, None)
     check(load().vtp_attention_bwd(_ptr(qkv), _ptr(o), _ptr(dout), _ptr(lse), _ptr(dqkv), _ptr(sin), _ptr(cos), B, T, H,
                                    prefix, int(causal), _st(stream)), "vtp_attention_bwd")
@@ -309,9 +319,14 @@ def strip_prefix(g, out, dcls, B: int, T: int, prefix: int, D: int, stream=None)
 
 
 def adamw_step(p, g, m, v, pb, teacher, teacher_b, n: int, *, lr, beta1, beta2, eps, wd, step, grad_scale=1.0,
-               ema_momentum=0.0, stream=None):
+               ema_momentum=0.0, hyper=None, stream=None):
     check(load().vtp_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(pb), _ptr(teacher), _ptr(teacher_b), n, lr, beta1,
-                                beta2, eps, wd, step, grad_scale, ema_momentum, _st(stream)), "vtp_adamw_step")
+                                beta2, eps, wd, step, grad_scale, ema_momentum, _ptr(hyper), _st(stream)), "vtp_adamw_step")
+
+
+def hyper_tick(hyper, beta1: float, beta2: float, lr_tab=None, wd_tab=None, mom_tab=None, n_tab: int = 0, stream=None):
+    check(load().vtp_hyper_tick(_ptr(hyper), beta1, beta2, _ptr(lr_tab), _ptr(wd_tab), _ptr(mom_tab), n_tab, _st(stream)),
+          "vtp_hyper_tick")
 
 
 def cast_f32_to_bf16(x, y, n: int, stream=None):
@@ -430,8 +445,8 @@ def comm_close_handle(ptr: int) -> None:
     check(load().vtp_comm_close_handle(ptr), "vtp_comm_close_handle", launch=False)
 
 
-def comm_barrier(pad_ptrs, rank: int, epoch: int, err_flag, stream=None):
-    check(load().vtp_comm_barrier(_ptr_array(pad_ptrs), len(pad_ptrs), rank, epoch, _ptr(err_flag), _st(stream)),
+def comm_barrier(pad_ptrs, rank: int, epoch: int, err_flag, poison=None, stream=None):
+    check(load().vtp_comm_barrier(_ptr_array(pad_ptrs), len(pad_ptrs), rank, epoch, _ptr(err_flag), _ptr(poison), _st(stream)),
           "vtp_comm_barrier")
 
 

@@ -41,6 +41,21 @@ def _swiglu_hidden(dim: int, ratio: float, ffn_layer: str) -> int:
     return d + (-d % align)
 
 
+def check_head_dims(c: VTPConfig) -> None:
+    """The attention / RoPE kernels (forward and backward) address the packed [M, 3D] qkv buffer as H heads of 64
+    columns (csrc/attention.cu: D = H * 64): every tower that runs must have embed_dim == 64 * num_heads, otherwise the
+    kernels would read with the wrong stride.  The reference accepts other head sizes; this path does not."""
+    towers = [("vision", c.vision_embed_dim, c.vision_num_heads)]
+    if c.train_reconstruction:
+        towers.append(("decoder", c.decoder_embed_dim, c.decoder_num_heads))
+    if c.train_clip:
+        towers.append(("text", c.text_embed_dim, c.text_num_heads))
+    for name, dim, heads in towers:
+        if heads <= 0 or dim != 64 * heads:
+            raise NotImplementedError(f"{name} tower: embed_dim {dim} / num_heads {heads} gives head_dim != 64; the "
+                                      "B200 attention kernels are specialised for head_dim == 64")
+
+
 class _Holder(nn.Module):
     """Parameter container (no forward): gives the reference's module-path state-dict keys."""
 
@@ -96,8 +111,7 @@ class VTPModel(VTPPreTrainedModel):
                 raise NotImplementedError(f"{what} is not implemented by the B200 path (reference default is None)")
         if c.vision_use_qk_norm or c.decoder_use_qk_norm:
             raise NotImplementedError("qk-norm is not implemented by the B200 path (reference default is False)")
-        if c.vision_embed_dim % 64 or c.vision_embed_dim // c.vision_num_heads != 64:
-            raise NotImplementedError("the attention kernels are specialised for head_dim == 64")
+        check_head_dims(c)
         self._init_vision_components()
         if c.train_clip:
             self._init_text_components()
@@ -344,6 +358,9 @@ class VTPModel(VTPPreTrainedModel):
         ps = self.config.vision_patch_size
         if image.shape[-1] % ps or image.shape[-2] % ps:
             raise ValueError(f"image size {tuple(image.shape[-2:])} is not a multiple of the patch size {ps}")
+        if (image.shape[-1] // ps) * (image.shape[-2] // ps) > 256 and self._mode() == "bf16":
+            raise NotImplementedError(f"image {tuple(image.shape[-2:])}: more than 256 patch tokens per image; the bf16 "
+                                      "attention kernels are single-pass over <= 256 keys (+cls) — see INTEGRATION.md")
         if not image.is_cuda:
             raise lib.VtpError("VTPModel inputs must live on the CUDA device (no CPU path)")
 

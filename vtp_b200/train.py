@@ -224,7 +224,10 @@ class VTPTrainer:
         c = cfg
         if c.vision_norm_layer != "rmsnorm" or c.decoder_norm_layer not in ("layernorm", "layernormbf16"):
             raise NotImplementedError("trainer supports the reference defaults: rmsnorm trunk, layernorm decoder")
-        from .model import _swiglu_hidden
+        from .model import _swiglu_hidden, check_head_dims
+        if not (c.train_clip and c.train_reconstruction):
+            raise NotImplementedError("the trainer runs all three objectives: train_clip and train_reconstruction must be on")
+        check_head_dims(c)
         self.D, self.Dd, self.Dt = c.vision_embed_dim, c.decoder_embed_dim, c.text_embed_dim
         self.hs = _swiglu_hidden(self.D, c.vision_mlp_ratio, c.vision_ffn_layer)
         self.hsd = _swiglu_hidden(self.Dd, 4.0, c.decoder_ffn_layer)
@@ -265,6 +268,11 @@ class VTPTrainer:
         self.head_wn = _e((K, hb), BF, self.device)       # weight-normed last layer (student), rebuilt every step
         self.head_wn_t = _e((K, hb), BF, self.device)     # teacher
         self.head_vnorm = _e((K,), F32, self.device)
+        # device-resident step state (csrc/backward.cu hyper_tick_kernel): {step, 1-b1^t, 1-b2^t, lr, wd, teacher momentum}
+        self.hyper = torch.zeros(8, dtype=F32, device=self.device)
+        self.hyper[3:6] = torch.tensor([self.tc.lr, self.tc.weight_decay, self.tc.teacher_momentum], device=self.device)
+        self._sched = (None, None, None, 0)     # device tables (lr, wd, momentum) + common length
+        self._graph = None                      # CUDA graph of the whole step, see capture_step()
         self.reset_parameters()
 
     def enable_lpips(self, module=None, seed: int = 0, chunk: int = 32):
@@ -548,6 +556,7 @@ class VTPTrainer:
         dev, Dt = self.device, self.Dt
         if self.peer is None or self.peer.B != B:
             if self.peer is not None:
+                self.peer.check()            # a timed-out barrier of the old buffer must not be dropped silently
                 self.peer.close()
             self.peer = PeerFeatures(B, Dt, dev, self.pg, world=self.world, rank=self.rank)
         pf = self.peer
@@ -559,9 +568,9 @@ class VTPTrainer:
         St = _e((Bg, Bgp), F32, dev)
         fi_all = torch.zeros((Bgp, Dt), dtype=BF, device=dev)
         ft_all = torch.zeros((Bgp, Dt), dtype=BF, device=dev)
-        pf.barrier()                       # every rank's features are written
+        pf.barrier(self.loss_acc[0:1])     # every rank's features are written (time-out -> NaN contrastive loss)
         lib.clip_gather_logits(pf.img_ptrs, pf.txt_ptrs, B, Dt, S, St, fi_all, ft_all)
-        pf.barrier()                       # every rank has read them: the buffers may be overwritten by the next step
+        pf.barrier(self.loss_acc[0:1])     # every rank has read them: the buffers may be overwritten by the next step
         ls = self.store.f32("logit_scale")
         dls = self.store.grad("logit_scale")
         coef = weight * 0.5 / B
@@ -737,7 +746,25 @@ class VTPTrainer:
         return dx
 
     # -------------------------------------------------------------- objective 2: SSL (vtp.py:365-386,410-484)
-    def ssl_fwd_bwd(self, global_crops, local_crops, mask_indices, masks_weight, weight: float = 1.0):
+    def split_masks(self, mask_indices: torch.Tensor, masks_weight: torch.Tensor, B: int, HW: int) -> Dict[str, torch.Tensor]:
+        """Per-image-group mask lists for TrainConfig.ssl_chunk (data dependent, so it synchronises): call it once per
+        batch in the input pipeline and pass the result on as batch keys `mask_indices@i` / `masks_weight@i`; the step
+        itself then contains no data-dependent shape and can be captured in a CUDA graph."""
+        chunk = self.tc.ssl_chunk if 0 < self.tc.ssl_chunk < B else B
+        out = {}
+        if chunk == B:
+            return out
+        img = mask_indices // HW
+        for i, b0 in enumerate(range(0, B, chunk)):
+            b1 = min(B, b0 + chunk)
+            bc = b1 - b0
+            s0 = (img >= b0) & (img < b1)
+            s1 = (img >= B + b0) & (img < B + b1)
+            out[f"mask_indices@{i}"] = torch.cat([mask_indices[s0] - b0 * HW, mask_indices[s1] - (B + b0 - bc) * HW])
+            out[f"masks_weight@{i}"] = torch.cat([masks_weight[s0], masks_weight[s1]])
+        return out
+
+    def ssl_fwd_bwd(self, global_crops, local_crops, mask_indices, masks_weight, weight: float = 1.0, mask_groups=None):
         """global_crops [2B,3,H,W] (view-major), local_crops [n_local*B,3,h,w] (crop-major), mask_indices int64 flat
         indices into [2B*HW] of masked global patches (ascending), masks_weight [n_masked] = 1/(#masked in that image).
         With TrainConfig.ssl_chunk = c the B source images are processed c at a time (all their crops together): the
@@ -758,19 +785,17 @@ class VTPTrainer:
             HW = (global_crops.shape[-2] // ps) * (global_crops.shape[-1] // ps)
             n_loc = tc.n_local_crops
             lc = local_crops.view(n_loc, B, *local_crops.shape[1:])
-            img = mask_indices // HW
-            for b0 in range(0, B, chunk):
+            if mask_groups is None or "mask_indices@0" not in mask_groups:
+                mask_groups = self.split_masks(mask_indices, masks_weight, B, HW)   # synchronises (boolean indexing)
+            for i, b0 in enumerate(range(0, B, chunk)):
                 b1 = min(B, b0 + chunk)
                 bc = b1 - b0
                 g = torch.cat([global_crops[b0:b1], global_crops[B + b0:B + b1]])
                 l = lc[:, b0:b1].reshape(n_loc * bc, *local_crops.shape[1:])
-                s0 = (img >= b0) & (img < b1)
-                s1 = (img >= B + b0) & (img < B + b1)
-                idx = torch.cat([mask_indices[s0] - b0 * HW, mask_indices[s1] - (B + b0 - bc) * HW])
-                mw = torch.cat([masks_weight[s0], masks_weight[s1]])
-                self._ssl_chunk(g, l, idx, mw, weight, B, csum)
+                self._ssl_chunk(g, l, mask_groups[f"mask_indices@{i}"], mask_groups[f"masks_weight@{i}"], weight, B, csum)
         # teacher centre EMA over the whole (global) batch (DINOv2 softmax_center_teacher / update_center)
-        cnt = torch.tensor([float(B2), float(max(n_m, 1))], device=dev)
+        cnt = torch.empty(2, dtype=F32, device=dev)          # fill kernels, no host copy: the step is graph-capturable
+        cnt[0:1].fill_(float(B2)), cnt[1:2].fill_(float(max(n_m, 1)))
         if self.world > 1:
             dist.all_reduce(csum, group=self.pg)
             dist.all_reduce(cnt, group=self.pg)
@@ -864,26 +889,118 @@ class VTPTrainer:
             import torch.distributed as dist
             dist.all_reduce(self.store.g, group=self.pg)   # collective C3; averaged by grad_scale in the optimiser
 
+    def set_schedules(self, lr=None, weight_decay=None, teacher_momentum=None):
+        """Per-step schedules for the learning rate, weight decay and EMA teacher momentum: `schedules.CosineSchedule`
+        objects (the reference's CosineScheduler, text_utils.py:160-207) or plain sequences, indexed by the optimiser
+        step (0-based) and held at their last value afterwards.  They live on the device; the optimiser looks them up
+        with its own step counter, also inside a captured graph.  None keeps the constant from TrainConfig."""
+        from .schedules import as_table, pad_tables
+        given = [(i, as_table(s)) for i, s in enumerate((lr, weight_decay, teacher_momentum)) if s is not None]
+        tabs = [None, None, None]
+        n = 0
+        if given:
+            padded = pad_tables([t for _, t in given])
+            n = int(padded[0].size)
+            for (i, _), t in zip(given, padded):
+                tabs[i] = torch.from_numpy(t).to(self.device)
+        self._sched = (tabs[0], tabs[1], tabs[2], n)
+        if self._graph is not None:
+            raise RuntimeError("set_schedules() after capture_step(): capture again (table pointers are part of the graph)")
+
+    def scheduled_values(self) -> Dict[str, float]:
+        """{step, lr, weight_decay, teacher_momentum} the LAST optimiser step used (synchronises)."""
+        h = self.hyper.cpu()
+        return {"step": int(h[0]), "lr": float(h[3]), "weight_decay": float(h[4]), "teacher_momentum": float(h[5])}
+
     def optimizer_step(self):
         st, tc = self.store, self.tc
         self.step_count += 1
+        lr_t, wd_t, mom_t, n_t = self._sched
+        lib.hyper_tick(self.hyper, tc.beta1, tc.beta2, lr_t, wd_t, mom_t, n_t)
         for start, end, decay, teacher in st.regions:
             n = end - start
             lib.adamw_step(st.p[start:end], st.g[start:end], st.m[start:end], st.v[start:end], st.pb[start:end],
                            st.tp[start:end] if teacher else None, st.tpb[start:end] if teacher else None, n,
                            lr=tc.lr, beta1=tc.beta1, beta2=tc.beta2, eps=tc.eps, wd=tc.weight_decay if decay else 0.0,
-                           step=self.step_count, grad_scale=1.0 / self.world, ema_momentum=tc.teacher_momentum)
+                           step=self.step_count, grad_scale=1.0 / self.world, ema_momentum=tc.teacher_momentum,
+                           hyper=self.hyper)
+
+    # -------------------------------------------------------------- CUDA graph of the whole step
+    def capture_step(self, batch: Dict[str, torch.Tensor], warmup: int = 2):
+        """Capture ONE full training step (three objectives, collectives, optimiser + EMA) into a CUDA graph that
+        `replay_step` launches with a single call: ~2 300 kernel launches per VTP-Small step cost ~200 ms of host time,
+        which is exposed whenever the caller synchronises per step (reading the loss).  The step state that changes from
+        step to step (Adam bias corrections, scheduled lr / wd / momentum, teacher centres) lives on the device, so the
+        replay needs no host scalar.  `warmup` REAL steps run on `batch` first (they train; lazy initialisation and the
+        allocator settle), then one step is captured without executing.  Batches given to `replay_step` must have the
+        shapes of `batch` (incl. the number of masked patches)."""
+        if self._graph is not None:
+            raise RuntimeError("a step graph exists already")
+        self._static = {k: v.to(self.device).clone() for k, v in batch.items()}
+        B = batch["global_crops"].shape[0] // 2
+        if 0 < self.tc.ssl_chunk < B and "mask_indices@0" not in self._static:
+            ps = self.cfg.vision_patch_size
+            HW = (batch["global_crops"].shape[-2] // ps) * (batch["global_crops"].shape[-1] // ps)
+            self._static.update(self.split_masks(self._static["mask_indices"], self._static["masks_weight"], B, HW))
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self.train_step(self._static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        l0 = lib.LAUNCHES
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.train_step(self._static)
+        self.step_count -= 1                      # the capture did not execute
+        self.graph_launches = lib.LAUNCHES - l0   # kernels of ours inside one replay
+        self._graph = graph
+        return self
+
+    def replay_step(self, batch: Optional[Dict[str, torch.Tensor]] = None) -> torch.Tensor:
+        """One training step by graph replay.  `batch` (device or pinned-host tensors) is copied into the graph's static
+        input buffers first; None re-uses their current contents.  Returns the loss vector like train_step."""
+        if self._graph is None:
+            raise RuntimeError("capture_step() first")
+        if batch is not None and batch is not self._static:
+            if any("@" in k for k in self._static) and "mask_indices@0" not in batch:
+                gc, ps = self._static["global_crops"], self.cfg.vision_patch_size
+                B, HW = gc.shape[0] // 2, (gc.shape[-2] // ps) * (gc.shape[-1] // ps)
+                batch = dict(batch)
+                batch.update(self.split_masks(batch["mask_indices"].to(self.device), batch["masks_weight"].to(self.device), B, HW))
+            for k, v in self._static.items():
+                if batch[k].shape != v.shape:
+                    raise ValueError(f"replay_step: '{k}' has shape {tuple(batch[k].shape)}, the graph was captured for {tuple(v.shape)}")
+                v.copy_(batch[k], non_blocking=True)
+        self._graph.replay()
+        self.step_count += 1
+        lib.LAUNCHES += self.graph_launches
+        return self.loss_acc
+
+    @property
+    def static_batch(self) -> Dict[str, torch.Tensor]:
+        """The graph's input buffers (fill them directly — e.g. H2D copies on a side stream — and call replay_step())."""
+        return self._static
+
+    def check_exchange(self):
+        """Raise if the peer-memory contrastive exchange reported a barrier time-out (synchronises)."""
+        if self.peer is not None:
+            self.peer.check()
 
     def train_step(self, batch: Dict[str, torch.Tensor]) -> torch.Tensor:
         """One full 3-objective step. Returns the device tensor of accumulated loss terms
-        [clip, dino_local, dino_global, ibot, rec_l1, lpips, -, -] (read it with .cpu() to synchronise)."""
+        [clip, dino_local, dino_global, ibot, rec_l1, lpips, -, -] (read it with .cpu() to synchronise).  A NaN in slot 0
+        with clip_exchange == "p2p" means the peer-memory barrier timed out (a rank never arrived): the step's update
+        is invalid — `check_exchange()` raises in that case."""
         tc = self.tc
         self.loss_acc.zero_()
         if tc.w_clip:
             self.clip_fwd_bwd(batch["image"], batch["text"], tc.w_clip)
         if tc.w_ssl:
             self.ssl_fwd_bwd(batch["global_crops"], batch["local_crops"], batch["mask_indices"], batch["masks_weight"],
-                             tc.w_ssl)
+                             tc.w_ssl, mask_groups=batch)
         if tc.w_rec:
             img = batch["rec_image"]
             nB = img.shape[0]
