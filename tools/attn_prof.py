@@ -18,9 +18,9 @@ bwd = lambda: lib.attention_bwd(qkv, o, do, lse, dqkv, B, T, H, prefix=prefix)
 if "--once" in sys.argv:
     for _ in range(2):
         fwd(); bwd()
-    os.environ["VTP_ATTN_FWD_PIPE"] = "1"   # persistent ping-pong forward (attention_pipe.cu)
+    os.environ["VTP_ATTN_FWD_PIPE"] = "0"   # the one-tile-per-CTA forward for comparison
     fwd(); fwd()
-    os.environ["VTP_ATTN_FWD_PIPE"] = "0"
+    del os.environ["VTP_ATTN_FWD_PIPE"]
     torch.cuda.synchronize(); print("done"); sys.exit(0)
 def t(fn, reps=10):
     for _ in range(3): fn()
@@ -31,16 +31,15 @@ def t(fn, reps=10):
     return e0.elapsed_time(e1) / reps * 1e3
 HW = T - prefix
 fl = 4.0 * T * T * 64 * B * H
-uf, ub = t(fwd), t(bwd)
-os.environ["VTP_ATTN_FWD8"] = "1"     # opt-in variant: two row threads per query row (attn_fwd8_kernel)
-o_ref = o.clone()
-uf8 = t(fwd)
+uf, ub = t(fwd), t(bwd)            # defaults: persistent ping-pong forward for 128 < HW <= 256, FULL paths at HW == 256
+o_def = o.clone()
+os.environ["VTP_ATTN_FWD_PIPE"] = "0"     # one-tile-per-CTA kernel, one thread per row
+u4 = t(fwd)
+d4 = (o.float() - o_def.float()).abs().max().item()
+os.environ["VTP_ATTN_FWD8"] = "1"         # two row threads per query row (attn_fwd8_kernel)
+u8 = t(fwd)
 os.environ["VTP_ATTN_FWD8"] = "0"
-if os.environ.get("VTP_TEST_UNVALIDATED") == "1" and 128 < T - prefix <= 256:
-    os.environ["VTP_ATTN_FWD_PIPE"] = "1"   # persistent ping-pong kernel (attention_pipe.cu)
-    ufp = t(fwd)
-    os.environ["VTP_ATTN_FWD_PIPE"] = "0"
-    print(f"fwd pipe variant: {ufp:.1f} us (x{uf / ufp:.2f} vs rows4), max |diff| vs rows4 = {(o.float() - o_ref.float()).abs().max().item():.3e}")
-print(f"fwd rows8 variant: {uf8:.1f} us (x{uf / uf8:.2f} vs rows4), max |diff| vs rows4 = {(o.float() - o_ref.float()).abs().max().item():.3e}")
+del os.environ["VTP_ATTN_FWD_PIPE"]
+print(f"fwd rows4 (one tile per CTA): {u4:.1f} us, rows8: {u8:.1f} us; default is x{u4 / uf:.2f} of rows4, max |default - rows4| = {d4:.3e}")
 print(f"B={B} T={T} H={H}: fwd {uf:.1f} us ({fl / uf / 1e6:.0f} TFLOP/s, {(M * 4 * D * 2) / uf / 1e3:.0f} GB/s)   "
       f"bwd {ub:.1f} us ({2.5 * fl / ub / 1e6:.0f} TFLOP/s, {(M * 8 * D * 2) / ub / 1e3:.0f} GB/s)")

@@ -779,8 +779,10 @@ extern "C" int vtp_attention_fwd(const void* qkv, void* out, float* lse, int B, 
         configured = true;
     }
     dim3 grid(p.pack ? 1 : ceil_div(HW, 128), H, p.pack ? ceil_div(B, p.pack) : B);
-    const char* vp = getenv("VTP_ATTN_FWD_PIPE");  // opt-in: persistent ping-pong kernel (attention_pipe.cu), 128 < HW <= 256
-    if (vp && vp[0] == '1' && !p.pack && !causal && p.nkt == 2 && HW % 8 == 0) return attn_fwd_pipe_launch(tm, p, (cudaStream_t)st);
+    // persistent ping-pong kernel (attention_pipe.cu) for 128 < HW <= 256: default since its round-2 hardware validation
+    // (x1.11 and bit-identical); VTP_ATTN_FWD_PIPE=0 selects the one-tile-per-CTA kernel below
+    const char* vp = getenv("VTP_ATTN_FWD_PIPE");
+    if (!(vp && vp[0] == '0') && !p.pack && !causal && p.nkt == 2 && HW % 8 == 0) return attn_fwd_pipe_launch(tm, p, (cudaStream_t)st);
     const char* v8 = getenv("VTP_ATTN_FWD8");  // opt-in: two row threads per query row (see attn_fwd8_kernel)
     if (v8 && v8[0] == '1')
         attn_fwd8_kernel<<<grid, ATT8_THREADS, ATT_SMEM, (cudaStream_t)st>>>(tm, p);

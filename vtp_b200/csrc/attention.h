@@ -18,7 +18,7 @@ struct AttnDev {
     float scale;
 };
 
-// persistent ping-pong forward for 128 < HW <= 256 (attention_pipe.cu), opt-in VTP_ATTN_FWD_PIPE=1
+// persistent ping-pong forward for 128 < HW <= 256 (attention_pipe.cu); default for those shapes, VTP_ATTN_FWD_PIPE=0 opts out
 int attn_fwd_pipe_launch(const CUtensorMap& tm, const AttnDev& p, cudaStream_t st);
 
 }  // namespace vtp

@@ -89,6 +89,10 @@ __device__ __forceinline__ void rope_bwd64(float (&g)[64], const __nv_bfloat16* 
     }
 }
 
+// FULL: HW == 256, no packing, no causal mask — every (query, key) pair of every step is valid, so the P / dS loop runs
+// without per-element predicates (ncu, profiles/ncu_attn_r2a.md: ~30 executed instructions per score element in the
+// generic loop, mostly mask predicates, selects and address arithmetic) and with hoisted swizzle offsets.
+template <bool FULL>
 __global__ void __launch_bounds__(AB_THREADS, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const AttnBwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -259,21 +263,62 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                     const bool isk = r >= 64;
                     const uint8_t* tile = smem + (isk ? BQ : BDO) + t * 16384;
                     const float* colv = (isk ? dscol : pcol) + g * 128;
-                    float acc = 0.f;
-#pragma unroll 8
-                    for (int i = 0; i < 128; ++i) {
-                        const __nv_bfloat16 e = *reinterpret_cast<const __nv_bfloat16*>(tile + sw_off(i, d));
-                        acc += colv[i] * __bfloat162float(e);
+                    // element (row i, dim d) of a swizzled 128-byte-row tile: row i = 8 a + k sits at a*1024 + k*128 +
+                    // (((d >> 3) ^ k) << 4) + 2 (d & 7): the eight k-offsets are loop invariant, a*1024 an immediate
+                    uint32_t ok[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) ok[k] = (uint32_t)(k * 128 + ((((d >> 3) ^ k) << 4) | ((d & 7) << 1)));
+                    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+                    for (int a = 0; a < 16; ++a) {
+                        const float4 c0 = *reinterpret_cast<const float4*>(colv + 8 * a);
+                        const float4 c1 = *reinterpret_cast<const float4*>(colv + 8 * a + 4);
+                        const float cv[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t e = *reinterpret_cast<const uint16_t*>(tile + a * 1024 + ok[k]);
+                            if (k & 1) acc1 = fmaf(cv[k], __uint_as_float(e << 16), acc1);
+                            else acc0 = fmaf(cv[k], __uint_as_float(e << 16), acc0);
+                        }
                     }
-                    atomicAdd(isk ? &dk0[d] : &dv0[d], acc);
+                    atomicAdd(isk ? &dk0[d] : &dv0[d], acc0 + acc1);
                 }
             }
             mbar_wait(bar_sdp, n & 1);
             tc_fence_after();
             if (n > 0) mbar_wait(bar_mma2, (n - 1) & 1);  // P/dS smem tiles free again
+            const float lsc = lse_i[t] * lse_l2, dl = delta_i[t];
+            if constexpr (FULL) {
+                const float sl2 = p.scale_log2, sc = p.scale, dls = dl * p.scale;
+                uint8_t* pb_ = smem + BP + g * 16384 + r * 128;   // my row of 64-key chunk g of the P / dS tiles
+                uint8_t* db_ = smem + BDS + g * 16384 + r * 128;
+#pragma unroll
+                for (int cc = 0; cc < 2; ++cc) {
+                    const int c32 = 2 * g + cc;
+                    uint32_t rs[32], rd[32];
+                    tmem_ld_32x32(trow + C_S + c32 * 32, rs);
+                    tmem_ld_32x32(trow + C_DP + c32 * 32, rd);
+                    tmem_ld_wait();
+                    uint32_t pk[16], dk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float pa = ex2f(fmaf(__uint_as_float(rs[i]), sl2, -lsc));
+                        const float pb = ex2f(fmaf(__uint_as_float(rs[i + 1]), sl2, -lsc));
+                        const float da = pa * fmaf(__uint_as_float(rd[i]), sc, -dls);       // s P (dP - delta)
+                        const float db = pb * fmaf(__uint_as_float(rd[i + 1]), sc, -dls);
+                        pk[i >> 1] = pack_bf16x2(pa, pb);
+                        dk[i >> 1] = pack_bf16x2(da, db);
+                    }
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4) {
+                        const uint32_t off = (uint32_t)(((cc * 4 + v4) ^ (r & 7)) << 4);
+                        *reinterpret_cast<uint4*>(pb_ + off) = make_uint4(pk[v4 * 4], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
+                        *reinterpret_cast<uint4*>(db_ + off) = make_uint4(dk[v4 * 4], dk[v4 * 4 + 1], dk[v4 * 4 + 2], dk[v4 * 4 + 3]);
+                    }
+                }
+            } else {
             const int kmin = p.pack ? pseq * T : 0;
             const int kmax = p.pack ? kmin + T : (p.causal ? min(HW, qi + 1) : HW);
-            const float lsc = lse_i[t] * lse_l2, dl = delta_i[t];
 #pragma unroll 1
             for (int cc = 0; cc < 2; ++cc) {
                 const int c32 = 2 * g + cc;
@@ -305,6 +350,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                     *reinterpret_cast<uint4*>(pb_ + off) = make_uint4(pk[v4 * 4], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
                     *reinterpret_cast<uint4*>(db_ + off) = make_uint4(dk[v4 * 4], dk[v4 * 4 + 1], dk[v4 * 4 + 2], dk[v4 * 4 + 3]);
                 }
+            }
             }
             tc_fence_before();
             fence_proxy_async_smem();
@@ -496,10 +542,15 @@ extern "C" int vtp_attention_bwd(const void* qkv, const void* o, const void* dou
     }
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+        VTP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
+        VTP_CUDA(cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, AB_SMEM));
         configured = true;
     }
-    attn_bwd_kernel<<<dim3(H, p.pack ? ceil_div(B, p.pack) : B), AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, p);
+    const dim3 grid(H, p.pack ? ceil_div(B, p.pack) : B);
+    if (p.HW == 256 && !p.pack && !p.causal && getenv("VTP_ATTN_BWD_GENERIC") == nullptr)
+        attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, p);
+    else
+        attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, p);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

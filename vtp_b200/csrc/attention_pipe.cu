@@ -1,6 +1,12 @@
 // vtp_b200 — persistent, software-pipelined self-attention forward for 128 < HW <= 256 (the ViT trunk, T = 1 + 256, and the
-// pixel decoder, T = 256): opt-in with VTP_ATTN_FWD_PIPE=1, NOT yet run on hardware (written after the round's GPU budget
-// was spent; its parity cases are gated behind VTP_TEST_UNVALIDATED=1).
+// pixel decoder, T = 256).  First hardware run in round 2: bit-identical to attn_fwd_kernel and 1.11x faster; the default for
+// these shapes since (VTP_ATTN_FWD_PIPE=0 selects the one-tile-per-CTA kernel).
+//
+// FULL (HW == 256, every key valid): the row threads run a predicate-free softmax — ncu of the generic loop showed ~25
+// executed instructions per score element, three quarters of them mask predicates, address arithmetic and selects
+// (profiles/ncu_attn_r2a.md).  The FULL path: max pass with four independent FMNMX chains over two TMEM loads in flight;
+// exp pass fully unrolled with the TMEM load of the next 32 columns in flight, hoisted swizzle offsets, two row-sum chains;
+// the second 128-key half is exponentiated into registers BEFORE waiting for the first half's P.V (which frees the P buffer).
 //
 // Why: the one-tile-per-CTA kernel (attention.cu) spends ~12.9 us per 128x256 tile for ~3 us of issue slots
 // (profiles/ncu_attn_r1b_before_cls_fix.md: 16 % warps active, 5 % tensor pipe) and a variant with twice the row threads
@@ -42,6 +48,7 @@ __device__ __forceinline__ uint32_t swz(int row, int col /* bf16 element 0..63 *
     return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
 }
 
+template <bool FULL>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm, const AttnDev p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if (smem_u32(smem) & 1023) __trap();
@@ -289,6 +296,95 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __
             float m = -INFINITY;
 #pragma unroll
             for (int j = 0; j < ATT_MAX_PREFIX; ++j) m = fmaxf(m, s_pre[j]);
+            float l = 0.f;
+            float p_pre[ATT_MAX_PREFIX];
+            if constexpr (FULL) {
+                // ---- pass 1: row max, 64 columns per round (two TMEM loads in flight), four independent chains
+                float m0 = m, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+#pragma unroll
+                for (int c = 0; c < 256; c += 64) {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32(trow + c, ra);
+                    tmem_ld_32x32(trow + c + 32, rb);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        m0 = fmaxf(m0, fmaxf(__uint_as_float(ra[i]), __uint_as_float(rb[i])));
+                        m1 = fmaxf(m1, fmaxf(__uint_as_float(ra[i + 1]), __uint_as_float(rb[i + 1])));
+                        m2 = fmaxf(m2, fmaxf(__uint_as_float(ra[i + 2]), __uint_as_float(rb[i + 2])));
+                        m3 = fmaxf(m3, fmaxf(__uint_as_float(ra[i + 3]), __uint_as_float(rb[i + 3])));
+                    }
+                }
+                m = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+                const float sl2 = p.scale_log2, msc = m * sl2;   // a full row always has a finite maximum
+#pragma unroll
+                for (int j = 0; j < ATT_MAX_PREFIX; ++j) {
+                    p_pre[j] = (s_pre[j] == -INFINITY) ? 0.f : ex2a(s_pre[j] * sl2 - msc);
+                    l += p_pre[j];
+                    p_pre[j] = bf16_round(p_pre[j]);
+                }
+                // ---- pass 2: p = exp2(s * scale*log2e - m * scale*log2e) as bf16 into the swizzled P tile.
+                // this row's eight 16-byte chunk slots of a 128-byte swizzled line (chunk ^ (row & 7)), computed once
+                uint32_t poff[8];
+#pragma unroll
+                for (int ch = 0; ch < 8; ++ch) poff[ch] = (uint32_t)r * 128u + (uint32_t)((ch ^ (r & 7)) << 4);
+                float l0 = 0.f, l1 = 0.f;
+                uint32_t cur[32], nxt[32];
+                tmem_ld_32x32(trow, cur);
+                tmem_ld_wait();
+                // half 0: straight into the P buffer (free: the previous job's P.V of this tile completed before s_full)
+#pragma unroll
+                for (int c32 = 0; c32 < 4; ++c32) {
+                    tmem_ld_32x32(trow + 32 * (c32 + 1), nxt);           // next 32 columns in flight (c32 = 3: first of half 1)
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float e0 = ex2a(fmaf(__uint_as_float(cur[i]), sl2, -msc));
+                        const float e1 = ex2a(fmaf(__uint_as_float(cur[i + 1]), sl2, -msc));
+                        l0 += e0, l1 += e1;
+                        pk[i >> 1] = pack_bf16x2(e0, e1);
+                    }
+                    uint8_t* pb = pbuf + (c32 >> 1) * 16384;
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        *reinterpret_cast<uint4*>(pb + poff[(c32 & 1) * 4 + v4]) = make_uint4(pk[v4 * 4], pk[v4 * 4 + 1], pk[v4 * 4 + 2], pk[v4 * 4 + 3]);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) cur[i] = nxt[i];
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&p_full[w * 2 + 0]);
+                // half 1: exponentiate into registers while the tensor core consumes half 0, store once the buffer is free
+                uint32_t pk1[64];
+#pragma unroll
+                for (int c32 = 0; c32 < 4; ++c32) {   // (no load-ahead here: 64 packed registers are live already)
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const float e0 = ex2a(fmaf(__uint_as_float(cur[i]), sl2, -msc));
+                        const float e1 = ex2a(fmaf(__uint_as_float(cur[i + 1]), sl2, -msc));
+                        l0 += e0, l1 += e1;
+                        pk1[c32 * 16 + (i >> 1)] = pack_bf16x2(e0, e1);
+                    }
+                    if (c32 < 3) {
+                        tmem_ld_32x32(trow + 128 + 32 * (c32 + 1), cur);
+                        tmem_ld_wait();
+                    }
+                }
+                l += l0 + l1;
+                mbar_wait(&pv_done[w * 2 + 0], ph);  // the P buffer is free again
+#pragma unroll
+                for (int c32 = 0; c32 < 4; ++c32) {
+                    uint8_t* pb = pbuf + (c32 >> 1) * 16384;
+#pragma unroll
+                    for (int v4 = 0; v4 < 4; ++v4)
+                        *reinterpret_cast<uint4*>(pb + poff[(c32 & 1) * 4 + v4]) =
+                            make_uint4(pk1[c32 * 16 + v4 * 4], pk1[c32 * 16 + v4 * 4 + 1], pk1[c32 * 16 + v4 * 4 + 2], pk1[c32 * 16 + v4 * 4 + 3]);
+                }
+                tc_fence_before();
+                fence_proxy_async_smem();
+                mbar_arrive(&p_full[w * 2 + 1]);
+            } else {
             const int kmax = HW;
             for (int c = 0; c < 256; c += 32) {
                 if (c >= kmax) continue;  // uniform: tcgen05.ld is warp-collective
@@ -300,8 +396,6 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __
                     if (c + i < kmax) m = fmaxf(m, __uint_as_float(rr[i]));
             }
             const float msc = (m == -INFINITY) ? 0.f : m * p.scale_log2;
-            float l = 0.f;
-            float p_pre[ATT_MAX_PREFIX];
 #pragma unroll
             for (int j = 0; j < ATT_MAX_PREFIX; ++j) {
                 p_pre[j] = (s_pre[j] == -INFINITY) ? 0.f : ex2a(s_pre[j] * p.scale_log2 - msc);
@@ -339,6 +433,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __
                 tc_fence_before();
                 fence_proxy_async_smem();
                 mbar_arrive(&p_full[w * 2 + half]);
+            }
             }
             // epilogue
             mbar_wait(&pv_done[w * 2 + 1], ph);
@@ -395,12 +490,16 @@ int attn_fwd_pipe_launch(const CUtensorMap& tm, const AttnDev& p, cudaStream_t s
                   "attention_fwd(pipe): needs 128 < HW <= 256, HW %% 8 == 0, no causal mask");
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM));
+        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM));
+        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM));
         configured = true;
     }
     const int njobs = p.B * p.H;
     const int grid = njobs < num_sms() ? njobs : num_sms();
-    attn_fwd_pipe_kernel<<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(tm, p);
+    if (p.HW == 256 && getenv("VTP_ATTN_PIPE_GENERIC") == nullptr)
+        attn_fwd_pipe_kernel<true><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(tm, p);
+    else
+        attn_fwd_pipe_kernel<false><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(tm, p);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }
