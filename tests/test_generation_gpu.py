@@ -81,7 +81,9 @@ def test_tokenizer_roundtrip_and_shards(tmp_path):
         zi, zf = tok.encode_images_device(xi), tok.encode_images_device(torch.flip(xi, dims=[3]))
         zs.append(zi.cpu())
         w.add(zi, zf, torch.arange(B) + 10 * i)
-    w.close()
+    w.close()                         # default: only rank 0 writes the statistics (multi-rank extraction shares the directory)
+    assert not os.path.exists(os.path.join(tmp_path, "latents_stats.pt"))
+    torch.save(w.stats(), os.path.join(tmp_path, "latents_stats.pt"))   # what close(write_stats=True) / rank 0 writes
     files = sorted(f for f in os.listdir(tmp_path) if f.endswith(".safetensors"))
     assert files == ["latents_rank01_shard000.safetensors", "latents_rank01_shard001.safetensors"]
     with safe_open(os.path.join(tmp_path, files[0]), "pt") as f:

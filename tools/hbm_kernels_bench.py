@@ -19,6 +19,7 @@ BF, F32 = torch.bfloat16, torch.float32
 ap = argparse.ArgumentParser()
 ap.add_argument("--out", default="gpurun_out/hbm_kernels.json")
 ap.add_argument("--reps", type=int, default=10)
+ap.add_argument("--once", action="store_true", help="launch every kernel once, no timing (for ncu --set full)")
 a = ap.parse_args()
 dev = "cuda"
 peak = 6562.6
@@ -41,6 +42,10 @@ def timeit(name, fn, nbytes, note=""):
 
 
 def _timeit(name, fn, nbytes, note=""):
+    if a.once:
+        fn()
+        torch.cuda.synchronize()
+        return
     for _ in range(3):
         fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -99,6 +104,20 @@ timeit("adamw + bf16 copy + EMA teacher", lambda: lib.adamw_step(p, gg, m1, v1, 
                                                                   eps=1e-8, wd=0.05, step=1, ema_momentum=0.994),
        n * (4 * 4 * 2 - 4 + 2 + 4 * 2 + 2), "p,m,v r/w; g read+zeroed; bf16 copies; teacher r/w")
 del p, gg, m1, v1, pb, tp, tpb
+# DINO / iBOT loss kernels at the bench shape: K = 65 536 prototypes, rows = cls + masked-patch tokens of 256 source images
+K, Rt = 65536, 4096
+tl = (torch.randn(Rt, K, device=dev) * 2).to(BF)
+center = torch.zeros(K, device=dev)
+timeit("dino_teacher_probs [4096, 65536]", lambda: lib.dino_teacher_probs(tl, center, Rt, K, 0.07), Rt * K * 4,
+       "centred + sharpened teacher softmax, in place")
+sl = (torch.randn(Rt, K, device=dev) * 2).to(BF)
+t0 = torch.arange(Rt, device=dev, dtype=torch.int32)
+t1 = torch.full((Rt,), -1, device=dev, dtype=torch.int32)
+wrow = torch.full((Rt,), 1.0 / Rt, device=dev)
+lacc = torch.zeros(1, device=dev)
+timeit("dino_student_ce [4096, 65536]", lambda: lib.dino_student_ce(sl, tl, t0, t1, wrow, Rt, K, 0.1, lacc), Rt * K * 6,
+       "student log-softmax CE + gradient in place, one teacher row each")
+del tl, sl
 rec = torch.randn(256, 3, 256, 256, device=dev)
 u8 = torch.empty(256, 256, 256, 3, dtype=torch.uint8, device=dev)
 sub = torch.tensor([-2.1179, -2.0357, -1.8044], device=dev)
