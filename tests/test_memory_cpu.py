@@ -54,3 +54,29 @@ def test_latent_statistics_formula():
     assert st["mean"].shape == (1, 4, 1, 1) and st["std"].dtype == torch.float32
     assert torch.allclose(st["mean"].double(), z.mean(dim=(0, 2, 3), keepdim=True), atol=1e-6)
     assert torch.allclose(st["std"].double(), z.std(dim=(0, 2, 3), keepdim=True), atol=1e-6)
+
+
+def test_gradient_buckets_partition_the_flat_buffer():
+    """train.grad_buckets: the per-tower all-reduce ranges cover [0, n) exactly once, and every tensor lies inside the
+    bucket of its tower (text + clip projection + logit scale | DINO head | pixel decoder | trunk)."""
+    from vtp_b200.train import ParamStore, _vit_specs, grad_buckets
+
+    st = ParamStore("cpu")
+    st.add("trunk.patch.w", (128, 768), True, True); st.add("trunk.cls", (128,), False, True)
+    _vit_specs(st, "trunk.", 128, 2, 344, False, True, 688)
+    st.add("visual_proj.w", (128, 128), True, True)
+    st.add("head.mlp0.w", (256, 128), True, True); st.add("head.last_g", (512,), False, True)
+    st.add("decoder.proj_in.w", (128, 64), True)
+    _vit_specs(st, "decoder.", 128, 2, 344, True, False, 688)
+    st.add("text.tok_emb", (1000, 128), True); st.add("text.pos", (77, 128), False)
+    _vit_specs(st, "text.", 128, 2, 512, True, False, 512)
+    st.add("logit_scale", (1,), False)
+    st.finalize()
+    b = grad_buckets(st.offset, st.n)
+    ranges = sorted(r for rs in b.values() for r in rs)
+    assert ranges[0][0] == 0 and ranges[-1][1] == st.n
+    assert all(a[1] == c[0] for a, c in zip(ranges, ranges[1:]))          # no gap, no overlap
+    inside = lambda name, which: any(lo <= st.offset[name] < hi for lo, hi in b[which])
+    assert inside("text.blocks.1.fc1.w", "text") and inside("logit_scale", "text") and inside("visual_proj.w", "text")
+    assert inside("head.last_g", "head") and inside("decoder.blocks.0.qkv.b", "decoder") and inside("trunk.cls", "trunk")
+    assert sum(len(v) for v in b.values()) <= 16                          # a handful of NCCL calls per step

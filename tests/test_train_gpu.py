@@ -21,19 +21,56 @@ pytestmark = pytest.mark.gpu
 TOL_G, TOL_L = 6e-2, 2e-2
 K, HH, HB = 512, 256, 64
 
+# Geometries the gradient-parity cases run at.  "tiny" is the fast default; "small2" / "large2" are the BENCHED shapes at
+# depth 2: VTP-Small (D = 384, 6 heads, T = 257 in-step attention backward, K = 65 536 smem-resident loss rows, 96-pixel local
+# crops = packed T = 37 tiles) and VTP-Large (D = 1024, 16 heads, SwiGLU hidden 2736 = ragged N / K tiles, text tower 768 / 12).
+GEOS = {
+    "tiny": dict(golden="tiny", img=64, local=32, K=512, HH=256, HB=64, heads=2, theads=2, dheads=2),
+    "small2": dict(cfg=dict(vision_embed_dim=384, vision_depth=2, vision_num_heads=6, text_embed_dim=384, text_num_heads=6,
+                            text_depth=2, decoder_embed_dim=384, decoder_num_heads=6, decoder_depth=2, text_vocab_size=2048),
+                   img=256, local=96, K=65536, HH=2048, HB=256, heads=6, theads=6, dheads=6),
+    "large2": dict(golden="large2", img=256, local=96, K=65536, HH=2048, HB=256, heads=16, theads=12, dheads=16),
+}
 
-def _setup():
-    meta, _ = load_golden("tiny")
-    cfg = VTPConfig(**meta["config"])
-    sd = seeded_state_dict(meta["spec"], seed=0)
-    head_spec = {"mlp.0.weight": [HH, 128], "mlp.0.bias": [HH], "mlp.2.weight": [HH, HH], "mlp.2.bias": [HH],
-                 "mlp.4.weight": [HB, HH], "mlp.4.bias": [HB], "last_layer.weight_g": [K, 1], "last_layer.weight_v": [K, HB]}
+
+class _Ctx:
+    pass
+
+
+def _setup(geo="tiny"):
+    g = GEOS[geo]
+    c = _Ctx()
+    c.geo, c.g = geo, g
+    seed_opts = {}
+    if "golden" in g:
+        meta, _ = load_golden(g["golden"])
+        cfg = VTPConfig(**meta["config"])
+        spec, seed_opts = meta["spec"], meta.get("seed_opts", {})
+    else:
+        from vtp_b200.model import VTPModel
+        cfg = VTPConfig(**g["cfg"])
+        spec = {k: list(v.shape) for k, v in VTPModel(cfg).state_dict().items()}
+    sd = seeded_state_dict(spec, seed=0, **seed_opts)
+    D = cfg.vision_embed_dim
+    Kp, hh, hb = g["K"], g["HH"], g["HB"]
+    head_spec = {"mlp.0.weight": [hh, D], "mlp.0.bias": [hh], "mlp.2.weight": [hh, hh], "mlp.2.bias": [hh],
+                 "mlp.4.weight": [hb, hh], "mlp.4.bias": [hb], "last_layer.weight_g": [Kp, 1], "last_layer.weight_v": [Kp, hb]}
     hsd = seeded_state_dict(head_spec, seed=3)
-    hsd["last_layer.weight_v"] = torch.randn(K, HB, generator=torch.Generator().manual_seed(9)) * 0.5
-    tc = TrainConfig(head_out_dim=K, head_hidden=HH, head_bottleneck=HB, n_local_crops=2)
+    hsd["last_layer.weight_v"] = torch.randn(Kp, hb, generator=torch.Generator().manual_seed(9)) * 0.5
+    tc = TrainConfig(head_out_dim=Kp, head_hidden=hh, head_bottleneck=hb, n_local_crops=2)
     tr = VTPTrainer(cfg, tc)
     tr.import_state_dict(sd, hsd)
-    return cfg, sd, hsd, tr
+    c.cfg, c.sd, c.hsd, c.tr = cfg, sd, hsd, tr
+    c.img, c.local, c.K = g["img"], g["local"], Kp
+    c.HW = (g["img"] // 16) ** 2
+    c.heads, c.theads, c.dheads = g["heads"], g["theads"], g["dheads"]
+    c.vocab = cfg.text_vocab_size
+    return c
+
+
+def _setup_tiny():
+    c = _setup("tiny")
+    return c.cfg, c.sd, c.hsd, c.tr
 
 
 def _leafs(sd):
@@ -65,12 +102,17 @@ def _vit_checks(tr, p, pre_ref, pre, blocks, ln):
     return errs
 
 
-def test_rec_objective_gradients():
-    cfg, sd, hsd, tr = _setup()
-    x = seeded_images(3, 64, 64)
-    p = _leafs(sd)
-    lat = vo.reconstruction_latents(x, p, depth=2, heads=2, mode="bf16")
-    rec = vo.decode_latents(lat, p, depth=2, heads=2, mode="bf16")
+GEO_PARAMS = ["tiny", "small2", "large2"]
+
+
+@pytest.mark.parametrize("geo", GEO_PARAMS)
+def test_rec_objective_gradients(geo):
+    c = _setup(geo)
+    tr = c.tr
+    x = seeded_images(3 if geo == "tiny" else 2, c.img, c.img)
+    p = _leafs(c.sd)
+    lat = vo.reconstruction_latents(x, p, depth=2, heads=c.heads, mode="bf16")
+    rec = vo.decode_latents(lat, p, depth=2, heads=c.dheads, mode="bf16")
     loss = vo.recon_loss(rec, x, None)
     loss.backward()
     out = tr.rec_fwd_bwd(x.cuda(), 1.0, return_image=True)
@@ -90,17 +132,19 @@ def test_rec_objective_gradients():
     errs["proj_out.b"] = _check(tr, "decoder.proj_out.b", p["pixel_decoder.proj_out.bias"].grad)
     errs["dec.norm_w"] = _check(tr, "decoder.norm_w", p["pixel_decoder.norm.weight"].grad)
     errs["dec.norm_b"] = _check(tr, "decoder.norm_b", p["pixel_decoder.norm.bias"].grad)
-    print("rec grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
+    print(f"[{geo}] rec grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
 
 
-def test_clip_objective_gradients():
-    cfg, sd, hsd, tr = _setup()
-    B = 6
-    x = seeded_images(B, 64, 64)
-    ids = seeded_captions(B, 77, 1000)
-    p = _leafs(sd)
-    fi = vo.clip_image_feature(x, p, depth=2, heads=2, mode="bf16")
-    ft = vo.text_feature(ids, p, layers=2, heads=2, mode="bf16")
+@pytest.mark.parametrize("geo", GEO_PARAMS)
+def test_clip_objective_gradients(geo):
+    c = _setup(geo)
+    tr = c.tr
+    B = 6 if geo == "tiny" else 4
+    x = seeded_images(B, c.img, c.img)
+    ids = seeded_captions(B, 77, c.vocab)
+    p = _leafs(c.sd)
+    fi = vo.clip_image_feature(x, p, depth=2, heads=c.heads, mode="bf16")
+    ft = vo.text_feature(ids, p, layers=2, heads=c.theads, mode="bf16")
     loss = vo.clip_loss(vo._r(fi, "bf16"), vo._r(ft, "bf16"), p["logit_scale"].exp())
     loss.backward()
     tr.clip_fwd_bwd(x.cuda(), ids.cuda(), 1.0)
@@ -123,20 +167,22 @@ def test_clip_objective_gradients():
         errs[q + "fc1.w"] = _check(tr, q + "fc1.w", p[r + "mlp.c_fc.weight"].grad)
         errs[q + "fc2.w"] = _check(tr, q + "fc2.w", p[r + "mlp.c_proj.weight"].grad)
         errs[q + "n1_b"] = _check(tr, q + "n1_b", p[r + "ln_1.bias"].grad)
-    print("clip grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
+    print(f"[{geo}] clip grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
 
 
-def test_ssl_objective_gradients():
-    cfg, sd, hsd, tr = _setup()
-    B, n_loc = 3, 2
-    gc = seeded_images(2 * B, 64, 64, seed=11)
-    lc = seeded_images(n_loc * B, 32, 32, seed=12)
-    HW = 16
-    # mask 5 patches on global crops 0, 2, 5
+@pytest.mark.parametrize("geo", GEO_PARAMS)
+def test_ssl_objective_gradients(geo):
+    c = _setup(geo)
+    tr, sd, hsd, K = c.tr, c.sd, c.hsd, c.K
+    B, n_loc = (3, 2) if geo == "tiny" else (2, 2)
+    gc = seeded_images(2 * B, c.img, c.img, seed=11)
+    lc = seeded_images(n_loc * B, c.local, c.local, seed=12)
+    HW = c.HW
+    # mask 30 % of the patches on some of the global crops (5 of 16 at the tiny geometry)
     gsel = torch.Generator().manual_seed(5)
     masks = torch.zeros(2 * B, HW, dtype=torch.bool)
-    for img in (0, 2, 5):
-        masks[img, torch.randperm(HW, generator=gsel)[:5]] = True
+    for img in ((0, 2, 5) if geo == "tiny" else (0, 3)):
+        masks[img, torch.randperm(HW, generator=gsel)[:max(5, int(0.3 * HW))]] = True
     mask_idx = masks.flatten().nonzero().flatten()
     mw = (1.0 / masks.sum(-1).clamp(min=1).float())[:, None].expand_as(masks)[masks]
     n_m = mask_idx.numel()
@@ -144,7 +190,7 @@ def test_ssl_objective_gradients():
     hp = _leafs(hsd)
     hp_full = {"h." + k: v for k, v in hp.items()}
     with torch.no_grad():
-        t_out = vo.trunk_forward([gc], [None], sd, depth=2, heads=2, mode="bf16", use_bottleneck=False)[0]
+        t_out = vo.trunk_forward([gc], [None], sd, depth=2, heads=c.heads, mode="bf16", use_bottleneck=False)[0]
         tcls = t_out["x_norm_clstoken"]
         tcls = torch.cat([tcls[B:], tcls[:B]])
         tpatch = t_out["x_norm_patchtokens"].flatten(0, 1)[mask_idx]
@@ -152,7 +198,7 @@ def test_ssl_objective_gradients():
         tlog = vo.dino_head(vo._r(torch.cat([tcls, tpatch]), "bf16"), th, "h.", mode="bf16")
         tp_cls = vo.teacher_probs(tlog[:2 * B], torch.zeros(K), 0.07)
         tp_m = vo.teacher_probs(tlog[2 * B:], torch.zeros(K), 0.07)
-    sg, sl = vo.trunk_forward([gc, lc], [masks, None], p, depth=2, heads=2, mode="bf16", use_bottleneck=False)
+    sg, sl = vo.trunk_forward([gc, lc], [masks, None], p, depth=2, heads=c.heads, mode="bf16", use_bottleneck=False)
     s_in = torch.cat([sl["x_norm_clstoken"], sg["x_norm_clstoken"], sg["x_norm_patchtokens"].flatten(0, 1)[mask_idx]])
     slog = vo.dino_head(vo._r(s_in, "bf16"), hp_full, "h.", mode="bf16")
     nl = n_loc * B
@@ -175,11 +221,11 @@ def test_ssl_objective_gradients():
         errs[f"head.mlp{j}.b"] = _check(tr, f"head.mlp{j}.b", hp[f"mlp.{j}.bias"].grad)
     errs["head.last_v"] = _check(tr, "head.last_v", hp["last_layer.weight_v"].grad)
     errs["head.last_g"] = _check(tr, "head.last_g", hp["last_layer.weight_g"].grad)
-    print("ssl grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
+    print(f"[{geo}] ssl grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
 
 
 def test_full_step_runs_and_learns():
-    cfg, sd, hsd, tr = _setup()
+    cfg, sd, hsd, tr = _setup_tiny()
     tr.tc.lr = 2e-4
     B, n_loc, HW = 4, 2, 16
     masks = torch.zeros(2 * B, HW, dtype=torch.bool)
@@ -213,7 +259,7 @@ def test_rec_objective_with_lpips_gradients():
     """recon = L1 + 1.0 * LPIPS (frozen seeded-random VGG16): loss terms and trunk/decoder gradients vs oracle autograd."""
     from vtp_b200.lpips import LPIPSLoss, random_weights
 
-    cfg, sd, hsd, tr = _setup()
+    cfg, sd, hsd, tr = _setup_tiny()
     vw, vb, lw = random_weights(0)
     tr.enable_lpips(LPIPSLoss(vw, vb, lw, device="cuda", chunk=2))
     x = seeded_images(3, 64, 64) * 0.5
@@ -257,7 +303,7 @@ def test_graph_step_equals_eager_steps():
     seq = [batch, batch, b2, batch, b2]                             # the capture's two warm-up steps train on `batch`
 
     def trainer():
-        _, _, _, t = _setup()
+        _, _, _, t = _setup_tiny()
         t.hyper[3] = 2e-4
         t.enable_lpips(seed=0, chunk=2)
         return t
@@ -287,7 +333,7 @@ def test_device_schedules_drive_the_optimizer():
     (eagerly and inside the captured graph), holding the last value past the end."""
     from vtp_b200.schedules import CosineSchedule
 
-    _, _, _, tr = _setup()
+    _, _, _, tr = _setup_tiny()
     lr = CosineSchedule(1e-3, 1e-5, total_iters=6, warmup_iters=2, start_warmup_value=1e-6)
     mom = CosineSchedule(0.99, 1.0, total_iters=4)
     tr.set_schedules(lr=lr, teacher_momentum=mom)

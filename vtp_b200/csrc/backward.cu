@@ -29,8 +29,12 @@ __device__ __forceinline__ void ld4<__nv_bfloat16>(const __nv_bfloat16* p, float
 // ------------------------------------------------------------------------------------------------ norm backward
 // g[m,:] += dx[m,:] where dx is the input-gradient of RMSNorm / LayerNorm given dy (bf16) ; dw += Σ dy∘xhat ; db += Σ dy
 // One warp per row, 8 rows per warp-iteration strip; per-block column partials -> fp32 atomics.
+// Occupancy: ncu (profiles/ncu_hbm_r2.md) showed the 512-thread / 124-register version at ONE block per SM (16 warps, 25 %
+// occupancy, 64 % of the copy bandwidth).  256-thread blocks capped at 80 registers run three per SM; D <= 384 gets its own
+// MAXV = 3 instantiation (36 column accumulators instead of 48) and the row values are re-derived from x, dy after the
+// row reduction instead of being kept in a second register array.
 template <typename TX, int MAXV>
-__global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restrict__ rstd_, const float* __restrict__ mean_,
+__global__ void __launch_bounds__(256, (MAXV <= 4 ? 3 : (MAXV <= 8 ? 2 : 1))) norm_bwd_kernel(const TX* __restrict__ x, const float* __restrict__ rstd_, const float* __restrict__ mean_,
                                 const float* __restrict__ w, const __nv_bfloat16* __restrict__ dy, float* __restrict__ g,
                                 float* __restrict__ dw, float* __restrict__ db, int M, int D, int rows_per_block,
                                 int is_ln, int x_rounded_bf16, __nv_bfloat16* __restrict__ gb_out,
@@ -49,21 +53,25 @@ __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restric
     for (int row = r0 + warp; row < r1; row += nw) {
         const float rstd = rstd_[row];
         const float mean = is_ln ? mean_[row] : 0.f;
-        float xh[MAXV][4], dxh[MAXV][4];
+        float xh[MAXV][4];   // normalised input; dy stays packed (bf16) and dy*w is re-derived after the row reduction
+        uint2 dyp[MAXV];
         float4 gv4[MAXV];  // stream gradient: loaded up front so its latency overlaps the row reductions
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int gidx = 0; gidx < MAXV; ++gidx) {
             const int c = (gidx * 32 + lane) * 4;
-            if (c < D) gv4[gidx] = *reinterpret_cast<const float4*>(g + (long)row * D + c);
+            if (c < D) {
+                gv4[gidx] = *reinterpret_cast<const float4*>(g + (long)row * D + c);
+                dyp[gidx] = *reinterpret_cast<const uint2*>(dy + (long)row * D + c);
+            }
         }
 #pragma unroll
         for (int gidx = 0; gidx < MAXV; ++gidx) {
             const int c = (gidx * 32 + lane) * 4;
             if (c < D) {
-                float xv[4], dv[4];
+                float xv[4];
                 ld4<TX>(x + (long)row * D + c, xv);
-                ld4<__nv_bfloat16>(dy + (long)row * D + c, dv);
+                const float dv[4] = {bf16_lo(dyp[gidx].x), bf16_hi(dyp[gidx].x), bf16_lo(dyp[gidx].y), bf16_hi(dyp[gidx].y)};
                 const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
                 const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -71,9 +79,9 @@ __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restric
                     float h = (xv[i] - mean) * rstd;
                     if (x_rounded_bf16) h = bf16_round(h);
                     xh[gidx][i] = h;
-                    dxh[gidx][i] = dv[i] * wv[i];
-                    s1 += dxh[gidx][i];
-                    s2 += dxh[gidx][i] * h;
+                    const float dx = dv[i] * wv[i];
+                    s1 += dx;
+                    s2 += dx * h;
                     aw[gidx][i] += dv[i] * h;
                     ab[gidx][i] += dv[i];
                 }
@@ -87,10 +95,11 @@ __global__ void norm_bwd_kernel(const TX* __restrict__ x, const float* __restric
             if (c < D) {
                 float4* gp = reinterpret_cast<float4*>(g + (long)row * D + c);
                 float4 gv = gv4[gidx];
-                gv.x += rstd * (dxh[gidx][0] - m1 - xh[gidx][0] * m2);
-                gv.y += rstd * (dxh[gidx][1] - m1 - xh[gidx][1] * m2);
-                gv.z += rstd * (dxh[gidx][2] - m1 - xh[gidx][2] * m2);
-                gv.w += rstd * (dxh[gidx][3] - m1 - xh[gidx][3] * m2);
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w + c));
+                gv.x += rstd * (bf16_lo(dyp[gidx].x) * w4.x - m1 - xh[gidx][0] * m2);
+                gv.y += rstd * (bf16_hi(dyp[gidx].x) * w4.y - m1 - xh[gidx][1] * m2);
+                gv.z += rstd * (bf16_lo(dyp[gidx].y) * w4.z - m1 - xh[gidx][2] * m2);
+                gv.w += rstd * (bf16_hi(dyp[gidx].y) * w4.w - m1 - xh[gidx][3] * m2);
                 *gp = gv;
                 if (gb_out) {  // bf16 copy of the updated stream gradient = dY operand of the next (earlier) sub-layer
                     uint2 t2;
@@ -304,7 +313,11 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
         bc1 = hyper[1], bc2 = hyper[2], lr = hyper[3], ema_mom = hyper[5];
         if (wd != 0.f) wd = hyper[4];     // regions without decay (norms, biases) keep 0
     }
-    // 4 parameters per thread per iteration (all buffers are 128-byte aligned and n % 4 == 0 by construction)
+    // 4 parameters per thread per iteration (all buffers are 128-byte aligned and n % 4 == 0 by construction).
+    // The two divisions and the square root per parameter use the hardware approximations (MUFU.RCP / MUFU.SQRT, <= 2 ulp):
+    // ncu (profiles/ncu_hbm_r2.md) showed 660 executed instructions per float4 with the IEEE sequences and their slow-path
+    // branches — 28 % of the copy bandwidth; the update is rounded to a bf16 compute copy anyway.
+    const float ibc1 = 1.f / bc1, ibc2 = 1.f / bc2;
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n4; i += (long)gridDim.x * blockDim.x) {
         float4 gi = reinterpret_cast<float4*>(g)[i];
         float4 mi = reinterpret_cast<float4*>(m)[i], vi = reinterpret_cast<float4*>(v)[i], pi = reinterpret_cast<float4*>(p)[i];
@@ -315,7 +328,9 @@ __global__ void adamw_kernel(float* __restrict__ p, float* __restrict__ g, float
         for (int k = 0; k < 4; ++k) {
             ma[k] = b1 * ma[k] + (1.f - b1) * ga[k];
             va[k] = b2 * va[k] + (1.f - b2) * ga[k] * ga[k];
-            pa[k] -= lr * ((ma[k] / bc1) / (sqrtf(va[k] / bc2) + eps) + wd * pa[k]);
+            float sq;
+            asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(va[k] * ibc2));
+            pa[k] -= lr * (__fdividef(ma[k] * ibc1, sq + eps) + wd * pa[k]);
         }
         reinterpret_cast<float4*>(m)[i] = make_float4(ma[0], ma[1], ma[2], ma[3]);
         reinterpret_cast<float4*>(v)[i] = make_float4(va[0], va[1], va[2], va[3]);
@@ -400,7 +415,7 @@ extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const
     VTP_CHECK_ARG(!is_ln || mean, "norm_bwd: LayerNorm needs mean");
     VTP_CHECK_ARG((reinterpret_cast<uintptr_t>(dw) & 15) == 0 && (!db || (reinterpret_cast<uintptr_t>(db) & 15) == 0),
                   "norm_bwd: dw/db must be 16B aligned");
-    const int threads = D <= 512 ? 512 : 256, rows_per_block = 128;  // register budget of the wider variants
+    const int threads = 256, rows_per_block = 128;   // 3 blocks of 256 threads per SM (see norm_bwd_kernel)
     const int grid = ceil_div(M, rows_per_block);
     VTP_CHECK_ARG(!g_colsum || (reinterpret_cast<uintptr_t>(g_colsum) & 15) == 0, "norm_bwd: g_colsum must be 16B aligned");
     const size_t smem = 3 * (size_t)D * sizeof(float);
@@ -409,11 +424,15 @@ extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const
 #define LB(T, MV) \
     norm_bwd_kernel<T, MV><<<grid, threads, smem, s>>>((const T*)x, rstd, mean, w, (const __nv_bfloat16*)dy, g, dw, db, M, D, rows_per_block, is_ln, xr, (__nv_bfloat16*)g_bf16_out, g_colsum)
     if (x_dtype == VTP_F32) {
-        if (D <= 512) LB(float, 4);
+        if (D <= 384) LB(float, 3);
+        else if (D <= 512) LB(float, 4);
+        else if (D <= 768) LB(float, 6);
         else if (D <= 1024) LB(float, 8);
         else LB(float, 16);
     } else {
-        if (D <= 512) LB(__nv_bfloat16, 4);
+        if (D <= 384) LB(__nv_bfloat16, 3);
+        else if (D <= 512) LB(__nv_bfloat16, 4);
+        else if (D <= 768) LB(__nv_bfloat16, 6);
         else if (D <= 1024) LB(__nv_bfloat16, 8);
         else LB(__nv_bfloat16, 16);
     }

@@ -70,51 +70,65 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
     return q;
 }
 
-__global__ void dino_teacher_kernel(__nv_bfloat16* __restrict__ t, const float* __restrict__ center, int K, float inv_temp) {
+// Round-2 rewrite (ncu, profiles/ncu_hbm_r2.md: 26 / 35 executed instructions per element, 25 % occupancy): 1024 threads per
+// row block (32 warps/SM), base-2 exponentials with the temperature folded into one FFMA per element, every pass fully
+// vectorised on 16-byte shared / global accesses.
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(1024, 1)
+dino_teacher_kernel(__nv_bfloat16* __restrict__ t, const float* __restrict__ center, int K, float inv_temp) {
     extern __shared__ uint4 rowq[];  // K/8 packed bf16x8 (128 KB at K = 65536)
     __shared__ float sh[32];
     uint4* tr = reinterpret_cast<uint4*>(t + (long)blockIdx.x * K);
     const float4* c4 = reinterpret_cast<const float4*>(center);
     const int K8 = K >> 3;
-    float m = -INFINITY;
+    const float it2 = inv_temp * 1.4426950408889634f;   // exp(z / temp) = 2^(z * it2)
+    float m = -INFINITY;                                // max of (t - c): inv_temp > 0, scale once afterwards
     for (int c = threadIdx.x; c < K8; c += blockDim.x) {
         const uint4 q = tr[c];
         rowq[c] = q;
         float f[8];
         unpack8(q, f);
         const float4 a = __ldg(c4 + 2 * c), b = __ldg(c4 + 2 * c + 1);
-        const float cc[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) m = fmaxf(m, (f[i] - cc[i]) * inv_temp);
+        m = fmaxf(m, fmaxf(fmaxf(f[0] - a.x, f[1] - a.y), fmaxf(f[2] - a.z, f[3] - a.w)));
+        m = fmaxf(m, fmaxf(fmaxf(f[4] - b.x, f[5] - b.y), fmaxf(f[6] - b.z, f[7] - b.w)));
     }
     m = block_reduce(m, sh, true);
-    float s = 0.f;
+    const float m2 = m * it2;
+    float s0 = 0.f, s1 = 0.f;
     for (int c = threadIdx.x; c < K8; c += blockDim.x) {
         float f[8];
         unpack8(rowq[c], f);
         const float4 a = __ldg(c4 + 2 * c), b = __ldg(c4 + 2 * c + 1);
-        const float cc[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s += __expf((f[i] - cc[i]) * inv_temp - m);
+        s0 += ex2_approx(fmaf(f[0] - a.x, it2, -m2)) + ex2_approx(fmaf(f[1] - a.y, it2, -m2)) +
+              ex2_approx(fmaf(f[2] - a.z, it2, -m2)) + ex2_approx(fmaf(f[3] - a.w, it2, -m2));
+        s1 += ex2_approx(fmaf(f[4] - b.x, it2, -m2)) + ex2_approx(fmaf(f[5] - b.y, it2, -m2)) +
+              ex2_approx(fmaf(f[6] - b.z, it2, -m2)) + ex2_approx(fmaf(f[7] - b.w, it2, -m2));
     }
-    s = block_reduce(s, sh, false);
-    const float lse = m + logf(s);
+    const float ssum = block_reduce(s0 + s1, sh, false);
+    const float l2 = m2 + log2f(ssum);                  // log2 of the partition function
     for (int c = threadIdx.x; c < K8; c += blockDim.x) {
         float f[8];
         unpack8(rowq[c], f);
         const float4 a = __ldg(c4 + 2 * c), b = __ldg(c4 + 2 * c + 1);
-        const float cc[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = __expf((f[i] - cc[i]) * inv_temp - lse);
+        f[0] = ex2_approx(fmaf(f[0] - a.x, it2, -l2)), f[1] = ex2_approx(fmaf(f[1] - a.y, it2, -l2));
+        f[2] = ex2_approx(fmaf(f[2] - a.z, it2, -l2)), f[3] = ex2_approx(fmaf(f[3] - a.w, it2, -l2));
+        f[4] = ex2_approx(fmaf(f[4] - b.x, it2, -l2)), f[5] = ex2_approx(fmaf(f[5] - b.y, it2, -l2));
+        f[6] = ex2_approx(fmaf(f[6] - b.z, it2, -l2)), f[7] = ex2_approx(fmaf(f[7] - b.w, it2, -l2));
         tr[c] = pack8(f);
     }
 }
 
 // student: for row r with teacher rows t0[r], t1[r] (−1 = none), weight w[r]:
 //   z = s/τ ;  loss += w Σ_v (lse(z) − Σ_k T_v[k] z[k]) ;  ds[k] = (w/τ) (n_v softmax(z)[k] − Σ_v T_v[k])   (in place, bf16)
-__global__ void dino_student_kernel(__nv_bfloat16* __restrict__ s, const __nv_bfloat16* __restrict__ tprobs,
-                                    const int* __restrict__ t0, const int* __restrict__ t1, const float* __restrict__ w,
-                                    int K, float inv_temp, float* __restrict__ loss_acc) {
+__global__ void __launch_bounds__(1024, 1)
+dino_student_kernel(__nv_bfloat16* __restrict__ s, const __nv_bfloat16* __restrict__ tprobs,
+                    const int* __restrict__ t0, const int* __restrict__ t1, const float* __restrict__ w,
+                    int K, float inv_temp, float* __restrict__ loss_acc) {
     extern __shared__ uint4 rowq[];  // K/8 packed student logits
     __shared__ float sh[32];
     const int r = blockIdx.x;
@@ -125,60 +139,58 @@ __global__ void dino_student_kernel(__nv_bfloat16* __restrict__ s, const __nv_bf
     const uint4* tb = i1 >= 0 ? reinterpret_cast<const uint4*>(tprobs + (long)i1 * K) : nullptr;
     const float nv = (ta ? 1.f : 0.f) + (tb ? 1.f : 0.f);
     const int K8 = K >> 3;
-    float m = -INFINITY, dot = 0.f;
+    const float it2 = inv_temp * 1.4426950408889634f;
+    float m = -INFINITY, dot = 0.f;                     // max of the raw logits; dot = Σ_k T[k] s[k] (scaled afterwards)
     for (int c = threadIdx.x; c < K8; c += blockDim.x) {
         const uint4 q = sr[c];
         rowq[c] = q;
         float z[8], tt[8];
         unpack8(q, z);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] *= inv_temp, tt[i] = 0.f, m = fmaxf(m, z[i]);
+        m = fmaxf(m, fmaxf(fmaxf(fmaxf(z[0], z[1]), fmaxf(z[2], z[3])), fmaxf(fmaxf(z[4], z[5]), fmaxf(z[6], z[7]))));
         if (ta) {
-            float f[8];
-            unpack8(__ldg(ta + c), f);
+            unpack8(__ldg(ta + c), tt);
+            if (tb) {
+                float f[8];
+                unpack8(__ldg(tb + c), f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tt[i] += f[i];
+                for (int i = 0; i < 8; ++i) tt[i] += f[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot = fmaf(tt[i], z[i], dot);
         }
-        if (tb) {
-            float f[8];
-            unpack8(__ldg(tb + c), f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tt[i] += f[i];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) dot += tt[i] * z[i];
     }
     m = block_reduce(m, sh, true);
-    dot = block_reduce(dot, sh, false);
-    float se = 0.f;
+    dot = block_reduce(dot, sh, false) * inv_temp;
+    const float m2 = m * it2;
+    float se0 = 0.f, se1 = 0.f;
     for (int c = threadIdx.x; c < K8; c += blockDim.x) {
         float z[8];
         unpack8(rowq[c], z);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) se += __expf(z[i] * inv_temp - m);
+        se0 += ex2_approx(fmaf(z[0], it2, -m2)) + ex2_approx(fmaf(z[1], it2, -m2)) + ex2_approx(fmaf(z[2], it2, -m2)) +
+               ex2_approx(fmaf(z[3], it2, -m2));
+        se1 += ex2_approx(fmaf(z[4], it2, -m2)) + ex2_approx(fmaf(z[5], it2, -m2)) + ex2_approx(fmaf(z[6], it2, -m2)) +
+               ex2_approx(fmaf(z[7], it2, -m2));
     }
-    se = block_reduce(se, sh, false);
-    const float lse = m + logf(se);
-    const float gscale = wr * inv_temp;
+    const float se = block_reduce(se0 + se1, sh, false);
+    const float l2 = m2 + log2f(se);
+    const float lse = l2 * 0.6931471805599453f;         // natural-log partition function of z = s / temp
+    const float gscale = wr * inv_temp, gn = gscale * nv;
     for (int c = threadIdx.x; c < K8; c += blockDim.x) {
         float z[8], tt[8];
         unpack8(rowq[c], z);
 #pragma unroll
         for (int i = 0; i < 8; ++i) tt[i] = 0.f;
         if (ta) {
-            float f[8];
-            unpack8(__ldg(ta + c), f);
+            unpack8(__ldg(ta + c), tt);
+            if (tb) {
+                float f[8];
+                unpack8(__ldg(tb + c), f);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) tt[i] += f[i];
-        }
-        if (tb) {
-            float f[8];
-            unpack8(__ldg(tb + c), f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) tt[i] += f[i];
+                for (int i = 0; i < 8; ++i) tt[i] += f[i];
+            }
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) z[i] = gscale * (nv * __expf(z[i] * inv_temp - lse) - tt[i]);
+        for (int i = 0; i < 8; ++i) z[i] = fmaf(gn, ex2_approx(fmaf(z[i], it2, -l2)), -gscale * tt[i]);
         sr[c] = pack8(z);
     }
     if (threadIdx.x == 0) atomicAdd(loss_acc, wr * (nv * lse - dot));
@@ -241,7 +253,7 @@ extern "C" int vtp_dino_teacher_probs(void* t_bf16, const float* center, int R, 
         VTP_CUDA(cudaFuncSetAttribute(dino_teacher_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conf = smem;
     }
-    dino_teacher_kernel<<<R, 512, smem, (cudaStream_t)st>>>((__nv_bfloat16*)t_bf16, center, K, 1.f / temp);
+    dino_teacher_kernel<<<R, 1024, smem, (cudaStream_t)st>>>((__nv_bfloat16*)t_bf16, center, K, 1.f / temp);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }
@@ -257,7 +269,7 @@ extern "C" int vtp_dino_student_ce(void* s_bf16, const void* tprobs_bf16, const 
         VTP_CUDA(cudaFuncSetAttribute(dino_student_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         conf = smem;
     }
-    dino_student_kernel<<<R, 512, smem, (cudaStream_t)st>>>((__nv_bfloat16*)s_bf16, (const __nv_bfloat16*)tprobs_bf16, t0, t1,
+    dino_student_kernel<<<R, 1024, smem, (cudaStream_t)st>>>((__nv_bfloat16*)s_bf16, (const __nv_bfloat16*)tprobs_bf16, t0, t1,
                                                           w, K, 1.f / temp, loss_acc);
     VTP_LAUNCH_CHECK();
     return VTP_OK;

@@ -181,6 +181,32 @@ def tower_blocks_backward(W: TowerW, G: TowerW, tape: list, g: torch.Tensor, B: 
     return g
 
 
+def grad_buckets(offset: Dict[str, int], n: int) -> Dict[str, List[Tuple[int, int]]]:
+    """Contiguous ranges of the flat gradient buffer per tower.  A tower's gradient is FINAL as soon as its last
+    backward of the step has run: text tower + clip projection + logit scale after the contrastive objective, DINO head
+    after the SSL head backward, pixel decoder after its backward inside the reconstruction objective; the trunk (all
+    three objectives accumulate into it) only at the end of the step.  Each finished bucket is all-reduced right away
+    (NCCL's own stream) under the remaining backward; only the trunk bucket is exposed."""
+    def bucket_of(name: str) -> str:
+        if name.startswith("text.") or name.startswith("visual_proj") or name == "logit_scale":
+            return "text"
+        if name.startswith("head."):
+            return "head"
+        if name.startswith("decoder."):
+            return "decoder"
+        return "trunk"
+    spans = sorted((off, name) for name, off in offset.items())
+    out: Dict[str, List[Tuple[int, int]]] = {"text": [], "head": [], "decoder": [], "trunk": []}
+    for i, (off, name) in enumerate(spans):
+        end = spans[i + 1][0] if i + 1 < len(spans) else n   # incl. the alignment padding behind the tensor
+        r = out[bucket_of(name)]
+        if r and r[-1][1] == off:
+            r[-1] = (r[-1][0], end)
+        else:
+            r.append((off, end))
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------ trainer
 @dataclass
 class TrainConfig:
@@ -272,8 +298,23 @@ class VTPTrainer:
         self.hyper = torch.zeros(8, dtype=F32, device=self.device)
         self.hyper[3:6] = torch.tensor([self.tc.lr, self.tc.weight_decay, self.tc.teacher_momentum], device=self.device)
         self._sched = (None, None, None, 0)     # device tables (lr, wd, momentum) + common length
+        self._buckets = self._grad_buckets()    # collective C3: gradient all-reduce per tower, overlapped with backward
+        self._pending = []                      # in-flight all-reduce handles of the current step
+        self._started = set()                   # buckets whose all-reduce has been started this step
         self._graph = None                      # CUDA graph of the whole step, see capture_step()
         self.reset_parameters()
+
+    def _grad_buckets(self) -> Dict[str, List[Tuple[int, int]]]:
+        return grad_buckets(self.store.offset, self.store.n)
+
+    def _reduce_bucket(self, which: str):
+        """Start the all-reduce of one finished gradient bucket (no-op single rank / already started this step)."""
+        if self.world == 1 or which in self._started:
+            return
+        import torch.distributed as dist
+        self._started.add(which)
+        for a, b in self._buckets[which]:
+            self._pending.append(dist.all_reduce(self.store.g[a:b], group=self.pg, async_op=True))
 
     def enable_lpips(self, module=None, seed: int = 0, chunk: int = 32):
         """Attach the LPIPS term (utils/lpips.py) to the reconstruction loss: rec = L1 + lpips_weight * LPIPS.  Without
@@ -627,7 +668,7 @@ class VTPTrainer:
 
     # -------------------------------------------------------------- objective 3: reconstruction (vtp.py:487-512)
     def rec_fwd_bwd(self, image: torch.Tensor, weight: float = 1.0, return_image: bool = False,
-                    norm_B: Optional[int] = None):
+                    norm_B: Optional[int] = None, final_group: bool = False):
         """norm_B: batch size the loss is normalised by (the whole per-GPU batch when `image` is one chunk of it)."""
         dev = self.device
         W, G = self.towers[("trunk", "param")], self.towers[("trunk", "grad")]
@@ -676,6 +717,8 @@ class VTPTrainer:
         dz = torch.zeros((M, bn), dtype=BF, device=dev)  # d(latent tokens), re-expanded to [B*T] rows (cls rows = 0)
         dgrad(gb, pin.w, dz, Md, rr_group=HW, rr_skip=1)
         wgrad(gb, tok, Gd.extra["proj_in"].w, Md)
+        if final_group:
+            self._reduce_bucket("decoder")   # pixel-decoder gradient is final: all-reduce under the encoder backward
         # ---- encoder side
         dxn = _e((M, D), BF, dev)
         dgrad(dz, bneck.w, dxn, M)
@@ -792,7 +835,8 @@ class VTPTrainer:
                 bc = b1 - b0
                 g = torch.cat([global_crops[b0:b1], global_crops[B + b0:B + b1]])
                 l = lc[:, b0:b1].reshape(n_loc * bc, *local_crops.shape[1:])
-                self._ssl_chunk(g, l, mask_groups[f"mask_indices@{i}"], mask_groups[f"masks_weight@{i}"], weight, B, csum)
+                self._ssl_chunk(g, l, mask_groups[f"mask_indices@{i}"], mask_groups[f"masks_weight@{i}"], weight, B, csum,
+                                final_group=(b1 == B))
         # teacher centre EMA over the whole (global) batch (DINOv2 softmax_center_teacher / update_center)
         cnt = torch.empty(2, dtype=F32, device=dev)          # fill kernels, no host copy: the step is graph-capturable
         cnt[0:1].fill_(float(B2)), cnt[1:2].fill_(float(max(n_m, 1)))
@@ -804,7 +848,8 @@ class VTPTrainer:
         lib.axpby(self.center_dino, mean[0].contiguous(), cm, 1 - cm, K)
         lib.axpby(self.center_ibot, mean[1].contiguous(), cm, 1 - cm, K)
 
-    def _ssl_chunk(self, global_crops, local_crops, mask_indices, masks_weight, weight: float, norm_B: int, csum):
+    def _ssl_chunk(self, global_crops, local_crops, mask_indices, masks_weight, weight: float, norm_B: int, csum,
+                   final_group: bool = True):
         """Teacher + student forward, DINO/iBOT losses and the full backward for one group of source images; the loss
         terms are normalised by `norm_B` (the whole per-GPU batch) and the raw teacher-logit sums are added to csum."""
         dev, tc = self.device, self.tc
@@ -867,6 +912,8 @@ class VTPTrainer:
         # ---------------- backward: head -> scatter to the two trunk passes
         dsin = self._head_bwd(htape, slog)
         del slog, htape
+        if final_group:
+            self._reduce_bucket("head")  # DINO head gradient is final: all-reduce under the trunk backward
         dl32 = torch.zeros((Bl * Tl, D), dtype=F32, device=dev)
         lib.scatter_add_rows(dsin[:Bl], dl32, l_rows, D)
         dxl = _e((Bl * Tl, D), BF, dev)
@@ -885,9 +932,14 @@ class VTPTrainer:
 
     # -------------------------------------------------------------- optimiser (+ EMA teacher, vtp.py:388-401)
     def allreduce_grads(self):
+        """Collective C3: whatever bucket has not been started yet (always the trunk), then wait for all of them; the
+        sum is averaged by grad_scale = 1/world inside the fused optimiser.  fp32 on the wire (exact accumulation)."""
         if self.world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(self.store.g, group=self.pg)   # collective C3; averaged by grad_scale in the optimiser
+            for which in ("text", "head", "decoder", "trunk"):
+                self._reduce_bucket(which)
+            for w in self._pending:
+                w.wait()                 # the compute stream waits for NCCL's stream; the host does not block
+            self._pending = []
 
     def set_schedules(self, lr=None, weight_decay=None, teacher_momentum=None):
         """Per-step schedules for the learning rate, weight decay and EMA teacher momentum: `schedules.CosineSchedule`
@@ -996,8 +1048,10 @@ class VTPTrainer:
         is invalid — `check_exchange()` raises in that case."""
         tc = self.tc
         self.loss_acc.zero_()
+        self._started = set()
         if tc.w_clip:
             self.clip_fwd_bwd(batch["image"], batch["text"], tc.w_clip)
+        self._reduce_bucket("text")      # text tower, clip projection, logit scale: final — reduce under the SSL objective
         if tc.w_ssl:
             self.ssl_fwd_bwd(batch["global_crops"], batch["local_crops"], batch["mask_indices"], batch["masks_weight"],
                              tc.w_ssl, mask_groups=batch)
@@ -1006,7 +1060,7 @@ class VTPTrainer:
             nB = img.shape[0]
             rc = tc.rec_chunk if 0 < tc.rec_chunk < nB else nB
             for b0 in range(0, nB, rc):
-                self.rec_fwd_bwd(img[b0:b0 + rc], tc.w_rec, norm_B=nB)
+                self.rec_fwd_bwd(img[b0:b0 + rc], tc.w_rec, norm_B=nB, final_group=(b0 + rc >= nB))
         self.allreduce_grads()
         self.optimizer_step()
         return self.loss_acc
