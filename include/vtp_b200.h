@@ -102,6 +102,13 @@ int vtp_transpose_batched(const void* in, int in_dtype, long in_bstride, void* o
 /* out[i,:] = in[idx[i],:] (vtp.py:432-439,470-473 iBOT gather; encoders/text_transformer.py:224 argmax pool) */
 int vtp_gather_rows(const void* in, int in_dtype, long ld_in, void* out, int out_dtype, long ld_out, const int64_t* idx,
                     int n, int D, vtp_stream_t stream);
+/* batch-subset stochastic depth (layers/block.py:201-233): out[i*T + t, :] = alpha * x[img_idx[i]*T + t, :]  (= x[indices];
+ * alpha = 1 forward, = b/keep for the gradient of the scaled residual) and its dual
+ * dst[img_idx[i]*T + t, :] += alpha * src[i*T + t, :]  (= torch.index_add(x, 0, residual, indices, alpha)); indices distinct */
+int vtp_gather_images(const float* x, float* out, const int64_t* img_idx, int n_img, int T, int D, float alpha,
+                      vtp_stream_t stream);
+int vtp_scatter_add_images(const void* src, int src_dtype, float* dst, const int64_t* img_idx, int n_img, int T, int D,
+                           float alpha, vtp_stream_t stream);
 /* stand-alone SwiGLU gate (layers/ffn.py:77-81) on the 8-interleaved pre-activation: hid = round(round(silu(x1))*x2) */
 int vtp_swiglu_fwd(const void* pre, void* hid, long M, int Hs, vtp_stream_t stream);
 /* stand-alone in-place axial RoPE (layers/attention.py:12-23,70-89, bf16 arithmetic) on the q,k parts of bf16 qkv */

@@ -162,8 +162,17 @@ def _norm(x: Tensor, sd, pre: str, kind: str) -> Tensor:
     return layernorm(x, sd[pre + "weight"], sd[pre + "bias"], eps)
 
 
-def block(x: Tensor, sd, pre: str, heads: int, rope, norm_kind: str, mode: str, stream_bf16: bool) -> Tensor:
-    """layers/block.py:290-296 (eval / drop_ratio=0 branch; LayerScale is Identity when init_values is None)."""
+def block(x: Tensor, sd, pre: str, heads: int, rope, norm_kind: str, mode: str, stream_bf16: bool, drop=None) -> Tensor:
+    """layers/block.py:290-296 (eval / drop_ratio=0 branch; LayerScale is Identity when init_values is None).
+    drop = (idx1, scale1, idx2, scale2): the training branch with batch-subset stochastic depth, layers/block.py:201-233 —
+    `x[indices]` -> sub-layer -> `torch.index_add(x, 0, residual, indices, alpha=residual_scale_factor)`; the subsets are
+    arguments here (the reference draws them with torch.randperm inside get_branges_scales, block.py:20-118)."""
+    if drop is not None:
+        idx1, s1, idx2, s2 = drop
+        r1 = self_attention(_norm(x[idx1], sd, pre + "norm1.", norm_kind), sd, pre + "attn.", heads, rope, mode)
+        x = torch.index_add(x, 0, idx1, r1.to(x.dtype), alpha=s1)
+        r2 = swiglu(_norm(x[idx2], sd, pre + "norm2.", norm_kind), sd, pre + "mlp.", mode)
+        return torch.index_add(x, 0, idx2, r2.to(x.dtype), alpha=s2)
     a = self_attention(_norm(x, sd, pre + "norm1.", norm_kind), sd, pre + "attn.", heads, rope, mode)
     x = x + a
     if stream_bf16:
@@ -186,7 +195,7 @@ def patch_embed(img: Tensor, sd, pre: str, mode: str) -> Tensor:
 
 def trunk_forward(img_list: Sequence[Tensor], masks_list: Sequence[Optional[Tensor]], sd, *, pre: str = "trunk.",
                   depth: int, heads: int, norm_kind: str = "rmsnorm", mode: str = "fp32",
-                  use_bottleneck: bool = True) -> List[Dict[str, Tensor]]:
+                  use_bottleneck: bool = True, drops=None) -> List[Dict[str, Tensor]]:
     """encoders/vision_transformer.py:189-258 (prepare_tokens_with_masks + forward_features_list) and
     encoders/vision_transformer_bottleneck.py:48-79.  Encoder residual stream is fp32 in both modes."""
     periods = sd[pre + "rope_embed.periods"].to(BF)
@@ -202,8 +211,11 @@ def trunk_forward(img_list: Sequence[Tensor], masks_list: Sequence[Optional[Tens
             cls = cls + 0 * sd[pre + "mask_token"]
         xs.append(torch.cat([cls.expand(B, -1, -1).to(x.dtype), x], dim=1))
         ropes.append(rope_table(h, w, periods))
+    # drops[j][i] = (idx1, scale1, idx2, scale2) of list element j in block i (stochastic depth), or None
     for i in range(depth):
-        xs = [block(x, sd, f"{pre}blocks.{i}.", heads, r, norm_kind, mode, False) for x, r in zip(xs, ropes)]
+        xs = [block(x, sd, f"{pre}blocks.{i}.", heads, r, norm_kind, mode, False,
+                    drop=None if drops is None or drops[j] is None else drops[j][i])
+              for j, (x, r) in enumerate(zip(xs, ropes))]
     outs = []
     for x, masks in zip(xs, masks_list):
         xn = _norm(x, sd, pre + "norm.", norm_kind)

@@ -77,29 +77,48 @@ def _leafs(sd):
     return {k: (v.clone().float().requires_grad_(True) if v.is_floating_point() and "periods" not in k else v) for k, v in sd.items()}
 
 
-def _check(tr, name, ref, tol=TOL_G):
+FLOORS = {}      # name -> (error, tolerance used) of the current test, for the printed summary
+
+
+def _check(tr, name, ref, ref32=None):
+    """Gradient parity bound.  Both sides compute in bf16 with different accumulation orders, so the yardstick is the
+    reference algorithm's OWN sensitivity to that precision: ref32 = the same gradient from the oracle in fp32 mode;
+    tolerance = max(3 %, 1.25 x |oracle bf16 - oracle fp32|) for this tensor (measured: ~3.5 % at the tiny geometry, ~10 %
+    at VTP-Large width / depth 2 — two bf16 implementations cannot agree better than each agrees with fp32).  Without a
+    noise floor the flat 6 % bound of round 1 applies."""
     got = tr.store.grad(name).float().cpu()
     e = rel(got, ref.reshape(got.shape))
-    assert e < tol, (name, e)
+    tol = TOL_G if ref32 is None else max(3e-2, 1.25 * rel(ref, ref32))
+    FLOORS[name] = (e, tol)
+    assert e < tol, (name, e, tol)
     return e
 
 
-def _vit_checks(tr, p, pre_ref, pre, blocks, ln):
+def _vit_checks(tr, p, pre_ref, pre, blocks, ln, p32=None):
+    g32 = (lambda k: p32[k].grad) if p32 is not None else (lambda k: None)
     errs = {}
     for i in blocks:
         r, q = f"{pre_ref}blocks.{i}.", f"{pre}blocks.{i}."
-        errs[q + "qkv.w"] = _check(tr, q + "qkv.w", p[r + "attn.qkv.weight"].grad)
-        errs[q + "qkv.b"] = _check(tr, q + "qkv.b", p[r + "attn.qkv.bias"].grad)
-        errs[q + "proj.w"] = _check(tr, q + "proj.w", p[r + "attn.proj.weight"].grad)
-        errs[q + "fc1.w"] = _check(tr, q + "fc1.w", interleave8(p[r + "mlp.w1.weight"].grad, p[r + "mlp.w2.weight"].grad))
-        errs[q + "fc1.b"] = _check(tr, q + "fc1.b", interleave8(p[r + "mlp.w1.bias"].grad, p[r + "mlp.w2.bias"].grad))
-        errs[q + "fc2.w"] = _check(tr, q + "fc2.w", p[r + "mlp.w3.weight"].grad)
-        errs[q + "fc2.b"] = _check(tr, q + "fc2.b", p[r + "mlp.w3.bias"].grad)
-        errs[q + "n1_w"] = _check(tr, q + "n1_w", p[r + "norm1.weight"].grad)
-        errs[q + "n2_w"] = _check(tr, q + "n2_w", p[r + "norm2.weight"].grad)
+        errs[q + "qkv.w"] = _check(tr, q + "qkv.w", p[r + "attn.qkv.weight"].grad, g32(r + "attn.qkv.weight"))
+        errs[q + "qkv.b"] = _check(tr, q + "qkv.b", p[r + "attn.qkv.bias"].grad, g32(r + "attn.qkv.bias"))
+        errs[q + "proj.w"] = _check(tr, q + "proj.w", p[r + "attn.proj.weight"].grad, g32(r + "attn.proj.weight"))
+        errs[q + "fc1.w"] = _check(tr, q + "fc1.w", interleave8(p[r + "mlp.w1.weight"].grad, p[r + "mlp.w2.weight"].grad),
+                                  None if p32 is None else interleave8(p32[r + "mlp.w1.weight"].grad, p32[r + "mlp.w2.weight"].grad))
+        errs[q + "fc1.b"] = _check(tr, q + "fc1.b", interleave8(p[r + "mlp.w1.bias"].grad, p[r + "mlp.w2.bias"].grad),
+                                  None if p32 is None else interleave8(p32[r + "mlp.w1.bias"].grad, p32[r + "mlp.w2.bias"].grad))
+        errs[q + "fc2.w"] = _check(tr, q + "fc2.w", p[r + "mlp.w3.weight"].grad, g32(r + "mlp.w3.weight"))
+        errs[q + "fc2.b"] = _check(tr, q + "fc2.b", p[r + "mlp.w3.bias"].grad, g32(r + "mlp.w3.bias"))
+        errs[q + "n1_w"] = _check(tr, q + "n1_w", p[r + "norm1.weight"].grad, g32(r + "norm1.weight"))
+        errs[q + "n2_w"] = _check(tr, q + "n2_w", p[r + "norm2.weight"].grad, g32(r + "norm2.weight"))
         if ln:
-            errs[q + "n1_b"] = _check(tr, q + "n1_b", p[r + "norm1.bias"].grad)
+            errs[q + "n1_b"] = _check(tr, q + "n1_b", p[r + "norm1.bias"].grad, g32(r + "norm1.bias"))
     return errs
+
+
+def _summary(geo, what):
+    worst = max(FLOORS.items(), key=lambda kv: kv[1][0] / kv[1][1])
+    print(f"[{geo}] {what}: {len(FLOORS)} gradient tensors, max rel error {max(e for e, _ in FLOORS.values()):.3f}, median tolerance "
+          f"{sorted(t for _, t in FLOORS.values())[len(FLOORS) // 2]:.3f}, tightest = {worst[0]} ({worst[1][0]:.3f} of {worst[1][1]:.3f})")
 
 
 GEO_PARAMS = ["tiny", "small2", "large2"]
@@ -110,29 +129,32 @@ def test_rec_objective_gradients(geo):
     c = _setup(geo)
     tr = c.tr
     x = seeded_images(3 if geo == "tiny" else 2, c.img, c.img)
-    p = _leafs(c.sd)
-    lat = vo.reconstruction_latents(x, p, depth=2, heads=c.heads, mode="bf16")
-    rec = vo.decode_latents(lat, p, depth=2, heads=c.dheads, mode="bf16")
-    loss = vo.recon_loss(rec, x, None)
-    loss.backward()
+    def oracle(mode):
+        q = _leafs(c.sd)
+        lat = vo.reconstruction_latents(x, q, depth=2, heads=c.heads, mode=mode)
+        rec_ = vo.decode_latents(lat, q, depth=2, heads=c.dheads, mode=mode)
+        l = vo.recon_loss(rec_, x, None)
+        l.backward()
+        return q, rec_.detach(), l
+
+    p, rec, loss = oracle("bf16")
+    p32, _, _ = oracle("fp32")          # the algorithm's own bf16 sensitivity = the yardstick of _check
     out = tr.rec_fwd_bwd(x.cuda(), 1.0, return_image=True)
     torch.cuda.synchronize()
-    assert rel(out, rec.detach()) < 2e-2
+    assert rel(out, rec) < 2e-2
     assert abs(tr.loss_acc[4].item() - loss.item()) < TOL_L * loss.item()
-    errs = _vit_checks(tr, p, "trunk.", "trunk.", [0, 1], False)
-    errs.update(_vit_checks(tr, p, "pixel_decoder.", "decoder.", [0, 1], True))
-    errs["patch.w"] = _check(tr, "trunk.patch.w", p["trunk.patch_embed.proj.weight"].grad.flatten(1))
-    errs["patch.b"] = _check(tr, "trunk.patch.b", p["trunk.patch_embed.proj.bias"].grad)
-    errs["cls"] = _check(tr, "trunk.cls", p["trunk.cls_token"].grad)
-    errs["norm"] = _check(tr, "trunk.norm_w", p["trunk.norm.weight"].grad)
-    errs["bneck"] = _check(tr, "trunk.bneck.w", p["trunk.feature_bottleneck.weight"].grad)
-    errs["proj_in.w"] = _check(tr, "decoder.proj_in.w", p["pixel_decoder.proj_in.weight"].grad.flatten(1))
-    errs["proj_in.b"] = _check(tr, "decoder.proj_in.b", p["pixel_decoder.proj_in.bias"].grad)
-    errs["proj_out.w"] = _check(tr, "decoder.proj_out.w", p["pixel_decoder.proj_out.weight"].grad.flatten(1))
-    errs["proj_out.b"] = _check(tr, "decoder.proj_out.b", p["pixel_decoder.proj_out.bias"].grad)
-    errs["dec.norm_w"] = _check(tr, "decoder.norm_w", p["pixel_decoder.norm.weight"].grad)
-    errs["dec.norm_b"] = _check(tr, "decoder.norm_b", p["pixel_decoder.norm.bias"].grad)
-    print(f"[{geo}] rec grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
+    FLOORS.clear()
+    g, g32 = (lambda k: p[k].grad), (lambda k: p32[k].grad)
+    errs = _vit_checks(tr, p, "trunk.", "trunk.", [0, 1], False, p32)
+    errs.update(_vit_checks(tr, p, "pixel_decoder.", "decoder.", [0, 1], True, p32))
+    for ours, key, flat in (("trunk.patch.w", "trunk.patch_embed.proj.weight", True), ("trunk.patch.b", "trunk.patch_embed.proj.bias", False),
+                            ("trunk.cls", "trunk.cls_token", False), ("trunk.norm_w", "trunk.norm.weight", False),
+                            ("trunk.bneck.w", "trunk.feature_bottleneck.weight", False),
+                            ("decoder.proj_in.w", "pixel_decoder.proj_in.weight", True), ("decoder.proj_in.b", "pixel_decoder.proj_in.bias", False),
+                            ("decoder.proj_out.w", "pixel_decoder.proj_out.weight", True), ("decoder.proj_out.b", "pixel_decoder.proj_out.bias", False),
+                            ("decoder.norm_w", "pixel_decoder.norm.weight", False), ("decoder.norm_b", "pixel_decoder.norm.bias", False)):
+        errs[ours] = _check(tr, ours, g(key).flatten(1) if flat else g(key), g32(key).flatten(1) if flat else g32(key))
+    _summary(geo, "rec")
 
 
 @pytest.mark.parametrize("geo", GEO_PARAMS)
@@ -142,32 +164,36 @@ def test_clip_objective_gradients(geo):
     B = 6 if geo == "tiny" else 4
     x = seeded_images(B, c.img, c.img)
     ids = seeded_captions(B, 77, c.vocab)
-    p = _leafs(c.sd)
-    fi = vo.clip_image_feature(x, p, depth=2, heads=c.heads, mode="bf16")
-    ft = vo.text_feature(ids, p, layers=2, heads=c.theads, mode="bf16")
-    loss = vo.clip_loss(vo._r(fi, "bf16"), vo._r(ft, "bf16"), p["logit_scale"].exp())
-    loss.backward()
+    def oracle(mode):
+        q = _leafs(c.sd)
+        fi = vo.clip_image_feature(x, q, depth=2, heads=c.heads, mode=mode)
+        ft = vo.text_feature(ids, q, layers=2, heads=c.theads, mode=mode)
+        l = vo.clip_loss(vo._r(fi, mode), vo._r(ft, mode), q["logit_scale"].exp())
+        l.backward()
+        return q, l
+
+    p, loss = oracle("bf16")
+    p32, _ = oracle("fp32")
     tr.clip_fwd_bwd(x.cuda(), ids.cuda(), 1.0)
     torch.cuda.synchronize()
     assert abs(tr.loss_acc[0].item() - loss.item()) < TOL_L * abs(loss.item()), (tr.loss_acc[0].item(), loss.item())
-    errs = _vit_checks(tr, p, "trunk.", "trunk.", [0, 1], False)
-    errs["visual_proj"] = _check(tr, "visual_proj.w", p["visual_proj.weight"].grad)
-    errs["patch.w"] = _check(tr, "trunk.patch.w", p["trunk.patch_embed.proj.weight"].grad.flatten(1))
-    errs["cls"] = _check(tr, "trunk.cls", p["trunk.cls_token"].grad)
-    errs["logit_scale"] = _check(tr, "logit_scale", p["logit_scale"].grad)
-    errs["text.proj"] = _check(tr, "text.proj.w", p["text_projection"].grad.t())
-    errs["text.tok_emb"] = _check(tr, "text.tok_emb", p["token_embedding.weight"].grad)
-    errs["text.pos"] = _check(tr, "text.pos", p["positional_embedding"].grad)
-    errs["text.norm_w"] = _check(tr, "text.norm_w", p["ln_final.weight"].grad)
+    FLOORS.clear()
+    g, g32 = (lambda k: p[k].grad), (lambda k: p32[k].grad)
+    errs = _vit_checks(tr, p, "trunk.", "trunk.", [0, 1], False, p32)
+    errs["visual_proj"] = _check(tr, "visual_proj.w", g("visual_proj.weight"), g32("visual_proj.weight"))
+    errs["patch.w"] = _check(tr, "trunk.patch.w", g("trunk.patch_embed.proj.weight").flatten(1), g32("trunk.patch_embed.proj.weight").flatten(1))
+    errs["cls"] = _check(tr, "trunk.cls", g("trunk.cls_token"), g32("trunk.cls_token"))
+    errs["logit_scale"] = _check(tr, "logit_scale", g("logit_scale"), g32("logit_scale"))
+    errs["text.proj"] = _check(tr, "text.proj.w", g("text_projection").t(), g32("text_projection").t())
+    errs["text.tok_emb"] = _check(tr, "text.tok_emb", g("token_embedding.weight"), g32("token_embedding.weight"))
+    errs["text.pos"] = _check(tr, "text.pos", g("positional_embedding"), g32("positional_embedding"))
+    errs["text.norm_w"] = _check(tr, "text.norm_w", g("ln_final.weight"), g32("ln_final.weight"))
     for i in (0, 1):
         r, q = f"text_transformer.resblocks.{i}.", f"text.blocks.{i}."
-        errs[q + "qkv.w"] = _check(tr, q + "qkv.w", p[r + "attn.in_proj_weight"].grad)
-        errs[q + "qkv.b"] = _check(tr, q + "qkv.b", p[r + "attn.in_proj_bias"].grad)
-        errs[q + "proj.w"] = _check(tr, q + "proj.w", p[r + "attn.out_proj.weight"].grad)
-        errs[q + "fc1.w"] = _check(tr, q + "fc1.w", p[r + "mlp.c_fc.weight"].grad)
-        errs[q + "fc2.w"] = _check(tr, q + "fc2.w", p[r + "mlp.c_proj.weight"].grad)
-        errs[q + "n1_b"] = _check(tr, q + "n1_b", p[r + "ln_1.bias"].grad)
-    print(f"[{geo}] clip grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
+        for ours, key in (("qkv.w", "attn.in_proj_weight"), ("qkv.b", "attn.in_proj_bias"), ("proj.w", "attn.out_proj.weight"),
+                          ("fc1.w", "mlp.c_fc.weight"), ("fc2.w", "mlp.c_proj.weight"), ("n1_b", "ln_1.bias")):
+            errs[q + ours] = _check(tr, q + ours, g(r + key), g32(r + key))
+    _summary(geo, "clip")
 
 
 @pytest.mark.parametrize("geo", GEO_PARAMS)
@@ -211,6 +237,7 @@ def test_ssl_objective_gradients(geo):
     got = tr.loss_acc[1:4].cpu()
     for j, k in enumerate(("dino_local", "dino_global", "ibot")):
         assert abs(got[j].item() - terms[k].item()) < 3e-2 * abs(terms[k].item()), (k, got[j].item(), terms[k].item())
+    FLOORS.clear()                  # flat 6 % bound here (measured max 1.0 / 1.5 / 2.1 % at tiny / small2 / large2)
     errs = _vit_checks(tr, p, "trunk.", "trunk.", [0, 1], False)
     errs["patch.w"] = _check(tr, "trunk.patch.w", p["trunk.patch_embed.proj.weight"].grad.flatten(1))
     errs["cls"] = _check(tr, "trunk.cls", p["trunk.cls_token"].grad)
@@ -221,7 +248,7 @@ def test_ssl_objective_gradients(geo):
         errs[f"head.mlp{j}.b"] = _check(tr, f"head.mlp{j}.b", hp[f"mlp.{j}.bias"].grad)
     errs["head.last_v"] = _check(tr, "head.last_v", hp["last_layer.weight_v"].grad)
     errs["head.last_g"] = _check(tr, "head.last_g", hp["last_layer.weight_g"].grad)
-    print(f"[{geo}] ssl grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
+    _summary(geo, "ssl")
 
 
 def test_full_step_runs_and_learns():
@@ -356,3 +383,81 @@ def test_device_schedules_drive_the_optimizer():
     t0 = tr.store.tp.clone()
     tr.replay_step()
     assert torch.equal(t0, tr.store.tp)
+
+
+def test_stochastic_depth_forward_matches_reference_golden():
+    """a8: batch-subset stochastic depth (layers/block.py:201-298) on the kernels vs the REAL reference's training branch
+    with the same preset subsets (tests/golden/tiny_drop.npz, oracle/make_golden_drop.py), bf16 mode vs the fp32 reference."""
+    import os
+
+    import numpy as np
+
+    from vtp_b200 import engine as E
+
+    c = _setup("tiny")
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_drop.npz")).items()}
+    x = seeded_images(3, 64, 64)
+    W = c.tr.towers[("trunk", "param")]
+    plan = E.DropPlan(float(g["ratio"][0]), preset=[p for p in g["presets"]])
+    xo, meta = E.trunk_forward(W, x.cuda(), "bf16", drop=plan)
+    out = E.trunk_outputs(W, xo, meta, "bf16", use_bottleneck=True)
+    assert plan.calls == 4
+    # bf16 kernels vs fp32 reference: the usual bf16-mode distance of this geometry (2e-2 bound, see DESIGN §5)
+    assert rel(out["x_norm_patchtokens"].float(), g["patch"]) < 2e-2
+    # and it is NOT the plain path: without the subsets the outputs differ by far more than bf16 noise
+    xo0, meta0 = E.trunk_forward(W, x.cuda(), "bf16")
+    out0 = E.trunk_outputs(W, xo0, meta0, "bf16", use_bottleneck=True)
+    assert rel(out0["x_norm_patchtokens"].float(), g["patch"]) > 0.1
+
+
+def test_stochastic_depth_gradients_match_oracle():
+    """Reconstruction objective with rec_drop_rate > 0 and preset subsets: loss and every trunk / decoder gradient vs autograd
+    through the oracle's restatement of the reference's index / index_add branch."""
+    c = _setup("tiny")
+    tr = c.tr
+    B = 4
+    x = seeded_images(B, c.img, c.img)
+    ratio = 0.5
+    keep = max(int(B * (1 - ratio)), 1)
+    gen = torch.Generator().manual_seed(77)
+    presets = [torch.randperm(B, generator=gen)[:keep] for _ in range(4)]
+    sc = B / keep
+    p = _leafs(c.sd)
+    drops = [[(presets[0], sc, presets[1], sc), (presets[2], sc, presets[3], sc)]]
+    o = vo.trunk_forward([x], [None], p, depth=2, heads=c.heads, mode="bf16", drops=drops)[0]
+    pt = o["x_norm_patchtokens"]
+    lat = pt.transpose(1, 2).reshape(B, pt.shape[-1], c.img // 16, c.img // 16)
+    rec = vo.decode_latents(lat, p, depth=2, heads=c.dheads, mode="bf16")
+    loss = vo.recon_loss(rec, x, None)
+    loss.backward()
+    tr.tc.rec_drop_rate = ratio
+    tr.drop_presets = [presets]
+    out = tr.rec_fwd_bwd(x.cuda(), 1.0, return_image=True)
+    torch.cuda.synchronize()
+    assert rel(out, rec.detach()) < 2e-2
+    assert abs(tr.loss_acc[4].item() - loss.item()) < TOL_L * loss.item()
+    errs = _vit_checks(tr, p, "trunk.", "trunk.", [0, 1], False)
+    errs.update(_vit_checks(tr, p, "pixel_decoder.", "decoder.", [0, 1], True))
+    errs["patch.w"] = _check(tr, "trunk.patch.w", p["trunk.patch_embed.proj.weight"].grad.flatten(1))
+    errs["cls"] = _check(tr, "trunk.cls", p["trunk.cls_token"].grad)
+    errs["bneck"] = _check(tr, "trunk.bneck.w", p["trunk.feature_bottleneck.weight"].grad)
+    print("stochastic-depth rec grad rel errors: max", max(errs.values()), {k: f"{v:.1e}" for k, v in errs.items()})
+
+
+def test_stochastic_depth_full_step_random_subsets():
+    """All three objectives with drop rates > 0 and the random (torch.randperm, device-side) subsets: the step runs, learns,
+    and is graph-capturable (the permutation is drawn inside the graph by the graph-safe CUDA generator)."""
+    c = _setup("tiny")
+    tr = c.tr
+    tr.tc.clip_drop_rate = tr.tc.ssl_drop_rate = tr.tc.rec_drop_rate = 0.25
+    tr.hyper[3] = 2e-4
+    batch = _tiny_batch()
+    l0 = tr.train_step(batch).cpu().clone()
+    for _ in range(4):
+        l1 = tr.train_step(batch).cpu().clone()
+    assert torch.isfinite(l0).all() and torch.isfinite(l1).all() and l1[4] < l0[4]
+    tr.capture_step(batch, warmup=1)
+    a = tr.replay_step().cpu().clone()
+    b = tr.replay_step().cpu().clone()
+    assert torch.isfinite(a).all() and torch.isfinite(b).all()
+    assert not torch.equal(a, b)          # different subsets (and parameters) every replay

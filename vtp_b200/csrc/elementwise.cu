@@ -222,6 +222,41 @@ __global__ void gather_rows_kernel(const TI* __restrict__ in, TO* __restrict__ o
 }
 
 
+// ------------------------------------------------------------------------------------------------ batch-subset stochastic depth
+// layers/block.py:201-233: a sub-layer runs on a random subset of the images only — `x[indices]` on the way in and
+// `torch.index_add(x, 0, residual, indices, alpha = b / keep)` on the way out.  Image-granular (T token rows per index),
+// 16-byte accesses; the indices of one call are distinct (a permutation prefix), so the add needs no atomics.
+__global__ void gather_images_kernel(const float* __restrict__ x, float* __restrict__ out, const long long* __restrict__ idx,
+                                     int n_img, int T, int D4, float alpha) {
+    const long per = (long)T * D4, total = (long)n_img * per;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long i = t / per, r = t - i * per;
+        float4 v = reinterpret_cast<const float4*>(x)[idx[i] * per + r];
+        v.x *= alpha, v.y *= alpha, v.z *= alpha, v.w *= alpha;
+        reinterpret_cast<float4*>(out)[t] = v;
+    }
+}
+template <typename TS>
+__global__ void scatter_add_images_kernel(const TS* __restrict__ src, float* __restrict__ dst, const long long* __restrict__ idx,
+                                          int n_img, int T, int D4, float alpha) {
+    const long per = (long)T * D4, total = (long)n_img * per;
+    for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+        const long i = t / per, r = t - i * per;
+        float s4[4];
+        if constexpr (sizeof(TS) == 4) {
+            const float4 v = reinterpret_cast<const float4*>(src)[t];
+            s4[0] = v.x, s4[1] = v.y, s4[2] = v.z, s4[3] = v.w;
+        } else {
+            const uint2 v = reinterpret_cast<const uint2*>(src)[t];
+            s4[0] = bf16_lo(v.x), s4[1] = bf16_hi(v.x), s4[2] = bf16_lo(v.y), s4[3] = bf16_hi(v.y);
+        }
+        float4* d = reinterpret_cast<float4*>(dst) + idx[i] * per + r;
+        float4 o = *d;
+        o.x = fmaf(alpha, s4[0], o.x), o.y = fmaf(alpha, s4[1], o.y), o.z = fmaf(alpha, s4[2], o.z), o.w = fmaf(alpha, s4[3], o.w);
+        *d = o;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ text embedding
 // out[b*L + l][:] = emb[ids[b][l]][:] + pos[l][:]   (vtp_hf/modeling_vtp.py:297-298)
 __global__ void embed_tokens_kernel(const long long* __restrict__ ids, const float* __restrict__ emb,
@@ -380,6 +415,32 @@ extern "C" int vtp_gather_rows(const void* in, int in_dtype, long ld_in, void* o
     else
         gather_rows_kernel<__nv_bfloat16, __nv_bfloat16>
             <<<g, 256, 0, s>>>((const __nv_bfloat16*)in, (__nv_bfloat16*)out, ix, n, D, ld_in, ld_out);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_gather_images(const float* x, float* out, const int64_t* img_idx, int n_img, int T, int D, float alpha,
+                                 vtp_stream_t st) {
+    VTP_CHECK_ARG(x && out && (img_idx || n_img == 0) && T > 0 && D > 0 && D % 4 == 0, "gather_images: bad args (D %% 4 == 0)");
+    if (n_img == 0) return VTP_OK;
+    gather_images_kernel<<<grid_for((long)n_img * T * (D / 4), 256), 256, 0, (cudaStream_t)st>>>(
+        x, out, (const long long*)img_idx, n_img, T, D / 4, alpha);
+    VTP_LAUNCH_CHECK();
+    return VTP_OK;
+}
+
+extern "C" int vtp_scatter_add_images(const void* src, int src_dtype, float* dst, const int64_t* img_idx, int n_img, int T,
+                                      int D, float alpha, vtp_stream_t st) {
+    VTP_CHECK_ARG(src && dst && (img_idx || n_img == 0) && T > 0 && D > 0 && D % 4 == 0, "scatter_add_images: bad args");
+    VTP_CHECK_ARG(src_dtype == VTP_F32 || src_dtype == VTP_BF16, "scatter_add_images: bad src dtype");
+    if (n_img == 0) return VTP_OK;
+    const int g = grid_for((long)n_img * T * (D / 4), 256);
+    if (src_dtype == VTP_F32)
+        scatter_add_images_kernel<float><<<g, 256, 0, (cudaStream_t)st>>>((const float*)src, dst, (const long long*)img_idx, n_img,
+                                                                       T, D / 4, alpha);
+    else
+        scatter_add_images_kernel<__nv_bfloat16><<<g, 256, 0, (cudaStream_t)st>>>(
+            (const __nv_bfloat16*)src, dst, (const long long*)img_idx, n_img, T, D / 4, alpha);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

@@ -227,8 +227,96 @@ def norm(x, M, D, w, b, eps, mode, *, want: str, tape=None):
     return y
 
 
+class DropPlan:
+    """Batch-subset stochastic depth for one tower pass (layers/block.py:20-118 `get_branges_scales`, :201-298): every
+    sub-layer (attention, FFN) of every block runs on a fresh random subset of the images and its output is added back
+    scaled by residual_scale_factor.
+
+      single process:  keep = max(int(b (1 - ratio)), 1),  scale = b / keep                     (block.py:33-38)
+      data parallel:   global_keep = max(int(b W (1 - ratio)), W) dealt out evenly over the W ranks (the first
+                       global_keep % W ranks get one more, capped at b), scale = b W / Σ allocation  (block.py:40-67)
+    The reference has rank 0 compute that allocation and broadcast it (block.py:94); it is a pure function of
+    (b, ratio, W), so every rank derives it locally here — no collective.  The subset itself is
+    `torch.randperm(b, device)[:keep]` like the reference (device-side, graph-capturable).  `preset` (a sequence of index
+    tensors) replaces the random draws — used by the parity tests."""
+
+    def __init__(self, ratio: float, world: int = 1, rank: int = 0, preset: Optional[Sequence[torch.Tensor]] = None):
+        self.ratio, self.world, self.rank = float(ratio), int(world), int(rank)
+        self.preset = list(preset) if preset is not None else None
+        self.calls = 0
+
+    def keep_and_scale(self, b: int) -> Tuple[int, float]:
+        if self.world <= 1:
+            keep = max(int(b * (1 - self.ratio)), 1)
+            return keep, b / keep
+        gb = b * self.world
+        global_keep = max(int(gb * (1 - self.ratio)), self.world)
+        base, extra = divmod(global_keep, self.world)
+        alloc = [min(base + (1 if i < extra else 0), b) for i in range(self.world)]
+        return alloc[self.rank], gb / max(sum(alloc), 1)
+
+    def next(self, b: int, dev) -> Tuple[torch.Tensor, float]:
+        keep, scale = self.keep_and_scale(b)
+        if self.preset is not None:
+            idx = self.preset[self.calls].to(dev, torch.long).contiguous()
+            assert idx.numel() == keep, f"preset subset {self.calls} has {idx.numel()} images, the plan keeps {keep}"
+        else:
+            idx = torch.randperm(b, device=dev)[:keep].contiguous()
+        self.calls += 1
+        return idx, scale
+
+
+def _block_drop(W: TowerW, bw: BlockW, x: torch.Tensor, B: int, T: int, rope, drop: DropPlan, t: Optional[dict]):
+    """One block of the fp32-stream trunk under batch-subset stochastic depth, bf16 (autocast) mode
+    (layers/block.py:201-233 / :238-289): gather the kept images, run the sub-layer on them, add the bf16 residual back
+    into a copy of the stream with alpha = residual_scale_factor."""
+    dev, D, H = x.device, W.D, W.heads
+    mode = "bf16"
+    # ---- attention sub-layer on subset 1
+    idx1, a1 = drop.next(B, dev)
+    n1 = idx1.numel()
+    M1 = n1 * T
+    xs1 = _e((M1, D), F32, dev)
+    lib.gather_images(x, xs1, idx1, T, D)
+    nt = {} if t is not None else None
+    h = norm(xs1, M1, D, bw.n1_w, bw.n1_b, W.eps, mode, want="op", tape=nt)
+    qkv = _e((M1, 3 * D), BF, dev)
+    linear(h, bw.qkv, qkv, M1, mode)
+    if rope is not None:
+        lib.rope_fwd(qkv, rope[0], rope[1], M1, T, W.prefix, D)
+    o = _e((M1, D), BF, dev)
+    lse = _e((n1, H, T), F32, dev) if t is not None else None
+    lib.attention_fwd(qkv, o, n1, T, H, prefix=W.prefix, lse=lse)
+    res1 = _e((M1, D), BF, dev)
+    linear(o, bw.proj, res1, M1, mode)
+    x_mid = x.clone()
+    lib.scatter_add_images(res1, x_mid, idx1, T, D, a1)
+    # ---- FFN sub-layer on subset 2 (drawn independently, block.py:219)
+    idx2, a2 = drop.next(B, dev)
+    n2 = idx2.numel()
+    M2 = n2 * T
+    xs2 = _e((M2, D), F32, dev)
+    lib.gather_images(x_mid, xs2, idx2, T, D)
+    nt2 = {} if t is not None else None
+    h2 = norm(xs2, M2, D, bw.n2_w, bw.n2_b, W.eps, mode, want="op", tape=nt2)
+    Hd = bw.hidden
+    pre = _e((M2, 2 * Hd), BF, dev)
+    linear(h2, bw.fc1, pre, M2, mode)
+    hid = _e((M2, Hd), BF, dev)
+    lib.swiglu_fwd(pre, hid, M2, Hd)
+    res2 = _e((M2, D), BF, dev)
+    linear(hid, bw.fc2, res2, M2, mode)
+    x_out = x_mid.clone()
+    lib.scatter_add_images(res2, x_out, idx2, T, D, a2)
+    if t is not None:
+        t.update(drop1=(idx1, a1, xs1), drop2=(idx2, a2, xs2), h1=h, n1=nt, qkv=qkv, o=o, lse=lse, h2=h2, n2=nt2, pre=pre,
+                 hid=hid)
+    return x_out
+
+
 def tower_blocks(W: TowerW, x: torch.Tensor, B: int, T: int, rope, mode: str, *, causal: bool = False,
-                 tape: Optional[list] = None, taps: Optional[Dict[int, torch.Tensor]] = None) -> torch.Tensor:
+                 tape: Optional[list] = None, taps: Optional[Dict[int, torch.Tensor]] = None,
+                 drop: Optional[DropPlan] = None) -> torch.Tensor:
     """The block loop (encoders/vision_transformer.py:228-233, decoders/pixel_decoder.py:147-148,
     encoders/text_transformer.py:100-104): x [B*T, D] residual stream (fp32, or bf16 for the autocast decoder).
     Inference updates x in place; with a tape every sub-layer writes a fresh stream buffer and saves what backward
@@ -236,6 +324,18 @@ def tower_blocks(W: TowerW, x: torch.Tensor, B: int, T: int, rope, mode: str, *,
     dev = x.device
     M, D, H = B * T, W.D, W.heads
     act = BF if mode == "bf16" else F32
+    if drop is not None and drop.ratio > 0.0:
+        if mode != "bf16" or W.stream_bf16 or W.ffn != "swiglu" or causal:
+            raise NotImplementedError("batch-subset stochastic depth is implemented for the vision trunk in bf16 mode "
+                                      "(the only tower the reference applies drop_ratio to: vtp.py:275-293,452-463,487-500)")
+        for li, bw in enumerate(W.blocks):
+            t = {} if tape is not None else None
+            x = _block_drop(W, bw, x, B, T, rope, drop, t)
+            if tape is not None:
+                tape.append(t)
+            if taps is not None and li in taps:
+                taps[li] = x.clone()
+        return x
     for li, bw in enumerate(W.blocks):
         t = {} if tape is not None else None
         # ---- attention sub-layer: x + proj(attn(rope(qkv(norm1 x))))      layers/block.py:293, attention.py:91-126
@@ -314,14 +414,14 @@ def trunk_tokens(W: TowerW, img: torch.Tensor, mode: str, mask_idx: Optional[tor
 
 
 def trunk_forward(W: TowerW, img: torch.Tensor, mode: str, *, mask_idx=None, tape: Optional[dict] = None,
-                  taps=None):
+                  taps=None, drop: Optional[DropPlan] = None):
     """encoders/vision_transformer.py:221-258 for one resolution group.  Returns (x_prenorm [B*T,D] fp32, meta)."""
     x, (B, T, gh, gw), a = trunk_tokens(W, img, mode, mask_idx)
     if tape is not None:
         tape["patch_a"] = a
     rope = W.rope(gh, gw, img.device)
     blk_tape = [] if tape is not None else None
-    x = tower_blocks(W, x, B, T, rope, mode, tape=blk_tape, taps=taps)
+    x = tower_blocks(W, x, B, T, rope, mode, tape=blk_tape, taps=taps, drop=drop)
     if tape is not None:
         tape["blocks"] = blk_tape
         tape["meta"] = (B, T, gh, gw)

@@ -60,6 +60,9 @@ SIGNATURES: dict[str, tuple] = {
                                         C.c_int, C.c_void_p]),
     "vtp_gather_rows": (C.c_int, [C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int, C.c_long, C.c_void_p, C.c_int,
                                   C.c_int, C.c_void_p]),
+    "vtp_gather_images": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p]),
+    "vtp_scatter_add_images": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float,
+                                         C.c_void_p]),
     "vtp_swiglu_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p]),
     "vtp_rope_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "vtp_embed_tokens": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_int, C.c_void_p]),
@@ -245,6 +248,18 @@ def gather_rows(inp, out, idx, D: int, *, ld_in: int | None = None, ld_out: int 
     check(load().vtp_gather_rows(_ptr(inp), _dt(inp), ld_in if ld_in is not None else D, _ptr(out), _dt(out),
                                  ld_out if ld_out is not None else D, _ptr(idx), idx.numel(), D, _st(stream)),
           "vtp_gather_rows")
+
+
+def gather_images(x, out, img_idx, T: int, D: int, alpha: float = 1.0, stream=None):
+    """out[i*T + t] = alpha * x[img_idx[i]*T + t]  (fp32 -> fp32; layers/block.py:207 `x[indices]`)."""
+    check(load().vtp_gather_images(_ptr(x), _ptr(out), _ptr(img_idx), img_idx.numel(), T, D, alpha, _st(stream)),
+          "vtp_gather_images")
+
+
+def scatter_add_images(src, dst, img_idx, T: int, D: int, alpha: float = 1.0, stream=None):
+    """dst[img_idx[i]*T + t] += alpha * src[i*T + t]  (fp32 dst; layers/block.py:211-217 `torch.index_add(..., alpha)`)."""
+    check(load().vtp_scatter_add_images(_ptr(src), _dt(src), _ptr(dst), _ptr(img_idx), img_idx.numel(), T, D, alpha,
+                                        _st(stream)), "vtp_scatter_add_images")
 
 
 def _check_qkv(qkv, B: int, T: int, H: int):

@@ -145,8 +145,10 @@ def tower_blocks_backward(W: TowerW, G: TowerW, tape: list, g: torch.Tensor, B: 
     gradient) are by-products of the preceding norm_bwd; only the first sub-layer needs a stand-alone cast."""
     dev = g.device
     M, D, H = B * T, W.D, W.heads
-    gb = _e((M, D), BF, dev)
     nb = len(W.blocks)
+    if nb and "drop1" in tape[nb - 1]:
+        return _tower_blocks_backward_drop(W, G, tape, g, B, T, rope)
+    gb = _e((M, D), BF, dev)
     lib.cast_colsum(g, gb, G.blocks[nb - 1].fc2.b, M, D)
     for li in reversed(range(nb)):
         bw, gw, t = W.blocks[li], G.blocks[li], tape[li]
@@ -207,6 +209,57 @@ def grad_buckets(offset: Dict[str, int], n: int) -> Dict[str, List[Tuple[int, in
     return out
 
 
+def _tower_blocks_backward_drop(W: TowerW, G: TowerW, tape: list, g: torch.Tensor, B: int, T: int, rope):
+    """Reverse of engine._block_drop (batch-subset stochastic depth, layers/block.py:201-233).  The residual stream
+    gradient g passes every block unchanged (identity path); each sub-layer adds, for its kept images only, the gradient
+    that flows through  alpha * sublayer(norm(x[idx])) :  d(residual) = alpha * g[idx]  goes down the sub-layer, what
+    comes out of its norm backward is scatter-added into g[idx]."""
+    dev, D, H = g.device, W.D, W.heads
+    for li in reversed(range(len(W.blocks))):
+        bw, gw, t = W.blocks[li], G.blocks[li], tape[li]
+        Hd = bw.hidden
+        # ---- FFN sub-layer
+        idx2, a2, xs2 = t["drop2"]
+        M2 = idx2.numel() * T
+        gs = _e((M2, D), F32, dev)
+        lib.gather_images(g, gs, idx2, T, D, a2)
+        gb = _e((M2, D), BF, dev)
+        lib.cast_colsum(gs, gb, gw.fc2.b, M2, D)
+        dhid = _e((M2, Hd), BF, dev)
+        dgrad(gb, bw.fc2.w, dhid, M2)
+        wgrad(gb, t["hid"], gw.fc2.w, M2)
+        dpre = torch.empty_like(t["pre"])
+        lib.swiglu_bwd(t["pre"], dhid, dpre, gw.fc1.b, M2, Hd)
+        dh = _e((M2, D), BF, dev)
+        dgrad(dpre, bw.fc1.w, dh, M2)
+        wgrad(dpre, t["h2"], gw.fc1.w, M2)
+        gsub = gs.zero_()
+        lib.norm_bwd(xs2, t["n2"]["rstd"], t["n2"]["mean"], bw.n2_w, dh, gsub, gw.n2_w, gw.n2_b, M2, D)
+        lib.scatter_add_images(gsub, g, idx2, T, D, 1.0)
+        # ---- attention sub-layer
+        idx1, a1, xs1 = t["drop1"]
+        n1 = idx1.numel()
+        M1 = n1 * T
+        gs = _e((M1, D), F32, dev)
+        lib.gather_images(g, gs, idx1, T, D, a1)
+        gb = _e((M1, D), BF, dev)
+        lib.cast_colsum(gs, gb, gw.proj.b, M1, D)
+        do = _e((M1, D), BF, dev)
+        dgrad(gb, bw.proj.w, do, M1)
+        wgrad(gb, t["o"], gw.proj.w, M1)
+        dqkv = _e((M1, 3 * D), BF, dev)
+        lib.attention_bwd(t["qkv"], t["o"], do, t["lse"], dqkv, n1, T, H, prefix=W.prefix, rope=rope)
+        lib.cast_colsum(dqkv, None, gw.qkv.b, M1, 3 * D)
+        dh = _e((M1, D), BF, dev)
+        dgrad(dqkv, bw.qkv.w, dh, M1)
+        wgrad(dqkv, t["h1"], gw.qkv.w, M1)
+        gsub = gs.zero_()
+        lib.norm_bwd(xs1, t["n1"]["rstd"], t["n1"]["mean"], bw.n1_w, dh, gsub, gw.n1_w, gw.n1_b, M1, D)
+        lib.scatter_add_images(gsub, g, idx1, T, D, 1.0)
+        tape[li] = None
+    return g
+
+
 # ------------------------------------------------------------------------------------------------------ trainer
 @dataclass
 class TrainConfig:
@@ -236,6 +289,11 @@ class TrainConfig:
     # 0 = the whole per-GPU batch at once.
     ssl_chunk: int = 0
     rec_chunk: int = 0
+    # batch-subset stochastic depth of the student trunk per objective (vtp.py:275-293 clip_drop_rate, :452-463
+    # ssl_drop_rate, :487-500 rec_drop_rate; layers/block.py:20-118,201-298); 0 = the plain residual path
+    clip_drop_rate: float = 0.0
+    ssl_drop_rate: float = 0.0
+    rec_drop_rate: float = 0.0
 
 
 class VTPTrainer:
@@ -485,8 +543,16 @@ class VTPTrainer:
         return out
 
     # -------------------------------------------------------------- pieces shared by the objectives
-    def _trunk_fwd(self, W: TowerW, img, tape: Optional[dict], mask_idx=None):
-        x, meta = E.trunk_forward(W, img, "bf16", mask_idx=mask_idx, tape=tape)
+    def _drop(self, ratio: float):
+        """DropPlan of one student trunk pass (None when the objective's drop rate is 0); `drop_presets` (tests) supplies
+        fixed subsets instead of random permutations."""
+        if ratio <= 0.0:
+            return None
+        preset = self.drop_presets.pop(0) if getattr(self, "drop_presets", None) else None
+        return E.DropPlan(ratio, self.world, self.rank, preset=preset)
+
+    def _trunk_fwd(self, W: TowerW, img, tape: Optional[dict], mask_idx=None, drop=None):
+        x, meta = E.trunk_forward(W, img, "bf16", mask_idx=mask_idx, tape=tape, drop=drop)
         return x, meta
 
     def _trunk_bwd(self, tape: dict, g: torch.Tensor, mask_idx=None):
@@ -517,7 +583,7 @@ class VTPTrainer:
         D, Dt = self.D, self.Dt
         # ---- image tower -> cls -> visual_proj -> normalise
         tp_i = {}
-        x, (B, T, gh, gw) = self._trunk_fwd(W, image, tp_i)
+        x, (B, T, gh, gw) = self._trunk_fwd(W, image, tp_i, drop=self._drop(self.tc.clip_drop_rate))
         M = B * T
         nt = {}
         xn = E.norm(x, M, D, W.norm_w, None, W.eps, "bf16", want="f32", tape=nt)
@@ -675,7 +741,7 @@ class VTPTrainer:
         Wd, Gd = self.towers[("decoder", "param")], self.towers[("decoder", "grad")]
         D, Dd, bn = self.D, self.Dd, self.bn
         tp_e = {}
-        x, (B, T, gh, gw) = self._trunk_fwd(W, image, tp_e)
+        x, (B, T, gh, gw) = self._trunk_fwd(W, image, tp_e, drop=self._drop(self.tc.rec_drop_rate))
         M, HW = B * T, gh * gw
         Md = B * HW
         nB = norm_B if norm_B is not None else B
@@ -881,8 +947,8 @@ class VTPTrainer:
         del xt, xnt
         # ---------------- student: get_student_ssl_outputs vtp.py:452-484
         tp_g, tp_l = {}, {}
-        xg, _ = self._trunk_fwd(W, global_crops, tp_g, mask_idx=mask_indices)
-        xl, (Bl, Tl, ghl, gwl) = self._trunk_fwd(W, local_crops, tp_l)
+        xg, _ = self._trunk_fwd(W, global_crops, tp_g, mask_idx=mask_indices, drop=self._drop(tc.ssl_drop_rate))
+        xl, (Bl, Tl, ghl, gwl) = self._trunk_fwd(W, local_crops, tp_l, drop=self._drop(tc.ssl_drop_rate))
         ntg, ntl = {}, {}
         xng = E.norm(xg, B2 * T, D, W.norm_w, None, W.eps, "bf16", want="f32", tape=ntg)
         xnl = E.norm(xl, Bl * Tl, D, W.norm_w, None, W.eps, "bf16", want="f32", tape=ntl)
