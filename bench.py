@@ -223,7 +223,7 @@ def main():
                "config": conf,
                "cpu_baseline": cb,
                "e2e": {"value": cb["value"], "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
         return
 
     import torch
@@ -354,9 +354,20 @@ def main():
     except Exception:
         pass
 
-    if rank != 0:
+    def shutdown():
+        """Release the step graph BEFORE the NCCL communicator (NCCL cannot destroy a communicator whose collectives live in a
+        CUDA graph: the first 2-GPU graph run of round 2 hung right here), with a hard-exit watchdog behind it — the JSON
+        line is already flushed at that point."""
         if world > 1:
+            t = threading.Timer(30.0, lambda: os._exit(0))
+            t.daemon = True
+            t.start()
+            tr.release_graph()
             dist.destroy_process_group()
+            t.cancel()
+
+    if rank != 0:
+        shutdown()
         return
     peaks = {}
     try:
@@ -407,9 +418,8 @@ def main():
                 out["extra_configs"] = json.load(f)
         except Exception:
             pass
-    print(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    print(json.dumps(out), flush=True)
+    shutdown()
 
 
 if __name__ == "__main__":

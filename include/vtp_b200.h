@@ -255,6 +255,16 @@ int vtp_image_to_u8(const void* img, int img_dtype, const float* sub3, const flo
  * over latents [B][C][HW] (fp32|bf16) */
 int vtp_latent_stats(const void* lat, int dtype, int B, int C, int HW, double* sum, double* sumsq, vtp_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Input side of the training step (vtp_b200/csrc/data.cu; SURVEY.md §8f rank 4 — the reference releases no training
+ * data loader, README.md:245 points at DINOv2 / OpenCLIP): every crop of the step in one pass.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* out[n] (fp32 NCHW [N][3][S][S]) = normalise(bilinear_resize(crop(src[src_idx[n]], boxes[n] = x0,y0,w,h), S x S, half-pixel
+ * centres), optional horizontal flip); src uint8 NHWC [B][H][W][3]; mean3 / std3 are HOST pointers (3 floats each). */
+int vtp_crop_resize_norm(const uint8_t* src_nhwc, int B, int H, int W, const int* src_idx, const float* boxes_xywh,
+                         const uint8_t* flips, float* out_nchw, int N, int S, const float* mean3, const float* std3,
+                         vtp_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -149,6 +149,7 @@ def _graph_worker(rank, world, port, out):
                 loss = tr.replay_step()
         torch.cuda.synchronize()
         res[mode] = (tr.store.p.clone(), loss.clone())
+        tr.release_graph()       # a live graph that captured NCCL collectives blocks destroy_process_group()
     p_e, p_g = res["eager"][0], res["graph"][0]
     p0 = p_g.clone()
     dist.broadcast(p0, src=0)

@@ -117,6 +117,8 @@ SIGNATURES: dict[str, tuple] = {
     "vtp_comm_get_handle": (C.c_int, [C.c_void_p, C.c_char_p]),
     "vtp_comm_open_handle": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
     "vtp_comm_close_handle": (C.c_int, [C.c_void_p]),
+    "vtp_crop_resize_norm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_void_p]),
     "vtp_comm_barrier": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_long, C.c_void_p, C.c_void_p, C.c_void_p]),
 }
 
@@ -478,3 +480,15 @@ def latent_stats(lat, sum64, sumsq64, stream=None):
     HW = lat.numel() // (B * Cc)
     check(load().vtp_latent_stats(_ptr(lat), _dt(lat), B, Cc, HW, _ptr(sum64), _ptr(sumsq64), _st(stream)),
           "vtp_latent_stats")
+
+
+# ------------------------------------------------------------------------------------------------ training input side
+def crop_resize_norm(src_u8, src_idx, boxes, flips, out, mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225), stream=None):
+    """src_u8 uint8 NHWC [B,H,W,3]; src_idx int32 [N]; boxes fp32 [N,4] (x0,y0,w,h); flips uint8 [N] | None;
+    out fp32 NCHW [N,3,S,S] = normalised bilinear crops."""
+    B, H, W, _ = src_u8.shape
+    N, _, S, _ = out.shape
+    m = (C.c_float * 3)(*mean)
+    sd = (C.c_float * 3)(*std)
+    check(load().vtp_crop_resize_norm(_ptr(src_u8), B, H, W, _ptr(src_idx), _ptr(boxes), _ptr(flips), _ptr(out), N, S, m, sd,
+                                      _st(stream)), "vtp_crop_resize_norm")

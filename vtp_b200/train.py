@@ -1097,6 +1097,19 @@ class VTPTrainer:
         lib.LAUNCHES += self.graph_launches
         return self.loss_acc
 
+    def release_graph(self):
+        """Destroy the captured step graph and its static inputs.  REQUIRED before `dist.destroy_process_group()` in a
+        multi-rank job: NCCL does not tear a communicator down while a CUDA graph that captured its collectives is alive
+        (the 2-GPU run of round 2 hung in destroy_process_group until the graph was released first)."""
+        if self._graph is not None:
+            torch.cuda.synchronize(self.device)
+            self._graph.reset()
+            self._graph = None
+            self._static = None
+            import gc
+            gc.collect()
+            torch.cuda.synchronize(self.device)
+
     @property
     def static_batch(self) -> Dict[str, torch.Tensor]:
         """The graph's input buffers (fill them directly — e.g. H2D copies on a side stream — and call replay_step())."""
