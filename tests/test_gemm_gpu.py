@@ -181,3 +181,39 @@ def test_gemm_fast_epilogue_modes(monkeypatch, variant, out_f32, resid, relu, M,
         # one bf16 ulp of slack where the fp32 accumulation order flips the rounding point
         assert (out.float() - ref.float()).abs().max().item() <= 2.0 ** -7 * ref.float().abs().max().item() + 1e-6
         assert _relerr(out, ref) < 2e-3
+
+
+@pytest.mark.parametrize("M,Hs,K,with_pre", [(300, 1024, 384, True), (300, 1024, 384, False), (4100, 2736, 1024, True),
+                                             (1000, 344, 128, True), (129, 64, 64, True), (2048, 2048, 768, False),
+                                             (515, 1368, 384, True)])
+def test_gemm_swiglu_fast_epilogue(monkeypatch, M, Hs, K, with_pre):
+    """SwiGLU gate in the lean TMA-store epilogue (fast_swiglu_tile, FAST 6 / 7): hidden = round(round(silu(x1)) * x2) and the
+    bf16 pre-activation, vs torch and vs the generic epilogue (VTP_GEMM_NO_FAST_SWIGLU=1) — bit-identical to the latter.
+    Shapes: 256- and 128-wide tiles, ragged N (2 * 2736 = 21.375 tiles; 2 * 344; 2 * 1368), M tails, one-tile problems."""
+    A = _mk((M, K), 41)
+    W1, W2 = _mk((Hs, K), 42, 0.05), _mk((Hs, K), 43, 0.05)
+    b1, b2 = torch.randn(Hs, device="cuda") * 0.1, torch.randn(Hs, device="cuda") * 0.1
+    Wp = torch.stack([W1.view(Hs // 8, 8, K), W2.view(Hs // 8, 8, K)], dim=1).reshape(2 * Hs, K).contiguous()
+    bp = torch.stack([b1.view(-1, 8), b2.view(-1, 8)], dim=1).reshape(-1).contiguous()
+    res = {}
+    for variant in ("fast", "generic"):
+        if variant == "generic":
+            monkeypatch.setenv("VTP_GEMM_NO_FAST_SWIGLU", "1")
+        else:
+            monkeypatch.delenv("VTP_GEMM_NO_FAST_SWIGLU", raising=False)
+        out = torch.full((M, Hs), float("nan"), device="cuda", dtype=torch.bfloat16)
+        pre = torch.full((M, 2 * Hs), float("nan"), device="cuda", dtype=torch.bfloat16) if with_pre else None
+        lib.gemm(A, Wp, out, M=M, N=2 * Hs, K=K, bias=bp, act=lib.ACT_SWIGLU8, ldo=Hs, out2=pre)
+        torch.cuda.synchronize()
+        res[variant] = (out, pre)
+    x1 = (A.float() @ W1.float().t() + b1).to(torch.bfloat16)
+    x2 = (A.float() @ W2.float().t() + b2).to(torch.bfloat16)
+    ref = (torch.nn.functional.silu(x1.float()).to(torch.bfloat16).float() * x2.float()).to(torch.bfloat16)
+    out, pre = res["fast"]
+    assert torch.isfinite(out.float()).all()
+    assert _relerr(out, ref) < 3e-3
+    assert torch.equal(out, res["generic"][0])
+    if with_pre:
+        pre_ref = torch.stack([x1.view(M, Hs // 8, 8), x2.view(M, Hs // 8, 8)], dim=2).reshape(M, 2 * Hs)
+        assert torch.isfinite(pre.float()).all()
+        assert _relerr(pre, pre_ref) < 3e-3 and torch.equal(pre, res["generic"][1])

@@ -368,6 +368,98 @@ __device__ __forceinline__ void arrive_tempty(uint64_t* bar) {
     else mbar_arrive(bar);
 }
 
+// ---- SwiGLU gate in the lean epilogue (FAST 6: hidden + pre-activation outputs, FAST 7: hidden only).
+// The stand-alone gate pass re-read the whole [M, 2Hs] pre-activation (539 MB per FFN forward at the bench shape, 6.6 ms of
+// the step); here the epilogue warp that owns two ADJACENT 64-column packed chunks (8-interleaved w1|w2: columns
+// [16g, 16g+8) = x1, [16g+8, 16g+16) = x2) stores them as the pre-activation through tmO2 and writes their 32 + 32 hidden
+// values  round(round(silu(x1)) * x2)  (layers/ffn.py:77-81 under autocast) into a second 32 x 128-byte staging tile that
+// leaves through ONE TMA store of the [M, Hs] hidden tensor (tmO).
+template <int BN, int FAST, bool G2>
+__device__ __forceinline__ void fast_swiglu_tile(const GemmDev& p, const CUtensorMap* tmO, const CUtensorMap* tmO2, uint8_t* stg,
+                                                 uint8_t* stg2, float* bias_s, int lane, int q, int hsel, uint32_t taddr,
+                                                 int m_blk, int n0, uint64_t* tfull, uint32_t aph, uint64_t* tempty) {
+    constexpr bool PRE = FAST == 6;
+    constexpr int TCH = BN / 64;             // packed 64-column chunks per tile row (BN in {128, 256})
+    const int m0 = m_blk * BM;
+    const int N = p.N;
+    const int c0 = 2 * hsel;                 // this warp's chunk pair (2 hsel, 2 hsel + 1) -> hidden columns [64 hsel, +64)
+    const bool have = c0 < TCH && n0 + c0 * 64 < N;
+    mbar_wait(tfull, aph);
+    tc_fence_after();
+    if (have) {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int col0 = n0 + (c0 + j) * 64;
+            const bool valid = col0 < N;     // warp-uniform (ragged last tile: N % 64 != 0 is clipped by the tensor maps)
+            uint32_t r0[32], r1[32];
+            if (valid) {
+                tmem_ld_32x32(taddr + (c0 + j) * 64, r0);
+                tmem_ld_32x32(taddr + (c0 + j) * 64 + 32, r1);
+            }
+            bias_s[lane] = (p.bias && col0 + lane < N) ? __ldg(p.bias + col0 + lane) : 0.f;
+            bias_s[32 + lane] = (p.bias && col0 + 32 + lane < N) ? __ldg(p.bias + col0 + 32 + lane) : 0.f;
+            if (lane == 0) bulk_wait_read0();   // earlier TMA stores of this warp have finished reading both staging tiles
+            __syncwarp();
+            if (valid) tmem_ld_wait();
+            if (j == 1) {                       // accumulator fully in registers: hand the TMEM buffer back
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) arrive_tempty<G2>(tempty);
+            }
+            uint32_t hw[16];                    // 32 hidden values of this chunk, packed
+            uint32_t xs[32];                    // the chunk's ROUNDED values regrouped: [0,16) = x1 pairs, [16,32) = x2 pairs
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {       // 8 pieces of 8 packed columns: even pieces = x1 of a group, odd = x2
+                const float4 ba = *reinterpret_cast<const float4*>(bias_s + 8 * i);
+                const float4 bb = *reinterpret_cast<const float4*>(bias_s + 8 * i + 4);
+                const uint32_t* r = i < 4 ? r0 + 8 * i : r1 + 8 * (i - 4);
+                float v[8] = {__uint_as_float(r[0]) + ba.x, __uint_as_float(r[1]) + ba.y, __uint_as_float(r[2]) + ba.z,
+                              __uint_as_float(r[3]) + ba.w, __uint_as_float(r[4]) + bb.x, __uint_as_float(r[5]) + bb.y,
+                              __uint_as_float(r[6]) + bb.z, __uint_as_float(r[7]) + bb.w};
+                if (!valid) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = 0.f;
+                }
+                uint4 w;
+                w.x = pack_bf16x2(v[0], v[1]), w.y = pack_bf16x2(v[2], v[3]);
+                w.z = pack_bf16x2(v[4], v[5]), w.w = pack_bf16x2(v[6], v[7]);
+                if (PRE) *reinterpret_cast<uint4*>(stg + stgb_off(lane, i)) = w;
+                // keep the ROUNDED values: the gate acts on the bf16 outputs of w1 / w2 (autocast)
+                xs[(i & 1) * 16 + (i >> 1) * 4 + 0] = w.x, xs[(i & 1) * 16 + (i >> 1) * 4 + 1] = w.y;
+                xs[(i & 1) * 16 + (i >> 1) * 4 + 2] = w.z, xs[(i & 1) * 16 + (i >> 1) * 4 + 3] = w.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const float a0 = bf16_lo(xs[k]), a1 = bf16_hi(xs[k]), b0 = bf16_lo(xs[16 + k]), b1 = bf16_hi(xs[16 + k]);
+                const float s0 = bf16_round(__fdividef(a0, 1.0f + __expf(-a0)));
+                const float s1 = bf16_round(__fdividef(a1, 1.0f + __expf(-a1)));
+                hw[k] = pack_bf16x2(s0 * b0, s1 * b1);
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)       // 32 hidden values = 64 bytes = chunks 4 j .. 4 j + 3 of the 128-byte hidden row
+                *reinterpret_cast<uint4*>(stg2 + stgb_off(lane, 4 * j + c)) = make_uint4(hw[4 * c], hw[4 * c + 1], hw[4 * c + 2], hw[4 * c + 3]);
+            if (PRE && valid && !(p.dbg & 1)) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(tmO2, stg, col0, m0 + q * 32);
+                    bulk_commit();
+                }
+            }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0 && !(p.dbg & 1)) {
+            tma_store_2d(tmO, stg2, (n0 >> 1) + 64 * hsel, m0 + q * 32);
+            bulk_commit();
+        }
+    } else {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_tempty<G2>(tempty);
+    }
+}
+
 template <int BN, int ACT, int FAST, bool G2>
 __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUtensorMap* tmO, uint8_t* stg, float* bias_s,
                                                    int lane, int q, int hsel, uint32_t taddr, int m_blk, int n0,
@@ -524,7 +616,7 @@ template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST, bo
 // MINB = 2 (short-K shapes): two CTAs per SM with a 2-stage ring double the epilogue warps per SM at ~100 registers.
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmO, const GemmDev p) {
+            const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmO2, const GemmDev p) {
     static_assert(!G2 || CL2, "cta_group::2 needs the 2-CTA cluster");
     constexpr int CLM = 2;                                      // CTAs per cluster (along M) sharing one B tile
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CLM) - 1u);  // every CTA of the cluster
@@ -539,10 +631,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint8_t* smem = FAST ? smem_raw
                          : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     if (FAST && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
+    constexpr int STG_BYTES = NUM_EPI_WARPS * STG_FLOATS * 4 * (FAST == 6 ? 2 : 1);  // FAST 6: + the hidden-tile staging
     float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // 8 epilogue warps x 4 KB
-    float* bias_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_FLOATS * 4);  // FAST only
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + NUM_EPI_WARPS * STG_FLOATS * 4 +
-                                                     (FAST ? NUM_EPI_WARPS * 256 : 0));
+    float* bias_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + STG_BYTES);  // FAST only
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STG_BYTES + (FAST ? NUM_EPI_WARPS * 256 : 0));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -558,6 +650,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tma_prefetch_desc(&tmA);
         tma_prefetch_desc(&tmB);
         if (FAST) tma_prefetch_desc(&tmO);
+        if (FAST == 6) tma_prefetch_desc(&tmO2);
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], (CL2 && !G2) ? CLM : 1);
         for (int s = 0; s < 2; ++s)
             mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], G2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
@@ -701,6 +794,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             const int m0 = m_blk * BM, n0 = n_blk * BN;
             const int grow0 = m0 + q * 32;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE;
+            if constexpr (FAST == 6 || FAST == 7) {
+                uint8_t* st1 = reinterpret_cast<uint8_t*>(stg);
+                // FAST 6: second tile behind the eight pre-activation tiles; FAST 7: the only tile holds the hidden values
+                uint8_t* st2 = FAST == 6 ? reinterpret_cast<uint8_t*>(stg_base) + (NUM_EPI_WARPS + (warp - 2)) * STG_FLOATS * 4 : st1;
+                fast_swiglu_tile<BN, FAST, G2>(p, &tmO, &tmO2, st1, st2, bias_base + (warp - 2) * 64, lane, q, hsel, taddr, m_blk,
+                                               n0, &tfull_bar[as], aph, &tempty_bar[as]);
+                if (++as == 2) as = 0, aph ^= 1;
+                continue;
+            }
             if constexpr (FAST != 0) {
                 fast_epilogue_tile<BN, ACT, FAST, G2>(p, &tmO, reinterpret_cast<uint8_t*>(stg), bias_base + (warp - 2) * 64, lane,
                                                   q, hsel, taddr, m_blk, n0, &tfull_bar[as], aph, &tempty_bar[as]);
@@ -767,8 +869,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
 template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0, bool G2 = false>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream,
-                       const CUtensorMap* tmO = nullptr) {
-    constexpr int smem_bytes = STAGES * (A_BYTES + (G2 ? BN / 2 : BN) * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 +
+                       const CUtensorMap* tmO = nullptr, const CUtensorMap* tmO2 = nullptr) {
+    constexpr int smem_bytes = STAGES * (A_BYTES + (G2 ? BN / 2 : BN) * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 * (FAST == 6 ? 2 : 1) +
                                (FAST ? NUM_EPI_WARPS * 256 + 256 : 1024 + 256);
     static bool configured = false;
     if (!configured) {
@@ -795,7 +897,8 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>, tmA, tmB, tmO ? *tmO : tmA, p));
+    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>, tmA, tmB, tmO ? *tmO : tmA,
+                                tmO2 ? *tmO2 : tmA, p));
     return VTP_OK;
 }
 
@@ -938,6 +1041,35 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     // (measured: proj+resid 237 -> 178 us, fc2+resid 244 -> 198 us at M = 131 584)
     const bool allow_2cta = getenv("VTP_GEMM_NO_2PERSM") == nullptr;
     const bool two = allow_2cta && BN == 128 && p.num_k_blocks <= two_max_kb && p.num_splits == 1;
+    // SwiGLU gate in the lean epilogue (fast_swiglu_tile): bf16 hidden output [M, N/2] (+ optional bf16 pre-activation [M, N])
+    const bool fast_swiglu = allow_fast && getenv("VTP_GEMM_NO_FAST_SWIGLU") == nullptr && a->act == VTP_ACT_SWIGLU8 && !conv &&
+                             !g2 && a->out_dtype == VTP_BF16 && a->round_bf16 && !a->resid && !a->mask_pos && !a->accumulate &&
+                             split_k == 1 && a->rr_group == 0 && a->ps_r == 0 && (BN == 256 || BN == 128) && a->ldo % 8 == 0;
+    if (fast_swiglu) {
+        CUtensorMap tmH, tmP;
+        {
+            uint64_t dims[2] = {(uint64_t)a->N / 2, (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldo * 2};
+            uint32_t box[2] = {64, 32};
+            int rc = make_tmap(&tmH, a->out, VTP_BF16, 2, dims, strides, box);
+            if (rc) return rc;
+        }
+        if (a->out2) {
+            uint64_t dims[2] = {(uint64_t)a->N, (uint64_t)a->M}, strides[1] = {(uint64_t)a->ldo2 * 2};
+            uint32_t box[2] = {64, 32};
+            int rc = make_tmap(&tmP, a->out2, VTP_BF16, 2, dims, strides, box);
+            if (rc) return rc;
+            if (cl2)
+                return (BN == 256) ? launch_gemm<256, 3, VTP_ACT_SWIGLU8, false, true, 1, 6>(tmA, tmB, p, stream, &tmH, &tmP)
+                                   : launch_gemm<128, 4, VTP_ACT_SWIGLU8, false, true, 1, 6>(tmA, tmB, p, stream, &tmH, &tmP);
+            return (BN == 256) ? launch_gemm<256, 3, VTP_ACT_SWIGLU8, false, false, 1, 6>(tmA, tmB, p, stream, &tmH, &tmP)
+                               : launch_gemm<128, 4, VTP_ACT_SWIGLU8, false, false, 1, 6>(tmA, tmB, p, stream, &tmH, &tmP);
+        }
+        if (cl2)
+            return (BN == 256) ? launch_gemm<256, 4, VTP_ACT_SWIGLU8, false, true, 1, 7>(tmA, tmB, p, stream, &tmH)
+                               : launch_gemm<128, 6, VTP_ACT_SWIGLU8, false, true, 1, 7>(tmA, tmB, p, stream, &tmH);
+        return (BN == 256) ? launch_gemm<256, 4, VTP_ACT_SWIGLU8, false, false, 1, 7>(tmA, tmB, p, stream, &tmH)
+                           : launch_gemm<128, 6, VTP_ACT_SWIGLU8, false, false, 1, 7>(tmA, tmB, p, stream, &tmH);
+    }
     if (fast) {
         CUtensorMap tmO;
         const int esz = a->out_dtype == VTP_F32 ? 4 : 2;

@@ -25,6 +25,11 @@ F32 = torch.float32
 # of inside the GEMM epilogue (measured faster at K = 384: see csrc/elementwise.cu).  The fused epilogues stay available
 # (fp32 mode uses them; set False to use them in bf16 mode too — identical numerics, tests cover both).
 SPLIT_EPILOGUES = True
+# SwiGLU gate: the lean TMA-store epilogue variant of round 2 (csrc/gemm.cu fast_swiglu_tile) writes the hidden tensor
+# (and, for training, the pre-activation) straight from the fc1 GEMM — no stand-alone gate pass re-reading [M, 2Hs].
+# VTP_FUSED_SWIGLU=0 restores the stand-alone swiglu_fwd kernel.
+import os as _os
+FUSED_SWIGLU = _os.environ.get("VTP_FUSED_SWIGLU", "1") != "0"
 
 
 def _e(shape, dtype, dev):
@@ -301,9 +306,12 @@ def _block_drop(W: TowerW, bw: BlockW, x: torch.Tensor, B: int, T: int, rope, dr
     h2 = norm(xs2, M2, D, bw.n2_w, bw.n2_b, W.eps, mode, want="op", tape=nt2)
     Hd = bw.hidden
     pre = _e((M2, 2 * Hd), BF, dev)
-    linear(h2, bw.fc1, pre, M2, mode)
     hid = _e((M2, Hd), BF, dev)
-    lib.swiglu_fwd(pre, hid, M2, Hd)
+    if FUSED_SWIGLU:
+        linear(h2, bw.fc1, hid, M2, mode, act=lib.ACT_SWIGLU8, ldo=Hd, out2=pre)
+    else:
+        linear(h2, bw.fc1, pre, M2, mode)
+        lib.swiglu_fwd(pre, hid, M2, Hd)
     res2 = _e((M2, D), BF, dev)
     linear(hid, bw.fc2, res2, M2, mode)
     x_out = x_mid.clone()
@@ -365,7 +373,7 @@ def tower_blocks(W: TowerW, x: torch.Tensor, B: int, T: int, rope, mode: str, *,
         Hd = bw.hidden
         hid = _e((M, Hd), act, dev)
         pre = None
-        if W.ffn == "swiglu" and mode == "bf16" and SPLIT_EPILOGUES:
+        if W.ffn == "swiglu" and mode == "bf16" and SPLIT_EPILOGUES and not FUSED_SWIGLU:
             pre = _e((M, 2 * Hd), BF, dev)
             linear(h2, bw.fc1, pre, M, mode)
             lib.swiglu_fwd(pre, hid, M, Hd)

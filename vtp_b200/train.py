@@ -294,6 +294,12 @@ class TrainConfig:
     clip_drop_rate: float = 0.0
     ssl_drop_rate: float = 0.0
     rec_drop_rate: float = 0.0
+    # collective C3: "end" = ONE all-reduce of the flat gradient buffer after the last backward; "overlap" = every tower's
+    # bucket is all-reduced as soon as it is final, under the remaining backward (env VTP_GRAD_REDUCE overrides).
+    # Measured at N = 8 (profiles/r2_logs/bench_{small,large}_n8{,_end}.json): "end" 231.1 / 1317.5 ms vs "overlap"
+    # 233.6 / 1325.4 ms (Small / Large) — NCCL's CTAs take SMs away from the persistent, full-machine GEMM and attention
+    # kernels for longer than the ~1 ms (Small) / ~8 ms (Large, 3 GB fp32) the exposed all-reduce costs over NVLink.
+    grad_reduce: str = "end"
 
 
 class VTPTrainer:
@@ -365,10 +371,19 @@ class VTPTrainer:
     def _grad_buckets(self) -> Dict[str, List[Tuple[int, int]]]:
         return grad_buckets(self.store.offset, self.store.n)
 
-    def _reduce_bucket(self, which: str):
+    def _grad_reduce_mode(self) -> str:
+        import os
+        mode = os.environ.get("VTP_GRAD_REDUCE", self.tc.grad_reduce)
+        if mode not in ("overlap", "end"):
+            raise ValueError(f"grad_reduce must be 'overlap' or 'end', got {mode!r}")
+        return mode
+
+    def _reduce_bucket(self, which: str, final: bool = False):
         """Start the all-reduce of one finished gradient bucket (no-op single rank / already started this step)."""
         if self.world == 1 or which in self._started:
             return
+        if not final and self._grad_reduce_mode() == "end":
+            return                       # deferred: allreduce_grads() starts every bucket after the last backward
         import torch.distributed as dist
         self._started.add(which)
         for a, b in self._buckets[which]:
@@ -1001,8 +1016,12 @@ class VTPTrainer:
         """Collective C3: whatever bucket has not been started yet (always the trunk), then wait for all of them; the
         sum is averaged by grad_scale = 1/world inside the fused optimiser.  fp32 on the wire (exact accumulation)."""
         if self.world > 1:
+            import torch.distributed as dist
+            if not self._started:        # "end" mode: nothing in flight — one call over the whole flat buffer
+                dist.all_reduce(self.store.g, group=self.pg)
+                return
             for which in ("text", "head", "decoder", "trunk"):
-                self._reduce_bucket(which)
+                self._reduce_bucket(which, final=True)
             for w in self._pending:
                 w.wait()                 # the compute stream waits for NCCL's stream; the host does not block
             self._pending = []
