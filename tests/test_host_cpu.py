@@ -167,3 +167,38 @@ def test_cosine_schedule_matches_reference_table():
         for kw in cases:
             ref, s = CosineScheduler(**kw), CosineSchedule(**kw)
             assert all(ref[i] == s[i] for i in range(kw["total_iters"] + 3))
+
+
+def test_from_pretrained_sharded_and_strict_arguments(tmp_path):
+    """HF sharded layout (model.safetensors.index.json) loads; unsupported from_pretrained arguments raise instead of being
+    dropped silently; torch_dtype converts the parameters but keeps the bf16 RoPE periods buffer."""
+    import json
+
+    import pytest
+    from safetensors.torch import save_file
+
+    from vtp_b200 import VTPConfig, VTPModel
+
+    cfg = VTPConfig(vision_embed_dim=128, vision_depth=1, vision_num_heads=2, text_embed_dim=128, text_num_heads=2, text_depth=1,
+                    decoder_embed_dim=128, decoder_num_heads=2, decoder_depth=1, text_vocab_size=64)
+    m = VTPModel(cfg)
+    m.save_pretrained(str(tmp_path))
+    sd = {k: v.detach().clone().contiguous() for k, v in m.state_dict().items()}
+    keys = sorted(sd)
+    a, b = keys[: len(keys) // 2], keys[len(keys) // 2:]
+    os.remove(os.path.join(tmp_path, "model.safetensors"))
+    save_file({k: sd[k] for k in a}, os.path.join(tmp_path, "model-00001-of-00002.safetensors"))
+    save_file({k: sd[k] for k in b}, os.path.join(tmp_path, "model-00002-of-00002.safetensors"))
+    with open(os.path.join(tmp_path, "model.safetensors.index.json"), "w") as f:
+        json.dump({"weight_map": {**{k: "model-00001-of-00002.safetensors" for k in a},
+                                  **{k: "model-00002-of-00002.safetensors" for k in b}}}, f)
+    m2 = VTPModel.from_pretrained(str(tmp_path))
+    assert all(torch.equal(v, m2.state_dict()[k]) for k, v in sd.items())
+    m3 = VTPModel.from_pretrained(str(tmp_path), torch_dtype=torch.bfloat16)
+    assert m3.trunk.cls_token.dtype == torch.bfloat16 and m3.trunk.rope_embed.periods.dtype == torch.bfloat16
+    with pytest.raises(TypeError):
+        VTPModel.from_pretrained(str(tmp_path), low_cpu_mem_usage=True)
+    with pytest.raises(NotImplementedError):
+        VTPModel.from_pretrained(str(tmp_path), device_map="auto")
+    with pytest.raises(FileNotFoundError):
+        VTPModel.from_pretrained("MiniMaxAI/VTP-Large-f16d64")

@@ -79,11 +79,17 @@ def test_bf16_mode_matches_reference_autocast(name):
         dev["txt_feat"] = (rel(ft, g["txt_feat_fp32"]), rel(g["txt_feat_bf16"], g["txt_feat_fp32"]))
     print(name, "bf16-mode rel vs ref-autocast:", {k: f"{v:.2e}" for k, v in e.items()})
     print(name, "  (ours vs fp32, ref-bf16 vs fp32):", {k: (f"{a:.2e}", f"{b:.2e}") for k, (a, b) in dev.items()})
-    assert max(e.values()) < 2e-2, e
+    # Derived bounds, per output, with the REFERENCE's own bf16 sensitivity d = |ref autocast-bf16 - ref fp32|
+    # as the yardstick (7e-3 at tiny ... 2.4e-2 for the chaotic cls token at depth 12):
+    #   (i)  our distance to the reference's bf16 output <= 1.25 d  (two independent bf16 evaluations cannot be closer to
+    #        each other than each is to fp32; measured 0.27-1.03 d), capped at 2e-2 absolute;
+    #   (ii) our distance to the reference's FP32 output <= 1.15 d + 2e-4  (measured 0.97-1.03 d: our bf16 path is exactly
+    #        as far from fp32 as the reference's own autocast path).
     for k, (ours, theirs) in dev.items():
+        assert e[k] < min(2e-2, 1.25 * theirs + 2e-4), (k, e[k], theirs)
         if k == "recon":
-            continue  # decoded from the reference's bf16 latents: deviation measured on recon_bf16 only
-        assert ours < 2.0 * theirs + 1e-3, (k, ours, theirs)
+            continue  # decoded from the reference's bf16 latents: compared with recon_bf16 above only
+        assert ours < 1.15 * theirs + 2e-4, (k, ours, theirs)
 
 
 def test_text_argmax_pool_index_is_exact():

@@ -280,19 +280,45 @@ class VTPModel(VTPPreTrainedModel):
 
     # ------------------------------------------------------------------ HF-format checkpoints
     @classmethod
-    def from_pretrained(cls, path: str, device: Optional[Union[str, torch.device]] = None, **_ignored):
+    def from_pretrained(cls, path: str, device: Optional[Union[str, torch.device]] = None,
+                        torch_dtype: Optional[torch.dtype] = None, device_map: Optional[Union[str, torch.device]] = None, **kwargs):
+        """HF checkpoint directory (config.json + model.safetensors, or the sharded `model.safetensors.index.json` layout).
+        `torch_dtype` converts the stored parameters (compute precision still follows the caller's autocast context);
+        `device_map` accepts a single device ("cuda", "cuda:0", torch.device) — sharding a model over devices is not
+        supported.  Hub names and any other `PreTrainedModel.from_pretrained` argument raise instead of being ignored."""
         from safetensors.torch import load_file
 
+        if kwargs:
+            raise TypeError(f"VTPModel.from_pretrained: unsupported arguments {sorted(kwargs)} (local directory, torch_dtype, "
+                            "device / device_map only)")
+        if not os.path.isdir(path):
+            raise FileNotFoundError(f"{path!r} is not a local checkpoint directory (hub names need network access)")
+        if device_map is not None:
+            if isinstance(device_map, dict) or device_map in ("auto", "balanced", "sequential"):
+                raise NotImplementedError("device_map must name ONE device; model sharding is not supported")
+            device = device_map if device is None else device
         with open(os.path.join(path, "config.json")) as f:
             cd = json.load(f)
         for k in ("architectures", "model_type", "transformers_version", "torch_dtype", "dtype"):
             cd.pop(k, None)
         model = cls(VTPConfig(**cd))
-        sd = load_file(os.path.join(path, "model.safetensors"))
+        index = os.path.join(path, "model.safetensors.index.json")
+        if os.path.exists(index):          # sharded checkpoint: {"weight_map": {key: shard file}}
+            with open(index) as f:
+                shards = sorted(set(json.load(f)["weight_map"].values()))
+            sd = {}
+            for sh in shards:
+                sd.update(load_file(os.path.join(path, sh)))
+        else:
+            sd = load_file(os.path.join(path, "model.safetensors"))
         missing, unexpected = model.load_state_dict(sd, strict=False)
         missing = [k for k in missing if not k.endswith("rope_embed.periods")]
         if missing or unexpected:
             raise RuntimeError(f"checkpoint mismatch: missing={missing[:5]} unexpected={unexpected[:5]}")
+        if torch_dtype is not None:
+            periods = {k: v.clone() for k, v in model.state_dict().items() if k.endswith("rope_embed.periods")}
+            model = model.to(torch_dtype)
+            model.load_state_dict(periods, strict=False)     # the bf16 RoPE periods buffer keeps its dtype
         return model.to(device) if device is not None else model
 
     def save_pretrained(self, path: str):
@@ -321,11 +347,22 @@ class VTPModel(VTPPreTrainedModel):
             return "bf16"
         return "fp32"
 
-    def _version(self) -> int:
-        return sum(p._version for p in self.parameters())
+    def _version(self):
+        """Cache key of the packed weights / captured graphs: in-place version counters AND where the parameters live
+        (`.to(device)`, `.half()` or `p.data = ...` do not bump `_version`).  Writers through `p.data.copy_()` must call
+        `invalidate_packed_weights()`."""
+        p0 = self.trunk.cls_token
+        return (sum(p._version for p in self.parameters()), str(p0.device), p0.dtype, p0.data_ptr())
 
     def invalidate_packed_weights(self):
         self._packs = {}
+        self._graphs = {}
+
+    def _apply(self, fn, *args, **kwargs):     # .to() / .cuda() / .half(): packed copies and graphs point at the old storage
+        out = super()._apply(fn, *args, **kwargs)
+        if hasattr(self, "_packs"):
+            self._packs, self._graphs = {}, {}
+        return out
 
     def _pack(self, tower: str, mode: str) -> E.TowerW:
         ver = self._version()
