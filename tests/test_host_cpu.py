@@ -202,3 +202,34 @@ def test_from_pretrained_sharded_and_strict_arguments(tmp_path):
         VTPModel.from_pretrained(str(tmp_path), device_map="auto")
     with pytest.raises(FileNotFoundError):
         VTPModel.from_pretrained("MiniMaxAI/VTP-Large-f16d64")
+
+
+def test_crop_box_sampling_follows_torchvision_get_params():
+    """vtp_b200.data.random_resized_crop_boxes restates torchvision RandomResizedCrop.get_params (area scale x log-uniform
+    aspect ratio, 10 tries, centre-crop fallback): boxes inside the image, areas / ratios inside the requested ranges, and
+    the same distribution as torchvision's own sampler (mean area / mean log-ratio within sampling error)."""
+    import math
+
+    import numpy as np
+    from torchvision.transforms import RandomResizedCrop
+
+    from vtp_b200.data import random_resized_crop_boxes
+
+    H, W = 300, 400
+    rng = np.random.default_rng(0)
+    for scale in ((0.32, 1.0), (0.05, 0.32), (0.9, 1.0)):
+        b = random_resized_crop_boxes(rng, 6000, H, W, scale)
+        assert (b[:, 0] >= 0).all() and (b[:, 1] >= 0).all() and (b[:, 0] + b[:, 2] <= W).all() and (b[:, 1] + b[:, 3] <= H).all()
+        area = b[:, 2] * b[:, 3] / (H * W)
+        assert area.min() >= scale[0] * 0.95 and area.max() <= min(1.0, scale[1] * 1.02)
+        torch.manual_seed(0)
+        img = torch.zeros(3, H, W)
+        tv = np.array([RandomResizedCrop.get_params(img, list(scale), [3 / 4, 4 / 3]) for _ in range(3000)], dtype=np.float64)  # i, j, h, w
+        tv_area = tv[:, 2] * tv[:, 3] / (H * W)
+        tv_lr = np.log(tv[:, 3] / tv[:, 2])
+        lr = np.log(b[:, 2] / b[:, 3])
+        assert abs(area.mean() - tv_area.mean()) < 0.02 and abs(lr.mean() - tv_lr.mean()) < 0.02
+        assert abs(lr.std() - tv_lr.std()) < 0.02
+    # an image so elongated that no ratio in [3/4, 4/3] fits at this scale: centre-crop fallback, clipped to the ratio range
+    fb = random_resized_crop_boxes(np.random.default_rng(1), 10, 100, 1000, (0.9, 1.0))
+    assert (fb[:, 3] == 100).all() and (np.abs(fb[:, 2] / fb[:, 3] - 4 / 3) < 0.02).all()
