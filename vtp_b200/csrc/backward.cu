@@ -48,7 +48,12 @@ __global__ void __launch_bounds__(256, (MAXV <= 4 ? 3 : (MAXV <= 8 ? 2 : 1))) no
     for (int gidx = 0; gidx < MAXV; ++gidx)
 #pragma unroll
         for (int i = 0; i < 4; ++i) aw[gidx][i] = 0.f, ab[gidx][i] = 0.f, ag[gidx][i] = 0.f;
-    const int r0 = blockIdx.x * rows_per_block;
+    // persistent blocks (round 2): a block walks strips blockIdx.x, blockIdx.x + gridDim.x, ... and flushes its column
+    // partials ONCE — 444 blocks x 288 float4 atomics instead of one flush per 128-row strip (1 028 of them at M = 131 584,
+    // 1 028-deep same-address chains in L2)
+    const int nstrips = (M + rows_per_block - 1) / rows_per_block;
+    for (int strip = blockIdx.x; strip < nstrips; strip += gridDim.x) {
+    const int r0 = strip * rows_per_block;
     const int r1 = min(M, r0 + rows_per_block);
     for (int row = r0 + warp; row < r1; row += nw) {
         const float rstd = rstd_[row];
@@ -110,6 +115,7 @@ __global__ void __launch_bounds__(256, (MAXV <= 4 ? 3 : (MAXV <= 8 ? 2 : 1))) no
             }
         }
     }
+    }
 #pragma unroll
     for (int gidx = 0; gidx < MAXV; ++gidx) {
         const int c = (gidx * 32 + lane) * 4;
@@ -140,6 +146,7 @@ __global__ void __launch_bounds__(256, (MAXV <= 4 ? 3 : (MAXV <= 8 ? 2 : 1))) no
 // and leave the block as ONE float4 atomic per 4 columns (same-address fp32 atomics serialise in a single L2 slice:
 // the first version issued one per 32 rows and spent 2-4x the HBM time waiting on them).
 static constexpr int CS_X = 128, CS_Y = 4, CS_ROWS = 256;
+static constexpr int CC_ROWS = 64;   // strip height of the persistent cast_colsum grid
 
 template <int NF>  // NF floats of partial sums per thread
 __device__ __forceinline__ void block_colsum_flush(float (&acc)[NF], float* sh /*[CS_Y][CS_X][NF]*/, float* dst, bool active) {
@@ -253,18 +260,22 @@ cast_colsum_kernel(const TX* __restrict__ x, long ldx, __nv_bfloat16* __restrict
     const int G = N / 4;
     const int gidx = blockIdx.x * CS_X + threadIdx.x;
     const bool active = gidx < G;
-    const int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    // persistent in y (round 2): strips of CC_ROWS rows, one flush of the column partials per block
+    const int nstrips = (M + CC_ROWS - 1) / CC_ROWS;
     if (active) {
+        for (int strip = blockIdx.y; strip < nstrips; strip += gridDim.y) {
+            const int r0 = strip * CC_ROWS, r1 = min(M, r0 + CC_ROWS);
 #pragma unroll 4
-        for (int row = r0 + threadIdx.y; row < r1; row += CS_Y) {
-            float v[4];
-            ld4<TX>(x + (long)row * ldx + 4 * gidx, v);
-            acc[0] += v[0], acc[1] += v[1], acc[2] += v[2], acc[3] += v[3];
-            if (y) {
-                uint2 t;
-                t.x = pack_bf16x2(v[0], v[1]), t.y = pack_bf16x2(v[2], v[3]);
-                *reinterpret_cast<uint2*>(y + (long)row * N + 4 * gidx) = t;
+            for (int row = r0 + threadIdx.y; row < r1; row += CS_Y) {
+                float v[4];
+                ld4<TX>(x + (long)row * ldx + 4 * gidx, v);
+                acc[0] += v[0], acc[1] += v[1], acc[2] += v[2], acc[3] += v[3];
+                if (y) {
+                    uint2 t;
+                    t.x = pack_bf16x2(v[0], v[1]), t.y = pack_bf16x2(v[2], v[3]);
+                    *reinterpret_cast<uint2*>(y + (long)row * N + 4 * gidx) = t;
+                }
             }
         }
     }
@@ -415,8 +426,10 @@ extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const
     VTP_CHECK_ARG(!is_ln || mean, "norm_bwd: LayerNorm needs mean");
     VTP_CHECK_ARG((reinterpret_cast<uintptr_t>(dw) & 15) == 0 && (!db || (reinterpret_cast<uintptr_t>(db) & 15) == 0),
                   "norm_bwd: dw/db must be 16B aligned");
-    const int threads = 256, rows_per_block = 128;   // 3 blocks of 256 threads per SM (see norm_bwd_kernel)
-    const int grid = ceil_div(M, rows_per_block);
+    const int threads = 256, rows_per_block = 32;    // strips of 32 rows (4 per warp), walked by a persistent grid
+    const int per_sm = D <= 512 ? 3 : (D <= 1024 ? 2 : 1);   // resident blocks per SM (launch bounds of the MAXV variant)
+    const int nstrips = ceil_div(M, rows_per_block);
+    const int grid = nstrips < per_sm * num_sms() ? nstrips : per_sm * num_sms();
     VTP_CHECK_ARG(!g_colsum || (reinterpret_cast<uintptr_t>(g_colsum) & 15) == 0, "norm_bwd: g_colsum must be 16B aligned");
     const size_t smem = 3 * (size_t)D * sizeof(float);
     cudaStream_t s = (cudaStream_t)st;
@@ -465,7 +478,9 @@ extern "C" int vtp_cast_colsum(const void* x, int x_dtype, long ldx, void* y_bf1
                                vtp_stream_t st) {
     VTP_CHECK_ARG(x && M > 0 && N % 4 == 0 && (y_bf16 || colsum), "cast_colsum: bad args");
     VTP_CHECK_ARG(!colsum || (reinterpret_cast<uintptr_t>(colsum) & 15) == 0, "cast_colsum: colsum must be 16B aligned");
-    dim3 grid(ceil_div(N / 4, CS_X), ceil_div(M, CS_ROWS)), block(CS_X, CS_Y);
+    const int gx = ceil_div(N / 4, CS_X), strips = ceil_div(M, CC_ROWS);
+    const int gy_cap = (4 * num_sms() + gx - 1) / gx;          // ~4 resident 512-thread blocks per SM in total
+    dim3 grid(gx, strips < gy_cap ? strips : gy_cap), block(CS_X, CS_Y);
     if (x_dtype == VTP_F32)
         cast_colsum_kernel<float><<<grid, block, 0, (cudaStream_t)st>>>((const float*)x, ldx, (__nv_bfloat16*)y_bf16, colsum,
                                                                        M, N);
