@@ -682,6 +682,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
                 const int m0 = m_blk * BM, n0 = n_blk * BN;
+                // implicit conv: tile origin once per tile, (tap, channel block) advanced incrementally — the producer is ONE
+                // thread and every runtime integer division in its k-loop is ~40 dependent instructions on the feed path
+                int cv_x0 = 0, cv_y0 = 0, cv_b = 0, cv_c = 0, cv_dx = -1, cv_dy = -1;
+                if (p.conv_C) {
+                    cv_x0 = (m_blk % p.conv_tiles_w) * p.conv_TW;
+                    cv_y0 = ((m_blk / p.conv_tiles_w) % p.conv_tiles_h) * p.conv_TH;
+                    cv_b = m_blk / (p.conv_tiles_w * p.conv_tiles_h);
+                    if (kb0 != 0) {  // (split-K never starts mid-way for conv, but stay general)
+                        const int cpk = p.conv_C >> 6, tap = kb0 / cpk;
+                        cv_c = (kb0 % cpk) << 6, cv_dx = tap % 3 - 1, cv_dy = tap / 3 - 1;
+                    }
+                }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
                     uint8_t* sa = smem + s * STAGE_BYTES;
@@ -691,11 +703,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     const uint32_t lbar = G2 ? mapa_u32(&full_bar[s], 0) : 0u;
                     const int k0 = kb * BK;
                     if (p.conv_C) {
-                        const int tx = m_blk % p.conv_tiles_w, ty = (m_blk / p.conv_tiles_w) % p.conv_tiles_h;
-                        const int bimg = m_blk / (p.conv_tiles_w * p.conv_tiles_h);
-                        const int cpk = p.conv_C >> 6, tap = kb / cpk, c0 = (kb % cpk) << 6;
-                        tma_load_4d(sa, &tmA, &full_bar[s], c0, tx * p.conv_TW + tap % 3 - 1, ty * p.conv_TH + tap / 3 - 1,
-                                    bimg);
+                        tma_load_4d(sa, &tmA, &full_bar[s], cv_c, cv_x0 + cv_dx, cv_y0 + cv_dy, cv_b);
+                        cv_c += 64;
+                        if (cv_c == p.conv_C) {
+                            cv_c = 0;
+                            if (++cv_dx == 2) cv_dx = -1, ++cv_dy;
+                        }
                     } else if (G2) {
                         if (!p.a_mn) {
                             tma_load_2d_g2(sa, &tmA, lbar, k0, m0);
