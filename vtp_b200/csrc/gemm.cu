@@ -368,6 +368,28 @@ __device__ __forceinline__ void arrive_tempty(uint64_t* bar) {
     else mbar_arrive(bar);
 }
 
+// Tile index t = work_id, work_id + stride, ... decomposed as t = (ks * num_m + m) * num_n + n WITHOUT a division per tile: the
+// producer and the MMA issuer are single threads, and three runtime integer divisions per tile (~150 dependent instructions)
+// sat directly on the operand-feed path of the short-K GEMMs (found on the implicit-conv form, profiles/r2_logs/lpips_layers*).
+struct TileIter {
+    int n, m, ks;          // current tile
+    int dn, dm, dks;       // decomposition of the stride
+    int nn, nm;
+    __device__ __forceinline__ TileIter(int t0, int stride, int num_n, int num_m) : nn(num_n), nm(num_m) {
+        n = t0 % num_n;
+        const int r = t0 / num_n;
+        m = r % num_m, ks = r / num_m;
+        dn = stride % num_n;
+        const int rs = stride / num_n;
+        dm = rs % num_m, dks = rs / num_m;
+    }
+    __device__ __forceinline__ void next() {
+        n += dn, m += dm, ks += dks;
+        if (n >= nn) n -= nn, ++m;
+        if (m >= nm) m -= nm, ++ks;
+    }
+};
+
 // ---- SwiGLU gate in the lean epilogue (FAST 6: hidden + pre-activation outputs, FAST 7: hidden only).
 // The stand-alone gate pass re-read the whole [M, 2Hs] pre-activation (539 MB per FFN forward at the bench shape, 6.6 ms of
 // the step); here the epilogue warp that owns two ADJACENT 64-column packed chunks (8-interleaved w1|w2: columns
@@ -675,10 +697,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
-            for (int t = work_id; t < num_tiles; t += work_stride) {
-                const int n_blk = t % p.num_n_blocks;
-                const int m_blk = ((t / p.num_n_blocks) % p.num_m_blocks) * (CL2 ? CLM : 1) + (int)crank;
-                const int ks = t / tiles_mn;
+            TileIter ti(work_id, work_stride, p.num_n_blocks, p.num_m_blocks);
+            for (int t = work_id; t < num_tiles; t += work_stride, ti.next()) {
+                const int n_blk = ti.n;
+                const int m_blk = ti.m * (CL2 ? CLM : 1) + (int)crank;
+                const int ks = ti.ks;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
                 const int m0 = m_blk * BM, n0 = n_blk * BN;
@@ -759,8 +782,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             uint32_t ph = 0;
             int as = 0;
             uint32_t aph = 0;
-            for (int t = work_id; t < num_tiles; t += work_stride) {
-                const int ks = t / tiles_mn;
+            TileIter ti(work_id, work_stride, p.num_n_blocks, p.num_m_blocks);
+            for (int t = work_id; t < num_tiles; t += work_stride, ti.next()) {
+                const int ks = ti.ks;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
                 mbar_wait(&tempty_bar[as], aph ^ 1);
@@ -801,9 +825,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const bool has_resid = p.resid != nullptr;
         int as = 0;
         uint32_t aph = 0;
-        for (int t = work_id; t < num_tiles; t += work_stride) {
-            const int n_blk = t % p.num_n_blocks;
-            const int m_blk = ((t / p.num_n_blocks) % p.num_m_blocks) * (CL2 ? CLM : 1) + (int)crank;
+        TileIter ti(work_id, work_stride, p.num_n_blocks, p.num_m_blocks);
+        for (int t = work_id; t < num_tiles; t += work_stride, ti.next()) {
+            const int n_blk = ti.n;
+            const int m_blk = ti.m * (CL2 ? CLM : 1) + (int)crank;
             const int m0 = m_blk * BM, n0 = n_blk * BN;
             const int grow0 = m0 + q * 32;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + as * ACC_STRIDE;
