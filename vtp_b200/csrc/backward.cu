@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(256, (MAXV <= 4 ? 3 : (MAXV <= 8 ? 2 : 1))) no
 // ROWS_PER_BLOCK strip with several independent loads in flight, partial sums are reduced across y in shared memory
 // and leave the block as ONE float4 atomic per 4 columns (same-address fp32 atomics serialise in a single L2 slice:
 // the first version issued one per 32 rows and spent 2-4x the HBM time waiting on them).
-static constexpr int CS_X = 128, CS_Y = 4, CS_ROWS = 256;
+static constexpr int CS_X = 128, CS_Y = 4;
 static constexpr int CC_ROWS = 64;   // strip height of the persistent cast_colsum grid
 
 template <int NF>  // NF floats of partial sums per thread
@@ -176,11 +176,13 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __
     const int G = Hs / 8;
     const int gidx = blockIdx.x * CS_X + threadIdx.x;
     const bool active = gidx < G;
-    const int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+    const int nstrips = (M + CC_ROWS - 1) / CC_ROWS;     // persistent in y: one flush of the bias-gradient partials per block
     if (active) {
+        for (int strip = blockIdx.y; strip < nstrips; strip += gridDim.y) {
+        const int r0 = strip * CC_ROWS, r1 = min(M, r0 + CC_ROWS);
 #pragma unroll 2
         for (int row = r0 + threadIdx.y; row < r1; row += CS_Y) {
             const uint4 x1p = *reinterpret_cast<const uint4*>(pre + (long)row * 2 * Hs + 16 * gidx);
@@ -207,6 +209,7 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __
             *reinterpret_cast<uint4*>(dpre + (long)row * 2 * Hs + 16 * gidx) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
             *reinterpret_cast<uint4*>(dpre + (long)row * 2 * Hs + 16 * gidx + 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
         }
+        }
     }
     if (dbias) block_colsum_flush<16>(acc, sh, dbias + 16 * gidx, active);
 }
@@ -219,11 +222,13 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __re
     const int G = N / 8;
     const int gidx = blockIdx.x * CS_X + threadIdx.x;
     const bool active = gidx < G;
-    const int r0 = blockIdx.y * CS_ROWS, r1 = min(M, r0 + CS_ROWS);
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    const int nstrips = (M + CC_ROWS - 1) / CC_ROWS;
     if (active) {
+        for (int strip = blockIdx.y; strip < nstrips; strip += gridDim.y) {
+        const int r0 = strip * CC_ROWS, r1 = min(M, r0 + CC_ROWS);
 #pragma unroll 2
         for (int row = r0 + threadIdx.y; row < r1; row += CS_Y) {
             const uint4 xp = *reinterpret_cast<const uint4*>(pre + (long)row * N + 8 * gidx);
@@ -245,6 +250,7 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __re
                 o[k] = pack_bf16x2(r[0], r[1]);
             }
             *reinterpret_cast<uint4*>(dpre + (long)row * N + 8 * gidx) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
         }
     }
     if (dbias) block_colsum_flush<8>(acc, sh, dbias + 8 * gidx, active);
@@ -457,7 +463,9 @@ extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const
 extern "C" int vtp_swiglu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int Hs, vtp_stream_t st) {
     VTP_CHECK_ARG(pre && dhid && dpre && M > 0 && Hs % 8 == 0, "swiglu_bwd: bad args");
     VTP_CHECK_ARG(!dbias || (reinterpret_cast<uintptr_t>(dbias) & 15) == 0, "swiglu_bwd: dbias must be 16B aligned");
-    dim3 grid(ceil_div(Hs / 8, CS_X), ceil_div(M, CS_ROWS)), block(CS_X, CS_Y);
+    const int gx = ceil_div(Hs / 8, CS_X), strips = ceil_div(M, CC_ROWS);
+    const int gy_cap = (4 * num_sms() + gx - 1) / gx;
+    dim3 grid(gx, strips < gy_cap ? strips : gy_cap), block(CS_X, CS_Y);
     swiglu_bwd_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
                                                             (__nv_bfloat16*)dpre, dbias, M, Hs);
     VTP_LAUNCH_CHECK();
@@ -467,7 +475,9 @@ extern "C" int vtp_swiglu_bwd(const void* pre, const void* dhid, void* dpre, flo
 extern "C" int vtp_gelu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int N, vtp_stream_t st) {
     VTP_CHECK_ARG(pre && dhid && dpre && M > 0 && N % 8 == 0, "gelu_bwd: bad args");
     VTP_CHECK_ARG(!dbias || (reinterpret_cast<uintptr_t>(dbias) & 15) == 0, "gelu_bwd: dbias must be 16B aligned");
-    dim3 grid(ceil_div(N / 8, CS_X), ceil_div(M, CS_ROWS)), block(CS_X, CS_Y);
+    const int gx = ceil_div(N / 8, CS_X), strips = ceil_div(M, CC_ROWS);
+    const int gy_cap = (4 * num_sms() + gx - 1) / gx;
+    dim3 grid(gx, strips < gy_cap ? strips : gy_cap), block(CS_X, CS_Y);
     gelu_bwd_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
                                                           (__nv_bfloat16*)dpre, dbias, M, N);
     VTP_LAUNCH_CHECK();
