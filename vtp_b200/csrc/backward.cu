@@ -169,7 +169,7 @@ __device__ __forceinline__ void block_colsum_flush(float (&acc)[NF], float* sh /
 }
 
 // pre packed [M][2Hs] (8-interleaved x1|x2, bf16), dhid [M][Hs] bf16 -> dpre [M][2Hs] bf16 ; dbias[2Hs] += colsum(dpre)
-__global__ void __launch_bounds__(CS_X * CS_Y)
+__global__ void __launch_bounds__(CS_X * CS_Y, 2)
 swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dhid,
                   __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int Hs) {
     __shared__ float sh[CS_Y * CS_X * 16];
@@ -179,12 +179,12 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-    const int nstrips = (M + CC_ROWS - 1) / CC_ROWS;     // persistent in y: one flush of the bias-gradient partials per block
+    // persistent in y: the grid sweeps the rows CS_Y at a time (row-interleaved blocks, ONE loop: the strip form cost 14
+    // registers and the second resident block), one flush of the bias-gradient partials per block
     if (active) {
-        for (int strip = blockIdx.y; strip < nstrips; strip += gridDim.y) {
-        const int r0 = strip * CC_ROWS, r1 = min(M, r0 + CC_ROWS);
+        const int row_step = gridDim.y * CS_Y;
 #pragma unroll 2
-        for (int row = r0 + threadIdx.y; row < r1; row += CS_Y) {
+        for (int row = blockIdx.y * CS_Y + threadIdx.y; row < M; row += row_step) {
             const uint4 x1p = *reinterpret_cast<const uint4*>(pre + (long)row * 2 * Hs + 16 * gidx);
             const uint4 x2p = *reinterpret_cast<const uint4*>(pre + (long)row * 2 * Hs + 16 * gidx + 8);
             const uint4 dhp = *reinterpret_cast<const uint4*>(dhid + (long)row * Hs + 8 * gidx);
@@ -209,13 +209,12 @@ swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __
             *reinterpret_cast<uint4*>(dpre + (long)row * 2 * Hs + 16 * gidx) = make_uint4(o1[0], o1[1], o1[2], o1[3]);
             *reinterpret_cast<uint4*>(dpre + (long)row * 2 * Hs + 16 * gidx + 8) = make_uint4(o2[0], o2[1], o2[2], o2[3]);
         }
-        }
     }
     if (dbias) block_colsum_flush<16>(acc, sh, dbias + 16 * gidx, active);
 }
 
 // pre [M][N] bf16, dhid [M][N] bf16 -> dpre = dhid * gelu'(pre) ; dbias[N] += colsum(dpre)
-__global__ void __launch_bounds__(CS_X * CS_Y)
+__global__ void __launch_bounds__(CS_X * CS_Y, 2)
 gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __restrict__ dhid,
                 __nv_bfloat16* __restrict__ dpre, float* __restrict__ dbias, int M, int N) {
     __shared__ float sh[CS_Y * CS_X * 8];
@@ -225,12 +224,10 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __re
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    const int nstrips = (M + CC_ROWS - 1) / CC_ROWS;
     if (active) {
-        for (int strip = blockIdx.y; strip < nstrips; strip += gridDim.y) {
-        const int r0 = strip * CC_ROWS, r1 = min(M, r0 + CC_ROWS);
+        const int row_step = gridDim.y * CS_Y;
 #pragma unroll 2
-        for (int row = r0 + threadIdx.y; row < r1; row += CS_Y) {
+        for (int row = blockIdx.y * CS_Y + threadIdx.y; row < M; row += row_step) {
             const uint4 xp = *reinterpret_cast<const uint4*>(pre + (long)row * N + 8 * gidx);
             const uint4 dp = *reinterpret_cast<const uint4*>(dhid + (long)row * N + 8 * gidx);
             const uint32_t xw[4] = {xp.x, xp.y, xp.z, xp.w}, dw[4] = {dp.x, dp.y, dp.z, dp.w};
@@ -250,7 +247,6 @@ gelu_bwd_kernel(const __nv_bfloat16* __restrict__ pre, const __nv_bfloat16* __re
                 o[k] = pack_bf16x2(r[0], r[1]);
             }
             *reinterpret_cast<uint4*>(dpre + (long)row * N + 8 * gidx) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
         }
     }
     if (dbias) block_colsum_flush<8>(acc, sh, dbias + 8 * gidx, active);
@@ -463,9 +459,9 @@ extern "C" int vtp_norm_bwd(const void* x, int x_dtype, const float* rstd, const
 extern "C" int vtp_swiglu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int Hs, vtp_stream_t st) {
     VTP_CHECK_ARG(pre && dhid && dpre && M > 0 && Hs % 8 == 0, "swiglu_bwd: bad args");
     VTP_CHECK_ARG(!dbias || (reinterpret_cast<uintptr_t>(dbias) & 15) == 0, "swiglu_bwd: dbias must be 16B aligned");
-    const int gx = ceil_div(Hs / 8, CS_X), strips = ceil_div(M, CC_ROWS);
-    const int gy_cap = (4 * num_sms() + gx - 1) / gx;
-    dim3 grid(gx, strips < gy_cap ? strips : gy_cap), block(CS_X, CS_Y);
+    const int gx = ceil_div(Hs / 8, CS_X), groups = ceil_div(M, CS_Y);
+    const int gy_cap = (2 * num_sms() + gx - 1) / gx;          // 2 resident 512-thread blocks per SM (64 registers): one wave
+    dim3 grid(gx, groups < gy_cap ? groups : gy_cap), block(CS_X, CS_Y);
     swiglu_bwd_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
                                                             (__nv_bfloat16*)dpre, dbias, M, Hs);
     VTP_LAUNCH_CHECK();
@@ -475,9 +471,9 @@ extern "C" int vtp_swiglu_bwd(const void* pre, const void* dhid, void* dpre, flo
 extern "C" int vtp_gelu_bwd(const void* pre, const void* dhid, void* dpre, float* dbias, int M, int N, vtp_stream_t st) {
     VTP_CHECK_ARG(pre && dhid && dpre && M > 0 && N % 8 == 0, "gelu_bwd: bad args");
     VTP_CHECK_ARG(!dbias || (reinterpret_cast<uintptr_t>(dbias) & 15) == 0, "gelu_bwd: dbias must be 16B aligned");
-    const int gx = ceil_div(N / 8, CS_X), strips = ceil_div(M, CC_ROWS);
-    const int gy_cap = (4 * num_sms() + gx - 1) / gx;
-    dim3 grid(gx, strips < gy_cap ? strips : gy_cap), block(CS_X, CS_Y);
+    const int gx = ceil_div(N / 8, CS_X), groups = ceil_div(M, CS_Y);
+    const int gy_cap = (2 * num_sms() + gx - 1) / gx;
+    dim3 grid(gx, groups < gy_cap ? groups : gy_cap), block(CS_X, CS_Y);
     gelu_bwd_kernel<<<grid, block, 0, (cudaStream_t)st>>>((const __nv_bfloat16*)pre, (const __nv_bfloat16*)dhid,
                                                           (__nv_bfloat16*)dpre, dbias, M, N);
     VTP_LAUNCH_CHECK();

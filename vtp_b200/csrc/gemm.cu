@@ -21,6 +21,12 @@ namespace vtp {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_BYTES = BM * BK * 2;
+static constexpr int BRES_KB = 9;                    // resident k-blocks of the B-resident conv form (3 x 3 taps x 64 channels)
+static constexpr int HALO_W = 16, HALO_H = 18;       // halo block of the BRES == 2 form: 18 rows of 16 pixels (tile 16 x 8)
+static constexpr int HALO_BYTES = HALO_W * HALO_H * BK * 2;
+#ifndef VTP_CONV_BRES_DEFAULT
+#define VTP_CONV_BRES_DEFAULT 0  // decided by measurement (profiles/): 0 off, 1 resident weights, 2 + halo block
+#endif
 static constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 
 struct GemmDev {
@@ -45,6 +51,7 @@ struct GemmDev {
     int conv_C, conv_H, conv_W, conv_TW, conv_TH, conv_tiles_h, conv_tiles_w, conv_B;
     const __nv_bfloat16* mask_pos;  // optional: out *= (mask_pos[row][col] > 0)   (ReLU backward in the dgrad epilogue)
     int ldm;
+    int halo_bo;  // BRES == 2: set the descriptor base-offset field to the row shift (diagnostic switch)
     int dbg;  // DIAG bits: 1 no global stores, 2 no tmem ld, 4 no epilogue work, 8 no MMA issue
 };
 
@@ -633,7 +640,12 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
 // MMA thread issues for both; full barriers (both CTAs' TMA bytes) and accumulator-empty barriers live in the leader.
 // Wider clusters (4 / 8 CTAs sharing one B tile) were built and measured in round 2 (profiles/r2_gemm_cluster_width.md):
 // slower than the pair on every shape of the step (fc1 197 -> 203 -> 216 us), so only the pair remains.
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST, bool G2>
+// BRES (implicit conv, 64 input channels -> <= 64 output channels; the two 64-channel VGG layers at 256 x 256 were bound by
+// the L2->SM feed: 9 taps x (16 KB pixels + 16 KB weights) per 128-pixel tile):
+//   1: the whole [BN x 9*64] weight matrix (72 KB) is loaded ONCE per CTA and stays resident; the ring carries only A;
+//   2: additionally the A operand is loaded once per tile as a (16+2) x 16-pixel HALO block (36 KB; tile = 16 rows x 8 pixels)
+//      and the nine taps are row-shifted UMMA descriptors into it (start + dy*2048 + dx*128, SBO = 2048): 8x less feed.
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST, bool G2, int BRES = 0>
 // 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168 (MINB = 1).
 // MINB = 2 (short-K shapes): two CTAs per SM with a 2-stage ring double the epilogue warps per SM at ~100 registers.
 __global__ void __launch_bounds__(NUM_THREADS, MINB)
@@ -642,8 +654,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     static_assert(!G2 || CL2, "cta_group::2 needs the 2-CTA cluster");
     constexpr int CLM = 2;                                      // CTAs per cluster (along M) sharing one B tile
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CLM) - 1u);  // every CTA of the cluster
-    constexpr int B_BYTES = (G2 ? BN / 2 : BN) * BK * 2;
-    constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static_assert(BRES == 0 || (!CL2 && !G2 && FAST != 0 && BN == 64), "resident-B conv form: 64-wide lean-epilogue tiles");
+    constexpr int A_ST_BYTES = BRES == 2 ? HALO_BYTES : A_BYTES;
+    constexpr int B_BYTES = BRES ? 0 : (G2 ? BN / 2 : BN) * BK * 2;
+    constexpr int STAGE_BYTES = A_ST_BYTES + B_BYTES;
+    constexpr int BRES_BYTES = BRES ? BRES_KB * BN * BK * 2 : 0;  // resident weights in front of the ring
     constexpr int ACC_STRIDE = BN == 192 ? 256 : BN;  // column distance of the two accumulator buffers
     constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;    // 256 or 512 (power of two)
 
@@ -654,13 +669,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                          : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     if (FAST && (smem_u32(smem_raw) & 1023u) != 0u) __trap();
     constexpr int STG_BYTES = NUM_EPI_WARPS * STG_FLOATS * 4 * (FAST == 6 ? 2 : 1);  // FAST 6: + the hidden-tile staging
-    float* stg_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES);  // 8 epilogue warps x 4 KB
-    float* bias_base = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + STG_BYTES);  // FAST only
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES + STG_BYTES + (FAST ? NUM_EPI_WARPS * 256 : 0));
+    uint8_t* ring = smem + BRES_BYTES;
+    float* stg_base = reinterpret_cast<float*>(ring + STAGES * STAGE_BYTES);  // 8 epilogue warps x 4 KB
+    float* bias_base = reinterpret_cast<float*>(ring + STAGES * STAGE_BYTES + STG_BYTES);  // FAST only
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + STAGES * STAGE_BYTES + STG_BYTES + (FAST ? NUM_EPI_WARPS * 256 : 0));
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* bres_bar = tempty_bar + 2;  // BRES: the resident weights have landed
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -676,6 +693,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], (CL2 && !G2) ? CLM : 1);
         for (int s = 0; s < 2; ++s)
             mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], G2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
+        mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -698,9 +716,24 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int s = 0;
             uint32_t ph = 0;
             TileIter ti(work_id, work_stride, p.num_n_blocks, p.num_m_blocks);
+            if constexpr (BRES != 0) {  // the whole weight matrix, once (N <= BN: rows beyond N are zero-filled)
+                mbar_expect_tx(bres_bar, BRES_BYTES);
+#pragma unroll
+                for (int kb = 0; kb < BRES_KB; ++kb) tma_load_2d(smem + kb * (BN * BK * 2), &tmB, bres_bar, kb * BK, 0);
+            }
             for (int t = work_id; t < num_tiles; t += work_stride, ti.next()) {
                 const int n_blk = ti.n;
                 const int m_blk = ti.m * (CL2 ? CLM : 1) + (int)crank;
+                if constexpr (BRES == 2) {  // one halo block per tile: pixels (x0-1 .. x0+14) x (y0-1 .. y0+16), zero fill = padding
+                    const int hx0 = (m_blk % p.conv_tiles_w) * p.conv_TW;
+                    const int hy0 = ((m_blk / p.conv_tiles_w) % p.conv_tiles_h) * p.conv_TH;
+                    const int hb = m_blk / (p.conv_tiles_w * p.conv_tiles_h);
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_expect_tx(&full_bar[s], HALO_BYTES);
+                    tma_load_4d(ring + s * STAGE_BYTES, &tmA, &full_bar[s], 0, hx0 - 1, hy0 - 1, hb);
+                    if (++s == STAGES) s = 0, ph ^= 1;
+                    continue;
+                }
                 const int ks = ti.ks;
                 const int kb0 = ks * p.kb_per_split;
                 const int kb1 = min(kb0 + p.kb_per_split, p.num_k_blocks);
@@ -719,7 +752,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 }
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[s], ph ^ 1);
-                    uint8_t* sa = smem + s * STAGE_BYTES;
+                    uint8_t* sa = ring + s * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     if (!G2) mbar_expect_tx(&full_bar[s], STAGE_BYTES);
                     else if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * STAGE_BYTES);  // both CTAs' bytes land here
@@ -745,7 +778,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
                         tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
                     }
-                    if (G2) {  // my half of B stays in MY shared memory: the pair's MMA reads both halves
+                    if constexpr (BRES != 0) {
+                        // weights are resident
+                    } else if (G2) {  // my half of B stays in MY shared memory: the pair's MMA reads both halves
                         if (!p.b_mn) {
                             tma_load_2d_g2(sb, &tmB, lbar, k0, n0 + (int)crank * (BN / 2));
                         } else {
@@ -783,6 +818,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int as = 0;
             uint32_t aph = 0;
             TileIter ti(work_id, work_stride, p.num_n_blocks, p.num_m_blocks);
+            if constexpr (BRES != 0) {
+                mbar_wait(bres_bar, 0);
+                tc_fence_after();
+            }
             for (int t = work_id; t < num_tiles; t += work_stride, ti.next()) {
                 const int ks = ti.ks;
                 const int kb0 = ks * p.kb_per_split;
@@ -790,11 +829,34 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 mbar_wait(&tempty_bar[as], aph ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * ACC_STRIDE;
-                for (int kb = kb0; kb < kb1; ++kb) {
+                if constexpr (BRES == 2) {  // nine taps = nine row-shifted windows of the halo block, K = 64 each
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
-                    const uint32_t a_base = smem_u32(smem + s * STAGE_BYTES);
-                    const uint32_t b_base = a_base + A_BYTES;
+                    const uint32_t a_base = smem_u32(ring + s * STAGE_BYTES);
+                    const uint32_t w_base = smem_u32(smem);
+                    const uint32_t bo_on = p.halo_bo;
+#pragma unroll
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const int dy = tap / 3, dx = tap % 3;
+#pragma unroll
+                        for (int j = 0; j < BK / 16; ++j) {
+                            // 8-row groups = 8 consecutive pixels of one tile row (halo row pitch 16 pixels = 2048 B = SBO); the
+                            // dx shift starts the group dx 128-byte rows into the swizzle pattern (base offset = dx)
+                            const uint64_t ad = umma_desc_sw128(a_base + dy * (HALO_W * 128) + dx * 128 + j * 32, 0, HALO_W * 128) |
+                                                ((uint64_t)(bo_on ? dx : 0) << 49);
+                            const uint64_t bd = umma_desc_sw128(w_base + tap * (BN * BK * 2) + j * 32, 0, 1024);
+                            if (p.dbg & 8) continue;
+                            umma_bf16_ss(d_tmem, ad, bd, idesc, (tap > 0 || j > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[s]);
+                    if (++s == STAGES) s = 0, ph ^= 1;
+                }
+                for (int kb = kb0; BRES != 2 && kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_base = smem_u32(ring + s * STAGE_BYTES);
+                    const uint32_t b_base = BRES ? smem_u32(smem) + kb * (BN * BK * 2) : a_base + A_BYTES;
 #pragma unroll
                     for (int j = 0; j < BK / 16; ++j) {
                         const uint64_t ad = p.a_mn ? umma_desc_sw128(a_base + j * 2048, 8192, 1024)
@@ -905,14 +967,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
 }
 
-template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0, bool G2 = false>
+template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0, bool G2 = false, int BRES = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream,
                        const CUtensorMap* tmO = nullptr, const CUtensorMap* tmO2 = nullptr) {
-    constexpr int smem_bytes = STAGES * (A_BYTES + (G2 ? BN / 2 : BN) * BK * 2) + NUM_EPI_WARPS * STG_FLOATS * 4 * (FAST == 6 ? 2 : 1) +
-                               (FAST ? NUM_EPI_WARPS * 256 + 256 : 1024 + 256);
+    constexpr int stage_bytes = BRES == 2 ? HALO_BYTES : (BRES == 1 ? A_BYTES : A_BYTES + (G2 ? BN / 2 : BN) * BK * 2);
+    constexpr int smem_bytes = (BRES ? BRES_KB * BN * BK * 2 : 0) + STAGES * stage_bytes +
+                               NUM_EPI_WARPS * STG_FLOATS * 4 * (FAST == 6 ? 2 : 1) + (FAST ? NUM_EPI_WARPS * 256 + 256 : 1024 + 256);
+    static_assert(smem_bytes <= 232448, "shared memory budget");
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>,
+        VTP_CUDA(cudaFuncSetAttribute(gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2, BRES>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         configured = true;
     }
@@ -935,7 +999,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = smem_bytes;
     cfg.stream = stream;
-    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2>, tmA, tmB, tmO ? *tmO : tmA,
+    VTP_CUDA(cudaLaunchKernelEx(&cfg, gemm_kernel<BN, STAGES, ACT, PS, CL2, MINB, FAST, G2, BRES>, tmA, tmB, tmO ? *tmO : tmA,
                                 tmO2 ? *tmO2 : tmA, p));
     return VTP_OK;
 }
@@ -982,7 +1046,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     int BN = (pad256 * 8 <= pad128 * 9) ? 256 : 128;  // accept <= 12.5 % padding for the higher-intensity tile
     // 2-CTA multicast variant whenever there are at least two m-blocks (odd counts are padded with an all-OOB tile)
     const bool allow_cl2 = getenv("VTP_GEMM_NO_CLUSTER") == nullptr;
-    const bool cl2 = allow_cl2 && ceil_div(a->M, BM) >= 2 && !(conv && getenv("VTP_GEMM_CONV_NO_CLUSTER"));
+    bool cl2 = allow_cl2 && ceil_div(a->M, BM) >= 2 && !(conv && getenv("VTP_GEMM_CONV_NO_CLUSTER"));
     // cta_group::2 (256 x BN pair tiles) wherever the 2-CTA cluster applies
     // measured (tools/gemm_diag.py): within 3 % of the TMA-multicast variant, slightly behind on every shape (both are
     // bound by L2->SM reads, which the two variants issue identically), so it is opt-in
@@ -1014,6 +1078,14 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
             if (eff > best + 0.02) best = eff, split_k = sp;
         }
     }
+    // 64 -> 64-channel convs (VGG conv1_2 forward and its dgrad): resident weights (1) + halo-block A operand (2), see gemm_kernel
+    int bres = 0;
+    if (conv && fast && a->conv_C == 64 && a->N == 64 && !a->b_mn_major && !g2) {
+        bres = getenv("VTP_GEMM_CONV_BRES") ? atoi(getenv("VTP_GEMM_CONV_BRES")) : VTP_CONV_BRES_DEFAULT;
+        if (bres < 0 || bres > 2) bres = 0;
+        if (bres == 2 && a->conv_W % 8 != 0) bres = 1;
+        if (bres) BN = 64, cl2 = false;
+    }
     const int two_max_kb = getenv("VTP_GEMM_2PERSM_MAXKB") ? atoi(getenv("VTP_GEMM_2PERSM_MAXKB")) : 16;
     const bool short_bn128 = getenv("VTP_GEMM_SHORTK_BN128") != nullptr;
     if (short_bn128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1 && a->conv_C == 0) BN = 128;
@@ -1041,13 +1113,14 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2), p.ldo2 = a->ldo2;
     p.mask_pos = reinterpret_cast<const __nv_bfloat16*>(a->mask_pos), p.ldm = a->ldm;
     p.dbg = getenv("VTP_GEMM_DBG") ? atoi(getenv("VTP_GEMM_DBG")) : 0;
+    p.halo_bo = getenv("VTP_GEMM_HALO_BO") ? atoi(getenv("VTP_GEMM_HALO_BO")) : 1;
 
 
     CUtensorMap tmA, tmB;
     if (conv) {
         const int W = a->conv_W, H = a->conv_H, Cc = a->conv_C, Bimg = a->M / (H * W);
         p.conv_C = Cc, p.conv_H = H, p.conv_W = W, p.conv_B = Bimg;
-        p.conv_TW = (W % 16 == 0) ? 16 : (W % 8 == 0 ? 8 : 4);
+        p.conv_TW = bres == 2 ? 8 : ((W % 16 == 0) ? 16 : (W % 8 == 0 ? 8 : 4));
         p.conv_TH = 128 / p.conv_TW;
         p.conv_tiles_w = W / p.conv_TW, p.conv_tiles_h = ceil_div(H, p.conv_TH);
         p.num_m_blocks = Bimg * p.conv_tiles_h * p.conv_tiles_w;
@@ -1055,6 +1128,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         uint64_t dims[4] = {(uint64_t)Cc, (uint64_t)W, (uint64_t)H, (uint64_t)Bimg};
         uint64_t strides[3] = {(uint64_t)Cc * 2, (uint64_t)W * Cc * 2, (uint64_t)H * W * Cc * 2};
         uint32_t box[4] = {64, (uint32_t)p.conv_TW, (uint32_t)p.conv_TH, 1};
+        if (bres == 2) box[1] = HALO_W, box[2] = HALO_H;  // the tile's pixels plus a one-pixel border (16 wide: 2048-byte rows)
         int rc = make_tmap_bf16(&tmA, a->A, 4, dims, strides, box);
         if (rc) return rc;
     } else {
@@ -1124,6 +1198,15 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         }
         if (rc) return rc;
         const int mode = a->mask_pos ? 5 : (a->out_dtype == VTP_F32 ? 3 : 1) + (a->resid ? 1 : 0);
+        if (bres) {  // conv, 64 -> 64 channels (mode 1 or 5 by construction of `fast`)
+#define VTP_BRES_CFG(ACT_, MODE_)                                                                                       \
+    return bres == 2 ? launch_gemm<64, 3, ACT_, false, false, 1, MODE_, false, 2>(tmA, tmB, p, stream, &tmO)            \
+                     : launch_gemm<64, 7, ACT_, false, false, 1, MODE_, false, 1>(tmA, tmB, p, stream, &tmO)
+            if (mode == 5) VTP_BRES_CFG(VTP_ACT_NONE, 5);
+            if (a->act == VTP_ACT_RELU) VTP_BRES_CFG(VTP_ACT_RELU, 1);
+            VTP_BRES_CFG(VTP_ACT_NONE, 1);
+#undef VTP_BRES_CFG
+        }
         if (mode == 5) {  // LPIPS dgrad with the ReLU mask: bf16 out, no bias / activation
             if (cl2)
                 return (BN == 256) ? launch_gemm<256, 4, VTP_ACT_NONE, false, true, 1, 5>(tmA, tmB, p, stream, &tmO)
