@@ -25,7 +25,7 @@ static constexpr int BRES_KB = 9;                    // resident k-blocks of the
 static constexpr int HALO_W = 16, HALO_H = 18;       // halo block of the BRES == 2 form: 18 rows of 16 pixels (tile 16 x 8)
 static constexpr int HALO_BYTES = HALO_W * HALO_H * BK * 2;
 #ifndef VTP_CONV_BRES_DEFAULT
-#define VTP_CONV_BRES_DEFAULT 0  // decided by measurement (profiles/): 0 off, 1 resident weights, 2 + halo block
+#define VTP_CONV_BRES_DEFAULT 2  // measured (profiles/r2_conv_halo.md): conv1_2 603 -> 357 (1) -> 205 us (2); 0 = off
 #endif
 static constexpr int NUM_THREADS = 320;  // TMA warp + MMA warp + 8 epilogue warps
 
@@ -51,7 +51,6 @@ struct GemmDev {
     int conv_C, conv_H, conv_W, conv_TW, conv_TH, conv_tiles_h, conv_tiles_w, conv_B;
     const __nv_bfloat16* mask_pos;  // optional: out *= (mask_pos[row][col] > 0)   (ReLU backward in the dgrad epilogue)
     int ldm;
-    int halo_bo;  // BRES == 2: set the descriptor base-offset field to the row shift (diagnostic switch)
     int dbg;  // DIAG bits: 1 no global stores, 2 no tmem ld, 4 no epilogue work, 8 no MMA issue
 };
 
@@ -692,7 +691,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (FAST == 6) tma_prefetch_desc(&tmO2);
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], (CL2 && !G2) ? CLM : 1);
         for (int s = 0; s < 2; ++s)
-            mbar_init(&tfull_bar[s], 1), mbar_init(&tempty_bar[s], G2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS);
+            mbar_init(&tfull_bar[s], 1),
+                mbar_init(&tempty_bar[s], BRES ? NUM_EPI_WARPS / 2 : (G2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS));
         mbar_init(bres_bar, 1);
         fence_barrier_init();
     }
@@ -834,16 +834,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(ring + s * STAGE_BYTES);
                     const uint32_t w_base = smem_u32(smem);
-                    const uint32_t bo_on = p.halo_bo;
 #pragma unroll
                     for (int tap = 0; tap < 9; ++tap) {
                         const int dy = tap / 3, dx = tap % 3;
 #pragma unroll
                         for (int j = 0; j < BK / 16; ++j) {
-                            // 8-row groups = 8 consecutive pixels of one tile row (halo row pitch 16 pixels = 2048 B = SBO); the
-                            // dx shift starts the group dx 128-byte rows into the swizzle pattern (base offset = dx)
-                            const uint64_t ad = umma_desc_sw128(a_base + dy * (HALO_W * 128) + dx * 128 + j * 32, 0, HALO_W * 128) |
-                                                ((uint64_t)(bo_on ? dx : 0) << 49);
+                            // 8-row groups = 8 consecutive pixels of one tile row (halo row pitch 16 pixels = 2048 B = SBO).  The dx
+                            // shift starts each group dx 128-byte rows into the 1024-byte swizzle pattern; the descriptor's
+                            // base-offset field stays 0: the 128B swizzle is a function of the absolute shared-memory address
+                            // bits (measured: base offset = dx gives wrong products, 0 is exact — profiles/r2_conv_halo.md)
+                            const uint64_t ad = umma_desc_sw128(a_base + dy * (HALO_W * 128) + dx * 128 + j * 32, 0, HALO_W * 128);
                             const uint64_t bd = umma_desc_sw128(w_base + tap * (BN * BK * 2) + j * 32, 0, 1024);
                             if (p.dbg & 8) continue;
                             umma_bf16_ss(d_tmem, ad, bd, idesc, (tap > 0 || j > 0) ? 1u : 0u);
@@ -900,6 +900,15 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 uint8_t* st2 = FAST == 6 ? reinterpret_cast<uint8_t*>(stg_base) + (NUM_EPI_WARPS + (warp - 2)) * STG_FLOATS * 4 : st1;
                 fast_swiglu_tile<BN, FAST, G2>(p, &tmO, &tmO2, st1, st2, bias_base + (warp - 2) * 64, lane, q, hsel, taddr, m_blk,
                                                n0, &tfull_bar[as], aph, &tempty_bar[as]);
+                if (++as == 2) as = 0, aph ^= 1;
+                continue;
+            }
+            if constexpr (BRES != 0) {
+                // 64-wide tiles are one column chunk: instead of idling every second warp, the two warps of a lane quarter
+                // take alternate tiles (warp group hsel owns accumulator buffer hsel; 4 arrivals free a buffer)
+                if (hsel == as)
+                    fast_epilogue_tile<BN, ACT, FAST, G2>(p, &tmO, reinterpret_cast<uint8_t*>(stg), bias_base + (warp - 2) * 64,
+                                                          lane, q, 0, taddr, m_blk, n0, &tfull_bar[as], aph, &tempty_bar[as]);
                 if (++as == 2) as = 0, aph ^= 1;
                 continue;
             }
@@ -1113,7 +1122,6 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     p.out2 = reinterpret_cast<__nv_bfloat16*>(a->out2), p.ldo2 = a->ldo2;
     p.mask_pos = reinterpret_cast<const __nv_bfloat16*>(a->mask_pos), p.ldm = a->ldm;
     p.dbg = getenv("VTP_GEMM_DBG") ? atoi(getenv("VTP_GEMM_DBG")) : 0;
-    p.halo_bo = getenv("VTP_GEMM_HALO_BO") ? atoi(getenv("VTP_GEMM_HALO_BO")) : 1;
 
 
     CUtensorMap tmA, tmB;
