@@ -52,19 +52,27 @@ def test_conv_mode_gemm_matches_conv2d():
 
 
 @pytest.mark.parametrize("variant", ["default", "VTP_GEMM_CONV_NO_FAST", "VTP_GEMM_CONV_NO_CLUSTER", "VTP_GEMM_CONV_BRES=0",
-                                     "VTP_GEMM_CONV_BRES=1", "VTP_GEMM_CONV_BRES=2"])
+                                     "VTP_GEMM_CONV_BRES=1", "VTP_GEMM_CONV_BRES=2", "VTP_GEMM_CONV_HALO=0",
+                                     "VTP_GEMM_CONV_HALO=1"])
 @pytest.mark.parametrize("B,H,W,Ci,Co,mask", [(1, 24, 16, 64, 64, False), (3, 8, 8, 128, 256, True), (2, 32, 32, 64, 64, True),
                                               (5, 16, 16, 256, 512, False), (1, 8, 8, 512, 512, True),
                                               (3, 40, 24, 64, 64, False), (2, 20, 12, 64, 64, True), (3, 256, 256, 64, 64, False),
-                                              (3, 256, 256, 64, 64, True)])
+                                              (3, 256, 256, 64, 64, True), (2, 32, 32, 64, 128, False), (2, 32, 32, 128, 64, True),
+                                              (3, 40, 24, 128, 128, True), (2, 128, 128, 128, 128, False), (1, 24, 16, 256, 128, True),
+                                              (2, 128, 128, 128, 64, True), (1, 16, 16, 128, 64, False)])
 def test_conv_mode_variants(monkeypatch, variant, B, H, W, Ci, Co, mask):
     """Implicit 3x3 conv GEMM through the TMA-store epilogue (4-D NHWC tensor map) on clustered / single-CTA kernels:
     odd tile counts (padded pair tile), Cout < tile width, bias+ReLU forward form and masked dgrad form; the 64 -> 64
     channel shapes also through the resident-weight (BRES=1) and halo-block (BRES=2) forms (many tiles per CTA at 256 x 256,
-    ragged heights, W = 12 falls back from the halo form)."""
-    if "=" in variant:
+    ragged heights, W = 12 falls back from the halo form); the other shapes with tiles <= 128 wide through the two-ring halo
+    form (HALO=1: one to four 64-channel blocks, 64- and 128-wide tiles, odd pair counts)."""
+    if "BRES=" in variant:
         if (Ci, Co) != (64, 64):
             pytest.skip("resident-weight forms only exist for 64 -> 64 channels")
+        monkeypatch.setenv(*variant.split("="))
+    elif "HALO=" in variant:
+        if (Ci, Co) == (64, 64) or Co > 128:
+            pytest.skip("two-ring halo form: tiles <= 128 wide, not the 64 -> 64 shapes")
         monkeypatch.setenv(*variant.split("="))
     elif variant != "default":
         monkeypatch.setenv(variant, "1")

@@ -24,6 +24,9 @@ static constexpr int A_BYTES = BM * BK * 2;
 static constexpr int BRES_KB = 9;                    // resident k-blocks of the B-resident conv form (3 x 3 taps x 64 channels)
 static constexpr int HALO_W = 16, HALO_H = 18;       // halo block of the BRES == 2 form: 18 rows of 16 pixels (tile 16 x 8)
 static constexpr int HALO_BYTES = HALO_W * HALO_H * BK * 2;
+#ifndef VTP_CONV_HALO_DEFAULT
+#define VTP_CONV_HALO_DEFAULT 0  // two-ring halo form for the other conv shapes with tiles <= 128 wide (decided by measurement)
+#endif
 #ifndef VTP_CONV_BRES_DEFAULT
 #define VTP_CONV_BRES_DEFAULT 2  // measured (profiles/r2_conv_halo.md): conv1_2 603 -> 357 (1) -> 205 us (2); 0 = off
 #endif
@@ -644,6 +647,9 @@ __device__ __forceinline__ void fast_epilogue_tile(const GemmDev& p, const CUten
 //   1: the whole [BN x 9*64] weight matrix (72 KB) is loaded ONCE per CTA and stays resident; the ring carries only A;
 //   2: additionally the A operand is loaded once per tile as a (16+2) x 16-pixel HALO block (36 KB; tile = 16 rows x 8 pixels)
 //      and the nine taps are row-shifted UMMA descriptors into it (start + dy*2048 + dx*128, SBO = 2048): 8x less feed.
+//   3: any channel count (multiple of 64) and tile width: TWO rings — a 2-stage ring of halo blocks (one per 64-channel block
+//      of the tile, used by nine taps) and a STAGES-deep ring of [BN x 64] weight k-blocks (pair multicast as before), k-order
+//      (channel block, tap).  A-operand feed per tile drops from 9 x 16 KB to 36 KB per 64 channels.
 template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST, bool G2, int BRES = 0>
 // 10 warps -> 3 on one scheduler: 3*32*R <= 16384 registers per SM sub-partition caps R at 168 (MINB = 1).
 // MINB = 2 (short-K shapes): two CTAs per SM with a 2-stage ring double the epilogue warps per SM at ~100 registers.
@@ -653,11 +659,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     static_assert(!G2 || CL2, "cta_group::2 needs the 2-CTA cluster");
     constexpr int CLM = 2;                                      // CTAs per cluster (along M) sharing one B tile
     constexpr uint16_t MC_MASK = (uint16_t)((1u << CLM) - 1u);  // every CTA of the cluster
-    static_assert(BRES == 0 || (!CL2 && !G2 && FAST != 0 && BN == 64), "resident-B conv form: 64-wide lean-epilogue tiles");
-    constexpr int A_ST_BYTES = BRES == 2 ? HALO_BYTES : A_BYTES;
-    constexpr int B_BYTES = BRES ? 0 : (G2 ? BN / 2 : BN) * BK * 2;
+    constexpr bool RESB = BRES == 1 || BRES == 2;  // resident weights
+    static_assert(!RESB || (!CL2 && !G2 && FAST != 0 && BN == 64), "resident-B conv form: 64-wide lean-epilogue tiles");
+    static_assert(BRES != 3 || (!G2 && FAST != 0), "two-ring halo conv form: lean epilogue, no cta_group::2");
+    constexpr bool ALT_EPI = BRES != 0 && BN == 64;  // one column chunk per tile: the epilogue warp groups alternate tiles
+    constexpr int AST = 2;                           // BRES == 3: halo-block stages
+    constexpr int A_ST_BYTES = BRES == 2 ? HALO_BYTES : (BRES == 3 ? 0 : A_BYTES);
+    constexpr int B_BYTES = RESB ? 0 : (G2 ? BN / 2 : BN) * BK * 2;
     constexpr int STAGE_BYTES = A_ST_BYTES + B_BYTES;
-    constexpr int BRES_BYTES = BRES ? BRES_KB * BN * BK * 2 : 0;  // resident weights in front of the ring
+    // in front of the ring: the resident weights (1, 2) or the halo-block ring (3)
+    constexpr int BRES_BYTES = RESB ? BRES_KB * BN * BK * 2 : (BRES == 3 ? AST * HALO_BYTES : 0);
     constexpr int ACC_STRIDE = BN == 192 ? 256 : BN;  // column distance of the two accumulator buffers
     constexpr uint32_t TMEM_COLS = 2 * ACC_STRIDE;    // 256 or 512 (power of two)
 
@@ -675,8 +686,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
-    uint64_t* bres_bar = tempty_bar + 2;  // BRES: the resident weights have landed
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+    uint64_t* bres_bar = tempty_bar + 2;  // BRES 1, 2: the resident weights have landed
+    uint64_t* afull_bar = bres_bar + 1;   // BRES 3: [AST] halo block landed
+    uint64_t* aempty_bar = afull_bar + 2; // BRES 3: [AST] halo block consumed by its nine taps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -692,8 +705,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int s = 0; s < STAGES; ++s) mbar_init(&full_bar[s], 1), mbar_init(&empty_bar[s], (CL2 && !G2) ? CLM : 1);
         for (int s = 0; s < 2; ++s)
             mbar_init(&tfull_bar[s], 1),
-                mbar_init(&tempty_bar[s], BRES ? NUM_EPI_WARPS / 2 : (G2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS));
+                mbar_init(&tempty_bar[s], ALT_EPI ? NUM_EPI_WARPS / 2 : (G2 ? 2 * NUM_EPI_WARPS : NUM_EPI_WARPS));
         mbar_init(bres_bar, 1);
+        for (int s = 0; s < 2; ++s) mbar_init(&afull_bar[s], 1), mbar_init(&aempty_bar[s], 1);
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -715,8 +729,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (lane == 0) {
             int s = 0;
             uint32_t ph = 0;
+            [[maybe_unused]] int sa_ = 0;
+            [[maybe_unused]] uint32_t aph_ = 0;
             TileIter ti(work_id, work_stride, p.num_n_blocks, p.num_m_blocks);
-            if constexpr (BRES != 0) {  // the whole weight matrix, once (N <= BN: rows beyond N are zero-filled)
+            if constexpr (RESB) {  // the whole weight matrix, once (N <= BN: rows beyond N are zero-filled)
                 mbar_expect_tx(bres_bar, BRES_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < BRES_KB; ++kb) tma_load_2d(smem + kb * (BN * BK * 2), &tmB, bres_bar, kb * BK, 0);
@@ -732,6 +748,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     mbar_expect_tx(&full_bar[s], HALO_BYTES);
                     tma_load_4d(ring + s * STAGE_BYTES, &tmA, &full_bar[s], 0, hx0 - 1, hy0 - 1, hb);
                     if (++s == STAGES) s = 0, ph ^= 1;
+                    continue;
+                }
+                if constexpr (BRES == 3) {  // per 64-channel block: one halo block, then its nine [BN x 64] weight k-blocks
+                    const int hx0 = (m_blk % p.conv_tiles_w) * p.conv_TW;
+                    const int hy0 = ((m_blk / p.conv_tiles_w) % p.conv_tiles_h) * p.conv_TH;
+                    const int hb = m_blk / (p.conv_tiles_w * p.conv_tiles_h);
+                    const int n0h = n_blk * BN;
+                    for (int c0 = 0; c0 < p.conv_C; c0 += 64) {
+                        mbar_wait(&aempty_bar[sa_], aph_ ^ 1);
+                        mbar_expect_tx(&afull_bar[sa_], HALO_BYTES);
+                        tma_load_4d(smem + sa_ * HALO_BYTES, &tmA, &afull_bar[sa_], c0, hx0 - 1, hy0 - 1, hb);
+                        if (++sa_ == AST) sa_ = 0, aph_ ^= 1;
+#pragma unroll 1
+                        for (int tap = 0; tap < 9; ++tap) {
+                            mbar_wait(&empty_bar[s], ph ^ 1);
+                            mbar_expect_tx(&full_bar[s], STAGE_BYTES);  // the whole k-block (in a pair: both halves land here)
+                            uint8_t* sb = ring + s * STAGE_BYTES;
+                            const int k0 = tap * p.conv_C + c0;
+                            if (CL2)
+                                tma_load_2d_mc(sb + crank * (BN / CLM) * 128, &tmB, &full_bar[s], k0, n0h + (int)crank * (BN / CLM),
+                                               MC_MASK);
+                            else tma_load_2d(sb, &tmB, &full_bar[s], k0, n0h);
+                            if (++s == STAGES) s = 0, ph ^= 1;
+                        }
+                    }
                     continue;
                 }
                 const int ks = ti.ks;
@@ -778,7 +819,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                         tma_load_2d(sa, &tmA, &full_bar[s], m0, k0);
                         tma_load_2d(sa + 8192, &tmA, &full_bar[s], m0 + 64, k0);
                     }
-                    if constexpr (BRES != 0) {
+                    if constexpr (RESB) {
                         // weights are resident
                     } else if (G2) {  // my half of B stays in MY shared memory: the pair's MMA reads both halves
                         if (!p.b_mn) {
@@ -818,10 +859,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             int as = 0;
             uint32_t aph = 0;
             TileIter ti(work_id, work_stride, p.num_n_blocks, p.num_m_blocks);
-            if constexpr (BRES != 0) {
+            if constexpr (RESB) {
                 mbar_wait(bres_bar, 0);
                 tc_fence_after();
             }
+            [[maybe_unused]] int sa_ = 0;
+            [[maybe_unused]] uint32_t aph_ = 0;
             for (int t = work_id; t < num_tiles; t += work_stride, ti.next()) {
                 const int ks = ti.ks;
                 const int kb0 = ks * p.kb_per_split;
@@ -852,11 +895,37 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                     umma_commit(&empty_bar[s]);
                     if (++s == STAGES) s = 0, ph ^= 1;
                 }
-                for (int kb = kb0; BRES != 2 && kb < kb1; ++kb) {
+                if constexpr (BRES == 3) {
+                    for (int c0 = 0; c0 < p.conv_C; c0 += 64) {
+                        mbar_wait(&afull_bar[sa_], aph_);
+                        tc_fence_after();
+                        const uint32_t a_base = smem_u32(smem + sa_ * HALO_BYTES);
+#pragma unroll
+                        for (int tap = 0; tap < 9; ++tap) {
+                            const int dy = tap / 3, dx = tap % 3;
+                            mbar_wait(&full_bar[s], ph);
+                            tc_fence_after();
+                            const uint32_t b_base = smem_u32(ring + s * STAGE_BYTES);
+#pragma unroll
+                            for (int j = 0; j < BK / 16; ++j) {
+                                const uint64_t ad = umma_desc_sw128(a_base + dy * (HALO_W * 128) + dx * 128 + j * 32, 0, HALO_W * 128);
+                                const uint64_t bd = umma_desc_sw128(b_base + j * 32, 0, 1024);
+                                if (p.dbg & 8) continue;
+                                umma_bf16_ss(d_tmem, ad, bd, idesc, (c0 > 0 || tap > 0 || j > 0) ? 1u : 0u);
+                            }
+                            if (CL2) umma_commit_mc(&empty_bar[s], MC_MASK);   // the peer multicasts into my slot too
+                            else umma_commit(&empty_bar[s]);
+                            if (++s == STAGES) s = 0, ph ^= 1;
+                        }
+                        umma_commit(&aempty_bar[sa_]);  // local: the halo ring is not shared
+                        if (++sa_ == AST) sa_ = 0, aph_ ^= 1;
+                    }
+                }
+                for (int kb = kb0; BRES < 2 && kb < kb1; ++kb) {
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint32_t a_base = smem_u32(ring + s * STAGE_BYTES);
-                    const uint32_t b_base = BRES ? smem_u32(smem) + kb * (BN * BK * 2) : a_base + A_BYTES;
+                    const uint32_t b_base = RESB ? smem_u32(smem) + kb * (BN * BK * 2) : a_base + A_BYTES;
 #pragma unroll
                     for (int j = 0; j < BK / 16; ++j) {
                         const uint64_t ad = p.a_mn ? umma_desc_sw128(a_base + j * 2048, 8192, 1024)
@@ -903,7 +972,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                 if (++as == 2) as = 0, aph ^= 1;
                 continue;
             }
-            if constexpr (BRES != 0) {
+            if constexpr (ALT_EPI) {
                 // 64-wide tiles are one column chunk: instead of idling every second warp, the two warps of a lane quarter
                 // take alternate tiles (warp group hsel owns accumulator buffer hsel; 4 arrivals free a buffer)
                 if (hsel == as)
@@ -979,8 +1048,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 template <int BN, int STAGES, int ACT, bool PS, bool CL2, int MINB, int FAST = 0, bool G2 = false, int BRES = 0>
 static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmDev& p, cudaStream_t stream,
                        const CUtensorMap* tmO = nullptr, const CUtensorMap* tmO2 = nullptr) {
-    constexpr int stage_bytes = BRES == 2 ? HALO_BYTES : (BRES == 1 ? A_BYTES : A_BYTES + (G2 ? BN / 2 : BN) * BK * 2);
-    constexpr int smem_bytes = (BRES ? BRES_KB * BN * BK * 2 : 0) + STAGES * stage_bytes +
+    constexpr int stage_bytes = BRES == 2 ? HALO_BYTES
+                                : (BRES == 1 ? A_BYTES : (BRES == 3 ? BN * BK * 2 : A_BYTES + (G2 ? BN / 2 : BN) * BK * 2));
+    constexpr int front_bytes = (BRES == 1 || BRES == 2) ? BRES_KB * BN * BK * 2 : (BRES == 3 ? 2 * HALO_BYTES : 0);
+    constexpr int smem_bytes = front_bytes + STAGES * stage_bytes +
                                NUM_EPI_WARPS * STG_FLOATS * 4 * (FAST == 6 ? 2 : 1) + (FAST ? NUM_EPI_WARPS * 256 + 256 : 1024 + 256);
     static_assert(smem_bytes <= 232448, "shared memory budget");
     static bool configured = false;
@@ -1095,6 +1166,12 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         if (bres == 2 && a->conv_W % 8 != 0) bres = 1;
         if (bres) BN = 64, cl2 = false;
     }
+    // every other conv shape with tiles <= 128 wide: two-ring halo form (3), pair multicast of the weights kept
+    bool halo3 = false;
+    if (conv && fast && !bres && !g2 && cl2 && a->conv_W % 8 == 0 && !a->b_mn_major && BN == 128) {
+        halo3 = (getenv("VTP_GEMM_CONV_HALO") ? atoi(getenv("VTP_GEMM_CONV_HALO")) : VTP_CONV_HALO_DEFAULT) != 0;
+        if (halo3 && a->N <= 64) BN = 64;
+    }
     const int two_max_kb = getenv("VTP_GEMM_2PERSM_MAXKB") ? atoi(getenv("VTP_GEMM_2PERSM_MAXKB")) : 16;
     const bool short_bn128 = getenv("VTP_GEMM_SHORTK_BN128") != nullptr;
     if (short_bn128 && ceil_div(a->K, BK) <= two_max_kb && split_k == 1 && a->conv_C == 0) BN = 128;
@@ -1128,7 +1205,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
     if (conv) {
         const int W = a->conv_W, H = a->conv_H, Cc = a->conv_C, Bimg = a->M / (H * W);
         p.conv_C = Cc, p.conv_H = H, p.conv_W = W, p.conv_B = Bimg;
-        p.conv_TW = bres == 2 ? 8 : ((W % 16 == 0) ? 16 : (W % 8 == 0 ? 8 : 4));
+        p.conv_TW = (bres == 2 || halo3) ? 8 : ((W % 16 == 0) ? 16 : (W % 8 == 0 ? 8 : 4));
         p.conv_TH = 128 / p.conv_TW;
         p.conv_tiles_w = W / p.conv_TW, p.conv_tiles_h = ceil_div(H, p.conv_TH);
         p.num_m_blocks = Bimg * p.conv_tiles_h * p.conv_tiles_w;
@@ -1136,7 +1213,7 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         uint64_t dims[4] = {(uint64_t)Cc, (uint64_t)W, (uint64_t)H, (uint64_t)Bimg};
         uint64_t strides[3] = {(uint64_t)Cc * 2, (uint64_t)W * Cc * 2, (uint64_t)H * W * Cc * 2};
         uint32_t box[4] = {64, (uint32_t)p.conv_TW, (uint32_t)p.conv_TH, 1};
-        if (bres == 2) box[1] = HALO_W, box[2] = HALO_H;  // the tile's pixels plus a one-pixel border (16 wide: 2048-byte rows)
+        if (bres == 2 || halo3) box[1] = HALO_W, box[2] = HALO_H;  // the tile's pixels plus a one-pixel border (16 wide: 2048-byte rows)
         int rc = make_tmap_bf16(&tmA, a->A, 4, dims, strides, box);
         if (rc) return rc;
     } else {
@@ -1214,6 +1291,15 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
             if (a->act == VTP_ACT_RELU) VTP_BRES_CFG(VTP_ACT_RELU, 1);
             VTP_BRES_CFG(VTP_ACT_NONE, 1);
 #undef VTP_BRES_CFG
+        }
+        if (halo3) {
+#define VTP_HALO_CFG(ACT_, MODE_)                                                                                       \
+    return BN == 64 ? launch_gemm<64, 8, ACT_, false, true, 1, MODE_, false, 3>(tmA, tmB, p, stream, &tmO)              \
+                    : launch_gemm<128, 6, ACT_, false, true, 1, MODE_, false, 3>(tmA, tmB, p, stream, &tmO)
+            if (mode == 5) VTP_HALO_CFG(VTP_ACT_NONE, 5);
+            if (a->act == VTP_ACT_RELU) VTP_HALO_CFG(VTP_ACT_RELU, 1);
+            VTP_HALO_CFG(VTP_ACT_NONE, 1);
+#undef VTP_HALO_CFG
         }
         if (mode == 5) {  // LPIPS dgrad with the ReLU mask: bf16 out, no bias / activation
             if (cl2)
