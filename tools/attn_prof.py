@@ -40,6 +40,28 @@ os.environ["VTP_ATTN_FWD8"] = "1"         # two row threads per query row (attn_
 u8 = t(fwd)
 os.environ["VTP_ATTN_FWD8"] = "0"
 del os.environ["VTP_ATTN_FWD_PIPE"]
+# TMA-store epilogues (round 2): same bits expected, time each setting
+def with_env(k, v, fn):
+    old = os.environ.get(k)
+    os.environ[k] = v
+    try:
+        return fn()
+    finally:
+        if old is None:
+            del os.environ[k]
+        else:
+            os.environ[k] = old
+for v in ("0", "1"):
+    uf_v = with_env("VTP_ATTN_PIPE_TSO", v, lambda: t(fwd))
+    o_v, lse_v = o.clone(), lse.clone()
+    ub_v = with_env("VTP_ATTN_BWD_TSO", v, lambda: t(bwd))
+    dq_v = dqkv.clone()
+    ub_np = with_env("VTP_ATTN_BWD_TSO", v, lambda: with_env("VTP_ATTN_BWD_NO_PREFETCH", "1", lambda: t(bwd)))
+    if v == "0":
+        o_0, lse_0, dq_0 = o_v, lse_v, dq_v
+    print(f"TSO={v}: fwd {uf_v:.1f} us  bwd {ub_v:.1f} us (without the O-row prefetch {ub_np:.1f} us)"
+          + ("" if v == "0" else f"   max|d o| {(o_v.float() - o_0.float()).abs().max().item():.3e}  max|d lse| {(lse_v - lse_0).abs().max().item():.3e}"
+             f"  max|d dqkv| {(dq_v.float() - dq_0.float()).abs().max().item():.3e}"), flush=True)
 print(f"fwd rows4 (one tile per CTA): {u4:.1f} us, rows8: {u8:.1f} us; default is x{u4 / uf:.2f} of rows4, max |default - rows4| = {d4:.3e}")
 print(f"B={B} T={T} H={H}: fwd {uf:.1f} us ({fl / uf / 1e6:.0f} TFLOP/s, {(M * 4 * D * 2) / uf / 1e3:.0f} GB/s)   "
       f"bwd {ub:.1f} us ({2.5 * fl / ub / 1e6:.0f} TFLOP/s, {(M * 8 * D * 2) / ub / 1e3:.0f} GB/s)")

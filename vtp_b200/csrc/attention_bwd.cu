@@ -20,6 +20,9 @@
 
 namespace vtp {
 
+#ifndef VTP_ATTN_BWD_TSO_DEFAULT
+#define VTP_ATTN_BWD_TSO_DEFAULT 0  // TMA-store row epilogues of the FULL path: decided by measurement
+#endif
 static constexpr int AB_THREADS = 320;  // 8 row warps (2 per scheduler) + TMA/MMA warp + cls warp
 static constexpr int BQ = 0, BK_ = 32768, BV = 65536, BDO = 98304, BP = 131072, BDS = 163840, BX = 196608;
 // extras after BX: p0[264] | ds0[264] | dk0[64] | dv0[64] | pcol[2][128] | dscol[2][128] | barriers
@@ -39,6 +42,8 @@ struct AttnBwdDev {
     // packed mode (T <= 64): `pack` whole sequences share the 128-row tile, their prefix tokens (`rprefix` per sequence)
     // are ordinary rows / key columns (prefix == 0 above) and P, dS are masked block-diagonally
     int pack, rprefix;
+    int tso;       // FULL only: last-key-half dK/dV rows and the dQ rows leave through shared memory + one TMA store per warp
+    int prefetch;  // row threads pull their O rows (delta = dO.O) and lse towards L2/L1 before the tile loads are waited for
 };
 
 __device__ __forceinline__ float ex2f(float x) {  // ex2.approx.ftz: no denormal slow path (exp2f() costs 4 extra instr)
@@ -89,12 +94,34 @@ __device__ __forceinline__ void rope_bwd64(float (&g)[64], const __nv_bfloat16* 
     }
 }
 
+// bf16 row (64 values) of a warp's 32-row slab -> the warp's 4 KB staging tile (128-byte swizzle, as the tensor map expects),
+// then ONE TMA store of the [32 rows x 64 columns] box: replaces eight scattered 16-byte global stores per thread whose
+// drain stalled the row threads at the end of every CTA (profiles/ncu_attn_r2b warp-state samples)
+__device__ __forceinline__ void stage_store_row64(const CUtensorMap* tmap, uint8_t* warp_stage, int lane, const float (&f)[64], int x,
+                                                  int y) {
+    uint8_t* ob = warp_stage + lane * 128;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        uint4 w;
+        w.x = pack_bf16x2(f[c * 8], f[c * 8 + 1]), w.y = pack_bf16x2(f[c * 8 + 2], f[c * 8 + 3]);
+        w.z = pack_bf16x2(f[c * 8 + 4], f[c * 8 + 5]), w.w = pack_bf16x2(f[c * 8 + 6], f[c * 8 + 7]);
+        *reinterpret_cast<uint4*>(ob + ((c ^ (lane & 7)) << 4)) = w;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(tmap, warp_stage, x, y);
+        bulk_commit();
+    }
+}
+
 // FULL: HW == 256, no packing, no causal mask — every (query, key) pair of every step is valid, so the P / dS loop runs
 // without per-element predicates (ncu, profiles/ncu_attn_r2a.md: ~30 executed instructions per score element in the
 // generic loop, mostly mask predicates, selects and address arithmetic) and with hoisted swizzle offsets.
 template <bool FULL>
 __global__ void __launch_bounds__(AB_THREADS, 1)
-attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do, const AttnBwdDev p) {
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const __grid_constant__ CUtensorMap tm_dq, const AttnBwdDev p) {
     extern __shared__ __align__(1024) uint8_t smem[];
     if (smem_u32(smem) & 1023) __trap();
     float* p0 = reinterpret_cast<float*>(smem + BX + X_P0);
@@ -122,11 +149,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm_qkv);
         tma_prefetch_desc(&tm_do);
+        if (FULL && p.tso) tma_prefetch_desc(&tm_dq);
         mbar_init(&bar_ld[0], 1), mbar_init(&bar_ld[1], 1), mbar_init(bar_sdp, 1), mbar_init(bar_pds, 256);
         mbar_init(bar_mma2, 1), mbar_init(bar_accfree, 256), mbar_init(bar_cls, 1);
         fence_barrier_init();
     }
     if (threadIdx.x < 128) dk0[threadIdx.x & 63] = 0.f, dv0[threadIdx.x & 63] = 0.f;
+    if (p.prefetch && !p.pack && warp < 8) {
+        // warp-state samples (profiles/ncu_attn_r2b): ~10 % of the row threads' time was the first-touch latency of their
+        // O rows (one 128-byte line per row and head, straight from HBM) at the start of every CTA
+        const int rr = (warp & 3) * 32 + lane, tt = warp >> 2;   // group g = warp >> 2 prefetches query tile g
+        if (tt < nkt && 128 * tt + rr < HW)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.o + (row0 + prefix + 128 * tt + rr) * D + h * 64));
+    }
     if (warp == 8) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
@@ -361,6 +396,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 mbar_wait(bar_mma2, n & 1);
                 tc_fence_after();
                 const int kj = 128 * kh + r;
+                // last key half: the P / dS tiles are idle (their last MMAs have completed) and serve as store staging
+                const bool tso = FULL && p.tso && kh == nkt - 1;
                 uint32_t a0[32], a1[32];
                 float gq[64];
                 if (prefix > 0) mbar_wait(bar_cls, 0);
@@ -380,7 +417,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
                             for (int d = 0; d < 64; ++d) gq[d] += pc * f[d];
                         }
-                        store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + 2 * D + h * 64, gq);
+                        if (tso)
+                            stage_store_row64(&tm_dq, smem + BP + q4 * 4096, lane, gq, 2 * D + h * 64,
+                                              (int)(row0 + prefix) + 128 * kh + q4 * 32);
+                        else store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + 2 * D + h * 64, gq);
                     } else {
                         if (prefix > 0) {
                             float f[64];
@@ -391,7 +431,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                         }
                         const int pos = p.pack ? ptok - p.rprefix : kj;  // patch position (prefix tokens are not rotated)
                         if (p.rope_sin && pos >= 0) rope_bwd64(gq, p.rope_sin + (long)pos * 64, p.rope_cos + (long)pos * 64);
-                        store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + D + h * 64, gq);
+                        if (tso)
+                            stage_store_row64(&tm_dq, smem + BP + 16384 + q4 * 4096, lane, gq, D + h * 64,
+                                              (int)(row0 + prefix) + 128 * kh + q4 * 32);
+                        else store_row64(p.dqkv + (row0 + prefix + kj) * 3 * D + D + h * 64, gq);
                     }
                 }
             }
@@ -416,9 +459,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 }
                 const int pos = p.pack ? ptok - p.rprefix : qi;
                 if (p.rope_sin && pos >= 0) rope_bwd64(gq, p.rope_sin + (long)pos * 64, p.rope_cos + (long)pos * 64);
-                store_row64(p.dqkv + (row0 + prefix + qi) * 3 * D + h * 64, gq);
+                if (FULL && p.tso)
+                    stage_store_row64(&tm_dq, smem + BDS + g * 16384 + q4 * 4096, lane, gq, h * 64,
+                                      (int)(row0 + prefix) + 128 * t + q4 * 32);
+                else store_row64(p.dqkv + (row0 + prefix + qi) * 3 * D + h * 64, gq);
             }
         }
+        if (FULL && p.tso && lane == 0) bulk_wait0();  // my warp's row stores have left shared memory and are complete
         tc_fence_before();
     } else {
         // ---------------------------------------------------- warp 9: the cls query row (prefix == 1)
@@ -523,11 +570,22 @@ extern "C" int vtp_attention_bwd(const void* qkv, const void* o, const void* dou
     p.nkt = HW > 128 ? 2 : 1;
     p.scale = 0.125f, p.scale_log2 = 0.125f * 1.4426950408889634f;
     p.pack = 0, p.rprefix = prefix;
+    p.prefetch = getenv("VTP_ATTN_BWD_NO_PREFETCH") == nullptr;
+    {
+        const char* ts = getenv("VTP_ATTN_BWD_TSO");
+        p.tso = ts ? ts[0] != '0' : VTP_ATTN_BWD_TSO_DEFAULT;
+    }
     if (!causal && T <= 64 && B > 1 && getenv("VTP_ATTN_NO_PACK") == nullptr) {
         p.pack = 128 / T;
         p.prefix = 0, p.HW = T, p.nkt = 1;
     }
-    CUtensorMap tq, td;
+    CUtensorMap tq, td, tdq;
+    {   // dqkv [B*T][3D]: 32-row x 64-column boxes (one warp's rows of one head's dq / dk / dv)
+        uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)B * T}, strides[1] = {(uint64_t)3 * D * 2};
+        uint32_t box[2] = {64, 32};
+        int rc = make_tmap_bf16(&tdq, dqkv, 2, dims, strides, box);
+        if (rc) return rc;
+    }
     {
         uint64_t dims[2] = {(uint64_t)3 * D, (uint64_t)B * T}, strides[1] = {(uint64_t)3 * D * 2};
         uint32_t box[2] = {64, 128};
@@ -548,9 +606,9 @@ extern "C" int vtp_attention_bwd(const void* qkv, const void* o, const void* dou
     }
     const dim3 grid(H, p.pack ? ceil_div(B, p.pack) : B);
     if (p.HW == 256 && !p.pack && !p.causal && getenv("VTP_ATTN_BWD_GENERIC") == nullptr)
-        attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, p);
+        attn_bwd_kernel<true><<<grid, AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, tdq, p);
     else
-        attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, p);
+        attn_bwd_kernel<false><<<grid, AB_THREADS, AB_SMEM, (cudaStream_t)st>>>(tq, td, tdq, p);
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

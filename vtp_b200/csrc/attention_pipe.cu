@@ -31,6 +31,9 @@
 
 namespace vtp {
 
+#ifndef VTP_ATTN_TSO_DEFAULT
+#define VTP_ATTN_TSO_DEFAULT 0  // TMA-store output epilogue of the FULL path: decided by measurement
+#endif
 static constexpr int PIPE_THREADS = 384;
 static constexpr int P_KV = 0;                    // 2 stages x (K 32768 | V 32768)
 static constexpr int P_Q = 131072;                // Q0 16384 | Q1 16384
@@ -48,8 +51,14 @@ __device__ __forceinline__ uint32_t swz(int row, int col /* bf16 element 0..63 *
     return row * 128 + ((((col >> 3) ^ (row & 7)) << 4) | ((col & 7) << 1));
 }
 
-template <bool FULL>
-__global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm, const AttnDev p) {
+// TSO (FULL only; round 2, from the warp-state samples of profiles/ncu_attn_r2b: 29 % of the row threads' time sat in the
+// output epilogue — eight 16-byte global stores per thread, each warp instruction touching 32 different 128-byte lines —
+// and 13 % in the cls-key score waiting for its global loads): the normalised O row goes through the warp's own 4 KB of the
+// (by then idle) P buffer and leaves as ONE TMA store per warp; the cls key / value rows are prefetched into L1 at the top of the job.
+template <bool FULL, bool TSO>
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+attn_fwd_pipe_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tmo, const AttnDev p) {
+    static_assert(!TSO || FULL, "the TMA-store epilogue writes whole 128-row tiles");
     extern __shared__ __align__(1024) uint8_t smem[];
     if (smem_u32(smem) & 1023) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + P_BAR);
@@ -69,6 +78,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __
 
     if (threadIdx.x == 0) {
         tma_prefetch_desc(&tm);
+        if (TSO) tma_prefetch_desc(&tmo);
         for (int s = 0; s < 2; ++s) {
             mbar_init(&kv_full[s], 1);
             mbar_init(&kv_empty[s], prefix > 0 ? 3 : 2);   // two MMA chains (+ the cls warp)
@@ -259,6 +269,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __
             const uint32_t ph = it & 1;
             // scores against the prefix keys (CUDA cores): q row from smem, k rows from global
             float s_pre[ATT_MAX_PREFIX];
+            if constexpr (TSO) {  // the job's prefix key / value rows (one 128-byte line each) into L1 before anybody needs them
+                if (lane < 2 * prefix)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(p.qkv + (seq_row0 + (lane >> 1)) * 3 * D + (1 + (lane & 1)) * D + h * 64));
+            }
             mbar_wait(q_full, ph);
             if (prefix > 0) {
                 float qf[64];
@@ -331,6 +345,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __
                 float l0 = 0.f, l1 = 0.f;
                 uint32_t cur[32], nxt[32];
                 tmem_ld_32x32(trow, cur);
+                if constexpr (TSO) {  // the previous job's O tile (TMA store out of this warp's rows of the P buffer) has been read
+                    if (lane == 0) bulk_wait_read0();
+                    __syncwarp();
+                }
                 tmem_ld_wait();
                 // half 0: straight into the P buffer (free: the previous job's P.V of this tile completed before s_full)
 #pragma unroll
@@ -461,7 +479,26 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __
                     }
                 }
             }
-            if (row_valid) {
+            if constexpr (TSO) {
+                // every row of a FULL tile is valid.  The P buffer is idle (its last P.V has completed): my row goes into the
+                // same swizzled 128-byte line layout the tensor map expects; lane 0 stores the warp's 32 rows
+                const float inv = 1.f / l;
+                uint8_t* ob = pbuf + (uint32_t)r * 128u;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    uint4 x;
+                    x.x = pack_bf16x2(o[c * 8] * inv, o[c * 8 + 1] * inv), x.y = pack_bf16x2(o[c * 8 + 2] * inv, o[c * 8 + 3] * inv);
+                    x.z = pack_bf16x2(o[c * 8 + 4] * inv, o[c * 8 + 5] * inv), x.w = pack_bf16x2(o[c * 8 + 6] * inv, o[c * 8 + 7] * inv);
+                    *reinterpret_cast<uint4*>(ob + ((c ^ (r & 7)) << 4)) = x;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmo, pbuf + q4 * 4096, h * 64, (int)(seq_row0 + prefix) + 128 * w + q4 * 32);
+                    bulk_commit();
+                }
+                if (p.lse) p.lse[((long)b * H + h) * T + qtok] = m * p.scale + logf(l);
+            } else if (row_valid) {
                 const float inv = 1.f / l;
                 __nv_bfloat16* op = p.out + (seq_row0 + qtok) * D + h * 64;
 #pragma unroll
@@ -476,6 +513,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) attn_fwd_pipe_kernel(const __
         }
     }
 
+    if (TSO && warp >= 4 && lane == 0) bulk_wait0();  // this warp's last O store has left shared memory and is complete
     tc_fence_before();
     __syncthreads();
     if (warp == 1) {
@@ -490,16 +528,28 @@ int attn_fwd_pipe_launch(const CUtensorMap& tm, const AttnDev& p, cudaStream_t s
                   "attention_fwd(pipe): needs 128 < HW <= 256, HW %% 8 == 0, no causal mask");
     static bool configured = false;
     if (!configured) {
-        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM));
-        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM));
+        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM));
+        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM));
+        VTP_CUDA(cudaFuncSetAttribute(attn_fwd_pipe_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, PIPE_SMEM));
         configured = true;
     }
     const int njobs = p.B * p.H;
     const int grid = njobs < num_sms() ? njobs : num_sms();
-    if (p.HW == 256 && getenv("VTP_ATTN_PIPE_GENERIC") == nullptr)
-        attn_fwd_pipe_kernel<true><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(tm, p);
-    else
-        attn_fwd_pipe_kernel<false><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(tm, p);
+    if (p.HW == 256 && getenv("VTP_ATTN_PIPE_GENERIC") == nullptr) {
+        const char* ts = getenv("VTP_ATTN_PIPE_TSO");
+        if (ts ? ts[0] != '0' : VTP_ATTN_TSO_DEFAULT) {
+            CUtensorMap tmo;  // out [B*T][D] bf16: 32-row x 64-column boxes (one head, one warp's rows)
+            uint64_t dims[2] = {(uint64_t)p.D, (uint64_t)p.B * p.T}, strides[1] = {(uint64_t)p.D * 2};
+            uint32_t box[2] = {64, 32};
+            int rc = make_tmap_bf16(&tmo, p.out, 2, dims, strides, box);
+            if (rc) return rc;
+            attn_fwd_pipe_kernel<true, true><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(tm, tmo, p);
+        } else {
+            attn_fwd_pipe_kernel<true, false><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(tm, tm, p);
+        }
+    } else {
+        attn_fwd_pipe_kernel<false, false><<<grid, PIPE_THREADS, PIPE_SMEM, st>>>(tm, tm, p);
+    }
     VTP_LAUNCH_CHECK();
     return VTP_OK;
 }

@@ -25,7 +25,7 @@ static constexpr int BRES_KB = 9;                    // resident k-blocks of the
 static constexpr int HALO_W = 16, HALO_H = 18;       // halo block of the BRES == 2 form: 18 rows of 16 pixels (tile 16 x 8)
 static constexpr int HALO_BYTES = HALO_W * HALO_H * BK * 2;
 #ifndef VTP_CONV_HALO_DEFAULT
-#define VTP_CONV_HALO_DEFAULT 0  // two-ring halo form for the other conv shapes with tiles <= 128 wide (decided by measurement)
+#define VTP_CONV_HALO_DEFAULT 1  // two-ring halo form for the other conv shapes with tiles <= 128 wide (measured: VGG per step 31.1 -> 29.1 ms)
 #endif
 #ifndef VTP_CONV_BRES_DEFAULT
 #define VTP_CONV_BRES_DEFAULT 2  // measured (profiles/r2_conv_halo.md): conv1_2 603 -> 357 (1) -> 205 us (2); 0 = off
