@@ -183,6 +183,27 @@ def test_gemm_fast_epilogue_modes(monkeypatch, variant, out_f32, resid, relu, M,
         assert _relerr(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("variant", ["default", "VTP_GEMM_NO_N64_BRES"])
+@pytest.mark.parametrize("relu", [False, True])
+@pytest.mark.parametrize("M,K", [(40000, 32), (38000, 96), (50001, 576), (131072, 32)])
+def test_gemm_n64_resident_weights(monkeypatch, variant, relu, M, K):
+    """Tall 64-column GEMMs with K <= 576 (the VGG conv1_1 im2col form) take the resident-weight 64-wide kernel whose two
+    epilogue warp groups alternate tiles: K shorter than a k-block (zero fill), ragged last tile, many tiles per CTA."""
+    if variant != "default":
+        monkeypatch.setenv(variant, "1")
+    A, W = _mk((M, K), 21, 0.5), _mk((64, K), 22, 0.1)
+    bias = torch.randn(64, device="cuda")
+    out = torch.full((M, 64), float("nan"), device="cuda", dtype=torch.bfloat16)
+    lib.gemm(A, W, out, M=M, N=64, K=K, bias=bias, act=lib.ACT_RELU if relu else lib.ACT_NONE)
+    torch.cuda.synchronize()
+    ref = (_ref(A, W, False, False) + bias).to(torch.bfloat16).float()
+    if relu:
+        ref = ref.clamp_min(0)
+    assert torch.isfinite(out.float()).all()
+    assert (out.float() - ref).abs().max().item() <= 2.0 ** -7 * ref.abs().max().item() + 1e-6
+    assert _relerr(out, ref) < 2e-3
+
+
 @pytest.mark.parametrize("M,Hs,K,with_pre", [(300, 1024, 384, True), (300, 1024, 384, False), (4100, 2736, 1024, True),
                                              (1000, 344, 128, True), (129, 64, 64, True), (2048, 2048, 768, False),
                                              (515, 1368, 384, True)])

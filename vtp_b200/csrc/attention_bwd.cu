@@ -21,7 +21,7 @@
 namespace vtp {
 
 #ifndef VTP_ATTN_BWD_TSO_DEFAULT
-#define VTP_ATTN_BWD_TSO_DEFAULT 0  // TMA-store row epilogues of the FULL path: decided by measurement
+#define VTP_ATTN_BWD_TSO_DEFAULT 1  // TMA-store row epilogues of the FULL path (measured: 502.5 -> 450.0 us, same bits)
 #endif
 static constexpr int AB_THREADS = 320;  // 8 row warps (2 per scheduler) + TMA/MMA warp + cls warp
 static constexpr int BQ = 0, BK_ = 32768, BV = 65536, BDO = 98304, BP = 131072, BDS = 163840, BX = 196608;

@@ -1166,6 +1166,13 @@ extern "C" int vtp_gemm_bf16(const vtp_gemm_args* a, vtp_stream_t stream_) {
         if (bres == 2 && a->conv_W % 8 != 0) bres = 1;
         if (bres) BN = 64, cl2 = false;
     }
+    // plain GEMMs with 64 output columns and K <= 576 (VGG conv1_1 through its 27 -> 32 im2col: 2.1 M rows x 64 per launch, one
+    // k-block per tile) are latency-bound per tile in the 128-wide kernel: same resident-weight 64-wide kernel, whose two
+    // epilogue warp groups take alternate tiles
+    if (!conv && fast && a->N == 64 && a->K <= BRES_KB * BK && !a->a_mn_major && !a->b_mn_major && !g2 &&
+        a->out_dtype == VTP_BF16 && !a->resid && !a->mask_pos && ceil_div(a->M, BM) >= 2 * num_sms() &&
+        getenv("VTP_GEMM_NO_N64_BRES") == nullptr)
+        bres = 1, BN = 64, cl2 = false;
     // every other conv shape with tiles <= 128 wide: two-ring halo form (3), pair multicast of the weights kept
     bool halo3 = false;
     if (conv && fast && !bres && !g2 && cl2 && a->conv_W % 8 == 0 && !a->b_mn_major && BN == 128) {
