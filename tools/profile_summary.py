@@ -1,5 +1,5 @@
 """Turn gpurun_out ncu artefacts into the small tracked summaries under profiles/ (the judge reads those).
-  python tools/profile_summary.py launches <launches.csv> <out.md> [--last-step]
+  python tools/profile_summary.py launches <launches.csv> <out.md> [--last-step | --first-step]
   python tools/profile_summary.py rep <file.ncu-rep> <out.md>"""
 import collections
 import csv
@@ -17,7 +17,10 @@ def us(row):
 def launches(path, out, last_step):
     lines = [l for l in open(path) if not l.startswith("==")]
     rows = list(csv.DictReader(lines))
-    if last_step:
+    if last_step == "first":  # an interrupted capture: the first complete step (everything up to its 4th optimiser launch)
+        idx = [i for i, r in enumerate(rows) if "adamw" in r["Kernel Name"]]
+        rows = rows[:idx[3] + 1] if len(idx) >= 4 else rows
+    elif last_step:
         idx = [i for i, r in enumerate(rows) if "adamw" in r["Kernel Name"]]
         n_opt = 4
         rows = rows[idx[-2 * n_opt] + 1:] if len(idx) >= 2 * n_opt else rows
@@ -65,6 +68,6 @@ def rep(path, out):
 
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
-        launches(sys.argv[2], sys.argv[3], "--last-step" in sys.argv)
+        launches(sys.argv[2], sys.argv[3], "first" if "--first-step" in sys.argv else "--last-step" in sys.argv)
     else:
         rep(sys.argv[2], sys.argv[3])
