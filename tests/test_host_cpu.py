@@ -233,3 +233,33 @@ def test_crop_box_sampling_follows_torchvision_get_params():
     # an image so elongated that no ratio in [3/4, 4/3] fits at this scale: centre-crop fallback, clipped to the ratio range
     fb = random_resized_crop_boxes(np.random.default_rng(1), 10, 100, 1000, (0.9, 1.0))
     assert (fb[:, 3] == 100).all() and (np.abs(fb[:, 2] / fb[:, 3] - 4 / 3) < 0.02).all()
+
+
+def test_tokenizer_img_transform_matches_torchvision_pipeline():
+    """`VTP_Tokenizer.img_transform` (one callable) == the torchvision pipeline the reference composes
+    (generation/tokenizer/vtp_tokenizer.py:75-82): same crop, same flips under the same seed, same normalisation."""
+    np = pytest.importorskip("numpy")
+    tvt = pytest.importorskip("torchvision.transforms")
+    from PIL import Image
+
+    from vtp_b200.generation import VTP_Tokenizer
+    from vtp_b200.image_utils import center_crop_arr
+
+    tok = VTP_Tokenizer.__new__(VTP_Tokenizer)   # no model / GPU needed for the host-side transform
+    tok.img_size = 64
+    for kind in ("imagenet", "half"):
+        tok._setup_normalization(kind)
+        assert tok.inv_mean == [-m / s for m, s in zip(tok.norm_mean, tok.norm_std)]
+        ref = tvt.Compose([tvt.Lambda(lambda im: center_crop_arr(im, 64)), tvt.RandomHorizontalFlip(p=0.5), tvt.ToTensor(),
+                           tvt.Normalize(mean=tok.norm_mean, std=tok.norm_std, inplace=True)])
+        ours = tok.img_transform(0.5)
+        rng = np.random.RandomState(0)
+        for i in range(6):
+            img = Image.fromarray((rng.rand(90 + 7 * i, 140 - 5 * i, 3) * 255).astype("uint8"))
+            torch.manual_seed(i)
+            a = ours(img)
+            torch.manual_seed(i)
+            b = ref(img)
+            assert torch.equal(a, b)
+    with pytest.raises(ValueError):
+        tok._setup_normalization("other")

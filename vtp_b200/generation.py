@@ -53,17 +53,15 @@ class VTP_Tokenizer:
         self._div = torch.tensor(self.inv_std, dtype=torch.float32, device=dev)
 
     def _setup_normalization(self, normalize_type: str):
-        """vtp_tokenizer.py:56-73: x_orig = x_norm * std + mean expressed as Normalize(-mean/std, 1/std)."""
-        if normalize_type == "half":
-            norm_cfg = NORMALIZE_HALF
-        elif normalize_type == "imagenet":
-            norm_cfg = NORMALIZE_IMAGENET
-        else:
+        """Same attributes as vtp_tokenizer.py:56-73 (norm_mean / norm_std and the inverse pair used by `transform_inv`):
+        de-normalisation x * std + mean is kept in the `Normalize(-mean / std, 1 / std)` form the reference uses, so that
+        the fused uint8 kernel reproduces its arithmetic bit for bit."""
+        table = {"half": NORMALIZE_HALF, "imagenet": NORMALIZE_IMAGENET}
+        if normalize_type not in table:
             raise ValueError(f"Unknown normalize_type: {normalize_type}. Use 'half' or 'imagenet'.")
-        self.norm_mean = norm_cfg["mean"]
-        self.norm_std = norm_cfg["std"]
-        self.inv_mean = [-m / s for m, s in zip(self.norm_mean, self.norm_std)]
-        self.inv_std = [1.0 / s for s in self.norm_std]
+        self.norm_mean, self.norm_std = list(table[normalize_type]["mean"]), list(table[normalize_type]["std"])
+        pairs = list(zip(self.norm_mean, self.norm_std))
+        self.inv_mean, self.inv_std = [-m / s for m, s in pairs], [1.0 / s for _, s in pairs]
 
     def transform_inv(self, x: torch.Tensor) -> torch.Tensor:
         """torchvision Normalize(inv_mean, inv_std) on a [B,3,H,W] tensor (plain torch; for callers that want floats)."""
@@ -72,18 +70,23 @@ class VTP_Tokenizer:
         return (x - sub) / div
 
     def img_transform(self, p_hflip: float = 0, img_size: Optional[int] = None):
-        """vtp_tokenizer.py:75-82 (torchvision pipeline on PIL images; host-side data loading, unchanged)."""
-        from torchvision import transforms
+        """Host-side image loading for the extraction loop: ADM centre crop -> random horizontal flip -> float tensor ->
+        normalise, i.e. what vtp_tokenizer.py:75-82 composes out of torchvision transforms, as one callable (the flip draws
+        `torch.rand(1)` exactly once per image, like `RandomHorizontalFlip`, so a seeded run sees the same flips)."""
+        from torchvision.transforms import functional as TF
 
         from .image_utils import center_crop_arr
 
-        img_size = img_size if img_size is not None else self.img_size
-        return transforms.Compose([
-            transforms.Lambda(lambda pil_image: center_crop_arr(pil_image, img_size)),
-            transforms.RandomHorizontalFlip(p=p_hflip),
-            transforms.ToTensor(),
-            transforms.Normalize(mean=self.norm_mean, std=self.norm_std, inplace=True),
-        ])
+        size = self.img_size if img_size is None else img_size
+        mean, std = self.norm_mean, self.norm_std
+
+        def load(pil_image):
+            img = center_crop_arr(pil_image, size)
+            if bool(torch.rand(1) < p_hflip):
+                img = TF.hflip(img)
+            return TF.normalize(TF.to_tensor(img), mean, std, inplace=True)
+
+        return load
 
     # ------------------------------------------------------------------ encode / decode (vtp_tokenizer.py:84-119)
     def encode_images_device(self, images: torch.Tensor) -> torch.Tensor:
