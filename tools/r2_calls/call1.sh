@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 first hardware pass (1 GPU): every gated case, the never-run model sizes, the opt-in kernel variants.
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 run() { local name="$1" t="$2"; shift 2; echo "=== $name (timeout ${t}s)"; local t0=$SECONDS
     timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1; local rc=$?

@@ -1,7 +1,7 @@
 #!/bin/bash
 # BASELINE configs[2]: VTP-Base full step, batch 1024 over 4 GPUs (256/GPU), contrastive feature all-gather across 4
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 run() { local name="$1" t="$2"; shift 2; echo "=== $name (timeout ${t}s)"; local t0=$SECONDS
     timeout -k 5 "$t" "$@" > "gpurun_out/$name.log" 2>&1; local rc=$?

@@ -1,7 +1,7 @@
 #!/bin/bash
 # BASELINE configs[3]: VTP-Large full step bf16, batch 2048 over 8 GPUs (256/GPU), gradient all-reduce over NVLink; + Small at N=8
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 run() { local name="$1" t="$2"; shift 2; echo "=== $name (timeout ${t}s)"; local t0=$SECONDS
     timeout -k 5 "$t" "$@" > "gpurun_out/$name.log" 2>&1; local rc=$?

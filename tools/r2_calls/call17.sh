@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:gemm_kernel -o gpurun_out/conv1_r2 -f python tools/lpips_conv1_once.py > gpurun_out/ncu_conv1.log 2>&1
 tail -3 gpurun_out/ncu_conv1.log

@@ -1,6 +1,6 @@
 #!/bin/bash
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 echo "== lpips tests"; timeout 200 python -m pytest -q -m gpu -p no:cacheprovider -x tests/test_lpips_gpu.py 2>&1 | tail -2
 echo "== layers"; timeout 100 python tools/lpips_layers_bench.py 2>&1 | tail -15

@@ -1,7 +1,7 @@
 #!/bin/bash
 # 2-GPU call: distributed tests + N=2 bench (graph / eager / peer-memory exchange)
 set -u
-cd "$(dirname "$0")/.."
+cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
 run() { local name="$1" t="$2"; shift 2; echo "=== $name (timeout ${t}s)"; local t0=$SECONDS
     timeout "$t" "$@" > "gpurun_out/$name.log" 2>&1; local rc=$?
