@@ -263,3 +263,22 @@ def test_tokenizer_img_transform_matches_torchvision_pipeline():
             assert torch.equal(a, b)
     with pytest.raises(ValueError):
         tok._setup_normalization("other")
+
+
+def test_every_env_switch_is_documented():
+    """Every `VTP_*` environment variable the library, bench.py or the entry points read is listed in INTEGRATION.md §4."""
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pat = re.compile(r'getenv\("(VTP_[A-Z0-9_]+)"\)|environ(?:\.get)?[\(\[]\s*"(VTP_[A-Z0-9_]+)"')
+    names = set()
+    srcs = [os.path.join(root, "bench.py"), os.path.join(root, "__graft_entry__.py")]
+    for d, _, files in os.walk(os.path.join(root, "vtp_b200")):
+        srcs += [os.path.join(d, f) for f in files if f.endswith((".cu", ".cuh", ".h", ".py"))]
+    for path in srcs:
+        for m in pat.finditer(open(path, encoding="utf-8", errors="ignore").read()):
+            names.add(m.group(1) or m.group(2))
+    assert len(names) > 20
+    doc = open(os.path.join(root, "INTEGRATION.md"), encoding="utf-8").read()
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
