@@ -69,7 +69,8 @@ def ibot_masks(n_images: int, HW: int, mask_ratio: float, mask_prob: float, devi
 class TrainBatchPipeline:
     """uint8 source images (+ captions) -> the device batch dict of `VTPTrainer.train_step`, one step ahead.
 
-        pipe = TrainBatchPipeline("cuda", tokenizer=get_tokenizer())      # any callable: list[str] -> int64 [B, 77]
+        from vtp_b200.text_tokenizer import get_tokenizer              # the reference's BPE, same ids (or any callable
+        pipe = TrainBatchPipeline("cuda", tokenizer=get_tokenizer())      #   list[str] -> int64 [B, 77])
         pipe.submit(images_u8, captions)            # images: uint8 [B, H, W, 3] (pinned host or device)
         for ...:
             batch = pipe.get(); pipe.submit(next_images, next_captions)   # prepared under the step that follows
